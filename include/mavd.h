@@ -1,0 +1,194 @@
+/*
+ * mavd.h — C ABI of the B200-native mav-detection hot path (libmavd.so).
+ *
+ * The reference (evroon/mav-detection) has no FFI layer: its boundary is a set of Python call
+ * signatures.  Every entry point below names the reference interface it replaces;
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *  - every function returns an int status (MAVD_OK == 0); nothing throws across this boundary;
+ *    mavd_last_error() returns a thread-local message for the last non-zero status
+ *  - pointers prefixed d_ are DEVICE pointers, h_ are HOST pointers
+ *  - all device entry points are stream-ordered and never retain caller pointers past the call
+ *  - frames are dense row-major (H, W) uint8; flow is dense (H, W, 2) float32, x displacement first
+ *    (the layout cv2.calcOpticalFlowFarneback / Dataset.get_flow_uv return)
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    MAVD_ERR_CUDA
+ */
+#ifndef MAVD_H_
+#define MAVD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAVD_ABI_VERSION 1
+
+enum {
+    MAVD_OK = 0,
+    MAVD_ERR_INVALID = 1,      /* bad shape / parameter / null pointer  -> ValueError   */
+    MAVD_ERR_CUDA = 2,         /* CUDA runtime failure                  -> RuntimeError */
+    MAVD_ERR_UNSUPPORTED = 3,  /* parameter outside the supported range -> ValueError   */
+    MAVD_ERR_NOMEM = 4         /* device allocation failed              -> MemoryError  */
+};
+
+/* cv2 flag values accepted in mavd_farneback_params.flags */
+#define MAVD_FARNEBACK_GAUSSIAN 256 /* cv2.OPTFLOW_FARNEBACK_GAUSSIAN */
+
+#define MAVD_N_SAMPLE_PAIRS 1000  /* focus_of_expansion.py:65 (N) */
+#define MAVD_SAMPLES_PER_FRAME (4 * MAVD_N_SAMPLE_PAIRS) /* 2000 row draws then 2000 column draws */
+#define MAVD_MAX_BOXES 32         /* component boxes kept per frame record */
+
+/* Arguments of cv2.calcOpticalFlowFarneback as called at src/farneback.py:76-80. */
+typedef struct mavd_farneback_params {
+    double pyr_scale;   /* < 1 */
+    int32_t levels;     /* N -> up to N+1 pyramid images, capped at 32 px */
+    int32_t winsize;    /* 2 <= winsize <= 63 */
+    int32_t iterations; /* >= 1 */
+    int32_t poly_n;     /* 1 <= poly_n <= 8 */
+    double poly_sigma;
+    int32_t flags;      /* 0 or MAVD_FARNEBACK_GAUSSIAN */
+} mavd_farneback_params;
+
+typedef struct mavd_config {
+    int32_t device;     /* CUDA device ordinal */
+    int32_t width;      /* frame width  W */
+    int32_t height;     /* frame height H */
+    int32_t max_pairs;  /* largest batch (frame pairs) one call may carry */
+    mavd_farneback_params farneback;
+} mavd_config;
+
+/* Per-frame IMU input of Detector.derotate (src/detector.py:70-117):
+ * ang = Dataset.get_angular_difference(i-1, i), dt = Dataset.get_delta_time(i).
+ * derotate == 0 reproduces the `current_frame_index < 1` pass-through (flow stays float32). */
+typedef struct mavd_imu {
+    double ang[3];
+    double dt;
+    int32_t derotate;
+    int32_t _pad;
+} mavd_imu;
+
+/* Tunables that are public attributes of FocusOfExpansion (src/focus_of_expansion.py:22-23)
+ * and the hard-coded mask constants of src/processor.py:333-341. */
+typedef struct mavd_detect_params {
+    double magnitude_threshold; /* 2.5  */
+    double ransac_threshold;    /* 30.0 */
+    double dyn_offset;          /* 0.25 */
+    double dyn_base;            /* 0.5  */
+    double dyn_gain;            /* 8.0  */
+    double dyn_min_mag;         /* 0.5  */
+    double fixed_min_mag;       /* 1.0  */
+    double fixed_angle;         /* 15.0 */
+} mavd_detect_params;
+
+/* Integer reductions behind FrameResult (src/frame_result.py:4-17, src/processor.py:343-362). */
+typedef struct mavd_frame_stats {
+    double max_phi;          /* FocusOfExpansion.max_flow (focus_of_expansion.py:179) */
+    int64_t n_total;         /* pixels set in total_mask      */
+    int64_t n_fixed;         /* pixels set in estimate_fixed  */
+    int64_t positives;       /* calculate_tpr_fpr: sum(gt > 127)            (im_helpers.py:245) */
+    int64_t negatives;       /* sum(255 - gt > 127)                           (im_helpers.py:246) */
+    int64_t tp_total, fp_total; /* against 255*total_mask                     (processor.py:351) */
+    int64_t tp_fixed, fp_fixed; /* against 255*estimate_fixed                 (processor.py:350) */
+    int32_t seg_bbox[4];     /* get_simple_bounding_box(segmentation): x0,y0,x1,y1 or -1 (im_helpers.py:55-84) */
+    double seg_flow_sum[2];  /* sum of derotated flow over segmentation > 127 (processor.py:343) */
+} mavd_frame_stats;
+
+typedef struct mavd_frame_record {
+    double foe[2];            /* FrameResult.foe_dense */
+    int32_t n_intersections;  /* K of focus_of_expansion.py:85 */
+    int32_t n_labels;         /* components of estimate_fixed (may exceed MAVD_MAX_BOXES) */
+    mavd_frame_stats stats;
+    int32_t boxes[MAVD_MAX_BOXES][5]; /* left, top, width, height, area; raster first-appearance order */
+} mavd_frame_record;
+
+typedef struct mavd_handle_s* mavd_handle;
+
+/* ---- library ---- */
+int mavd_abi_version(void);
+const char* mavd_last_error(void);
+void mavd_default_detect_params(mavd_detect_params* out);
+
+/* ---- lifecycle: one handle per (device, W, H, Farneback parameters).  Owns all workspace. ---- */
+int mavd_create(const mavd_config* cfg, mavd_handle* out);
+int mavd_destroy(mavd_handle h);
+int mavd_workspace_bytes(mavd_handle h, size_t* out);
+/* Pyramid geometry actually used: n_images = capped levels + 1; arrays sized >= 16, finest first. */
+int mavd_level_info(mavd_handle h, int32_t* n_images, int32_t* widths, int32_t* heights);
+
+/* ---- stage 0 (next-row f1): cv2.cvtColor(img, COLOR_BGR2GRAY) at src/farneback.py:74 ---- */
+int mavd_bgr2gray(const uint8_t* d_bgr, uint8_t* d_gray, int64_t n_pixels, void* stream);
+
+/* ---- stage 1: cv2.calcOpticalFlowFarneback(prev, next, None, ...) — src/farneback.py:76-80 ----
+ * d_frames holds dense (H, W) uint8 frames; pair p uses frames p*pair_stride and p*pair_stride+1.
+ * pair_stride 1: a sequence of n_pairs+1 frames (each frame's pyramid + polynomial expansion is
+ * computed once and shared by its two pairs); pair_stride 2: n_pairs independent (prev, next) pairs.
+ * d_flow receives n_pairs dense (H, W, 2) float32 fields. */
+int mavd_farneback(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride,
+                   float* d_flow, void* stream);
+
+/* Test tap: copy an internal buffer of the LAST mavd_farneback call out as a dense array.
+ * kind 0: pyramid image (h_l, w_l); 1: polynomial expansion R (h_l, w_l, 5), index = frame;
+ * 2: matrices M after the last update (h_l, w_l, 5), index = pair; 3: level flow (h_l, w_l, 2). */
+int mavd_farneback_tap(mavd_handle h, int32_t kind, int32_t level, int32_t index, float* d_out,
+                       void* stream);
+
+/* ---- stage 1.5: Detector.derotate — src/detector.py:70-117.  d_out is (H, W, 2) float64. ---- */
+int mavd_derotate(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, double* d_out,
+                  void* stream);
+
+/* ---- stage 2: FocusOfExpansion.get_FOE_dense + ransac — src/focus_of_expansion.py:32-86 ----
+ * d_samples: per frame MAVD_SAMPLES_PER_FRAME/2... see layout: [ry(2000) | rx(2000)] int32, the two
+ * np.random.randint draws of focus_of_expansion.py:69-71 made by the host in frame order.
+ * Derotation is applied inline to the sampled vectors.  d_foe: n x 2 float64 (x, y); (0,0) = none. */
+int mavd_foe(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu,
+             const mavd_detect_params* prm, const int32_t* d_samples, double* d_foe,
+             int32_t* d_n_intersections, void* stream);
+
+/* ---- stage 3: FocusOfExpansion.get_phi + mask block — focus_of_expansion.py:150-184,
+ *      processor.py:307,333-341 (+ the reductions of processor.py:343-362 when d_seg is given) ----
+ * d_sky / d_seg: (H, W) uint8 per frame (stride 0 = one image shared by all frames), nullable.
+ * d_phi: nullable; float64 (H, W) per frame when imu.derotate != 0, float32 otherwise (the dtype
+ * the reference returns); the buffer is always n * H * W * 8 bytes, float32 results use the front.
+ * d_total / d_fixed: (H, W) uint8 0/1 masks (total_mask, estimate_fixed); either may be NULL. */
+int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu,
+                        const mavd_detect_params* prm, const double* d_foe,
+                        const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg, int64_t seg_stride,
+                        void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
+                        void* stream);
+
+/* ---- stage 4 (not in the reference): 8-connected components of a mask ----
+ * Labels are numbered 1..n by first appearance in a raster scan (0 = background).
+ * d_boxes: n x max_boxes x 5 int32 [left, top, width, height, area]; d_n_labels: n int32 (true count). */
+int mavd_ccl(mavd_handle h, const uint8_t* d_mask, int32_t n, int32_t* d_labels, int32_t* d_boxes,
+             int32_t max_boxes, int32_t* d_n_labels, void* stream);
+
+/* ---- whole path, device buffers: flow -> derotate -> FoE -> phi/masks -> components ----
+ * Equivalent to one iteration of Processor.run_detection (src/processor.py:305-362) per pair.
+ * d_flow_out / d_fixed_out / d_total_out nullable.  d_records: n_pairs mavd_frame_record. */
+int mavd_process(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride,
+                 const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* d_samples,
+                 const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg, int64_t seg_stride,
+                 float* d_flow_out, uint8_t* d_total_out, uint8_t* d_fixed_out,
+                 mavd_frame_record* d_records, void* stream);
+
+/* ---- whole path, HOST buffers (the end-to-end call): copies frames/samples/sky/seg in, runs
+ * mavd_process, copies the records (and, when non-NULL, estimate_fixed masks and flow) back.
+ * Host buffers should be pinned for the copies to be asynchronous; the call returns after the
+ * results have landed (it synchronises `stream`). */
+int mavd_process_host(mavd_handle h, const uint8_t* h_frames, int32_t n_pairs, int32_t pair_stride,
+                      const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
+                      const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
+                      float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream);
+
+/* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
+int64_t mavd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAVD_H_ */

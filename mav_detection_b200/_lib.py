@@ -1,0 +1,111 @@
+"""ctypes binding of libmavd.so (include/mavd.h).  There is no CPU fallback: if the CUDA library
+has not been built, importing a compute entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libmavd.so')
+
+MAVD_OK, MAVD_ERR_INVALID, MAVD_ERR_CUDA, MAVD_ERR_UNSUPPORTED, MAVD_ERR_NOMEM = 0, 1, 2, 3, 4
+N_SAMPLE_PAIRS = 1000
+SAMPLES_PER_FRAME = 4 * N_SAMPLE_PAIRS
+MAX_BOXES = 32
+OPTFLOW_FARNEBACK_GAUSSIAN = 256
+
+
+class FarnebackParams(C.Structure):
+    _fields_ = [('pyr_scale', C.c_double), ('levels', C.c_int32), ('winsize', C.c_int32),
+                ('iterations', C.c_int32), ('poly_n', C.c_int32), ('poly_sigma', C.c_double),
+                ('flags', C.c_int32)]
+
+
+class Config(C.Structure):
+    _fields_ = [('device', C.c_int32), ('width', C.c_int32), ('height', C.c_int32),
+                ('max_pairs', C.c_int32), ('farneback', FarnebackParams)]
+
+
+class Imu(C.Structure):
+    _fields_ = [('ang', C.c_double * 3), ('dt', C.c_double), ('derotate', C.c_int32), ('_pad', C.c_int32)]
+
+
+class DetectParams(C.Structure):
+    _fields_ = [('magnitude_threshold', C.c_double), ('ransac_threshold', C.c_double),
+                ('dyn_offset', C.c_double), ('dyn_base', C.c_double), ('dyn_gain', C.c_double),
+                ('dyn_min_mag', C.c_double), ('fixed_min_mag', C.c_double), ('fixed_angle', C.c_double)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [('max_phi', C.c_double), ('n_total', C.c_int64), ('n_fixed', C.c_int64),
+                ('positives', C.c_int64), ('negatives', C.c_int64), ('tp_total', C.c_int64),
+                ('fp_total', C.c_int64), ('tp_fixed', C.c_int64), ('fp_fixed', C.c_int64),
+                ('seg_bbox', C.c_int32 * 4), ('seg_flow_sum', C.c_double * 2)]
+
+
+class FrameRecord(C.Structure):
+    _fields_ = [('foe', C.c_double * 2), ('n_intersections', C.c_int32), ('n_labels', C.c_int32),
+                ('stats', FrameStats), ('boxes', (C.c_int32 * 5) * MAX_BOXES)]
+
+
+# every symbol include/mavd.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SIGNATURES = {
+    'mavd_abi_version': (C.c_int, []),
+    'mavd_last_error': (C.c_char_p, []),
+    'mavd_default_detect_params': (None, [C.POINTER(DetectParams)]),
+    'mavd_create': (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    'mavd_destroy': (C.c_int, [_P]),
+    'mavd_workspace_bytes': (C.c_int, [_P, C.POINTER(C.c_size_t)]),
+    'mavd_level_info': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'mavd_bgr2gray': (C.c_int, [_P, _P, C.c_int64, _P]),
+    'mavd_farneback': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    'mavd_farneback_tap': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    'mavd_derotate': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), _P, _P]),
+    'mavd_foe': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P, _P, _P, _P]),
+    'mavd_residual_masks': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
+                                      _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    'mavd_ccl': (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P]),
+    'mavd_process': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
+                               _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    'mavd_process_host': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
+                                    _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
+    'mavd_launch_count': (C.c_int64, []),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class MavdError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libmavd.so.  Raises (never falls back) when the extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MavdError('libmavd.so is not built (%s). Run `python -c "import __graft_entry__ as g; g.build()"` '
+                        'from the repository root; there is no CPU fallback.' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    assert lib.mavd_abi_version() == 1
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    """Map the C status to the exception type the reference would raise (errors)."""
+    if status == MAVD_OK:
+        return
+    msg = load().mavd_last_error().decode('utf-8', 'replace')
+    if status in (MAVD_ERR_INVALID, MAVD_ERR_UNSUPPORTED):
+        raise ValueError(msg)
+    if status == MAVD_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise MavdError(msg)

@@ -1,0 +1,509 @@
+// C ABI of libmavd (include/mavd.h): handle lifecycle, parameter tables, stage entry points and the
+// whole-path calls.  No exceptions cross this boundary; every failure is an int status plus a
+// thread-local message.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mavd {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline int cv_round(double v) { return (int)nearbyint(v); }  // round-half-even, like cvRound
+
+// cv::resize(INTER_LINEAR) source index / weight per destination index (pixel-centre mapping).
+static void resize_tables(int src, int dst, std::vector<int>& i0, std::vector<float>& a) {
+    i0.resize(dst);
+    a.resize(dst);
+    const double inv_scale = (double)dst / src;
+    const double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        float w = f - (float)s;
+        if (s < 0) { s = 0; w = 0.f; }
+        if (s >= src - 1) { s = src - 1; w = 0.f; }
+        i0[d] = s;
+        a[d] = w;
+    }
+}
+
+// cv::getGaussianKernel(ksz, sigma, CV_32F)
+static std::vector<float> gaussian_kernel(int ksz, double sigma) {
+    std::vector<float> k(ksz);
+    if (sigma <= 0 && ksz == 3) { k[0] = 0.25f; k[1] = 0.5f; k[2] = 0.25f; return k; }
+    if (sigma <= 0) sigma = ((ksz - 1) * 0.5 - 1) * 0.3 + 0.8;
+    std::vector<double> t(ksz);
+    double sum = 0;
+    for (int i = 0; i < ksz; ++i) {
+        double x = i - (ksz - 1) * 0.5;
+        t[i] = exp(-0.5 * x * x / (sigma * sigma));
+        sum += t[i];
+    }
+    for (int i = 0; i < ksz; ++i) k[i] = (float)(t[i] / sum);
+    return k;
+}
+
+// FarnebackPrepareGaussian: taps and the four needed entries of inv(G) (Appendix A of SURVEY.md).
+static int poly_setup(int n, double sigma, PolyConst& pc) {
+    if (sigma < 1.1920929e-07) sigma = n * 0.3;
+    float g[2 * kMaxPolyN + 1], xg[2 * kMaxPolyN + 1], xxg[2 * kMaxPolyN + 1];
+    double s = 0;
+    for (int x = -n; x <= n; ++x) {
+        g[x + n] = (float)exp(-x * x / (2 * sigma * sigma));
+        s += g[x + n];
+    }
+    s = 1. / s;
+    for (int x = -n; x <= n; ++x) {
+        g[x + n] = (float)(g[x + n] * s);
+        xg[x + n] = (float)(x * g[x + n]);
+        xxg[x + n] = (float)(x * x * g[x + n]);
+    }
+    double G[6][6];
+    memset(G, 0, sizeof(G));
+    for (int y = -n; y <= n; ++y)
+        for (int x = -n; x <= n; ++x) {
+            const float gg = g[y + n] * g[x + n];
+            G[0][0] += gg;
+            G[1][1] += gg * x * x;
+            G[3][3] += gg * x * x * x * x;
+            G[5][5] += gg * x * x * y * y;
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    // Gauss-Jordan inverse of the 6x6 (symmetric positive definite) matrix
+    double A[6][12];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 12; ++j) A[i][j] = j < 6 ? G[i][j] : (j - 6 == i ? 1.0 : 0.0);
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r)
+            if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+        if (fabs(A[piv][c]) < 1e-300) return MAVD_ERR_INVALID;
+        if (piv != c)
+            for (int j = 0; j < 12; ++j) { double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+        const double d = A[c][c];
+        for (int j = 0; j < 12; ++j) A[c][j] /= d;
+        for (int r = 0; r < 6; ++r)
+            if (r != c) {
+                const double f = A[r][c];
+                if (f != 0)
+                    for (int j = 0; j < 12; ++j) A[r][j] -= f * A[c][j];
+            }
+    }
+    pc.n = n;
+    for (int k = 0; k <= kMaxPolyN; ++k) {
+        pc.g[k] = k <= n ? g[n + k] : 0.f;
+        pc.xg[k] = k <= n ? xg[n + k] : 0.f;
+        pc.xxg[k] = k <= n ? xxg[n + k] : 0.f;
+    }
+    pc.ig11 = (float)A[1][6 + 1];
+    pc.ig03 = (float)A[0][6 + 3];
+    pc.ig33 = (float)A[3][6 + 3];
+    pc.ig55 = (float)A[5][6 + 5];
+    return MAVD_OK;
+}
+
+struct Arena {
+    std::vector<void*> ptrs;
+    size_t bytes = 0;
+    template <typename T>
+    int alloc(T** out, size_t count) {
+        void* p = nullptr;
+        size_t b = count * sizeof(T);
+        if (b == 0) b = sizeof(T);
+        cudaError_t e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", b, cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? MAVD_ERR_NOMEM : MAVD_ERR_CUDA;
+        }
+        ptrs.push_back(p);
+        bytes += b;
+        *out = (T*)p;
+        return MAVD_OK;
+    }
+    template <typename T>
+    int upload(T** out, const std::vector<T>& v) {
+        int rc = alloc(out, v.size());
+        if (rc != MAVD_OK) return rc;
+        if (!v.empty()) MAVD_CUDA(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return MAVD_OK;
+    }
+};
+
+}  // namespace mavd
+
+using namespace mavd;
+
+struct mavd_handle_full : mavd_handle_s {
+    Arena arena;
+};
+
+#define TRY(x)                       \
+    do {                             \
+        int rc__ = (x);              \
+        if (rc__ != MAVD_OK) return rc__; \
+    } while (0)
+
+extern "C" {
+
+int mavd_abi_version(void) { return MAVD_ABI_VERSION; }
+const char* mavd_last_error(void) { return g_err; }
+int64_t mavd_launch_count(void) { return g_launches.load(); }
+
+void mavd_default_detect_params(mavd_detect_params* p) {
+    if (!p) return;
+    p->magnitude_threshold = 2.5;  // focus_of_expansion.py:22
+    p->ransac_threshold = 30.0;    // focus_of_expansion.py:23
+    p->dyn_offset = 0.25;          // processor.py:334-335
+    p->dyn_base = 0.5;
+    p->dyn_gain = 8.0;
+    p->dyn_min_mag = 0.5;          // processor.py:338
+    p->fixed_min_mag = 1.0;        // processor.py:341
+    p->fixed_angle = 15.0;         // processor.py:340
+}
+
+static int validate(const mavd_config* c) {
+    MAVD_REQUIRE(c != nullptr, MAVD_ERR_INVALID, "config is NULL");
+    const mavd_farneback_params& f = c->farneback;
+    MAVD_REQUIRE(c->width >= 8 && c->height >= 8 && c->width <= 16384 && c->height <= 16384, MAVD_ERR_INVALID,
+                 "frame size %dx%d out of range", c->width, c->height);
+    MAVD_REQUIRE(c->max_pairs >= 1, MAVD_ERR_INVALID, "max_pairs must be >= 1");
+    MAVD_REQUIRE(f.pyr_scale > 0.0 && f.pyr_scale < 1.0, MAVD_ERR_INVALID, "pyr_scale must be in (0, 1)");
+    MAVD_REQUIRE(f.levels >= 0, MAVD_ERR_INVALID, "levels must be >= 0");
+    MAVD_REQUIRE(f.iterations >= 1, MAVD_ERR_UNSUPPORTED, "iterations must be >= 1");
+    MAVD_REQUIRE(f.winsize >= 2 && f.winsize / 2 <= kMaxWinHalf, MAVD_ERR_UNSUPPORTED,
+                 "winsize %d unsupported (2..%d)", f.winsize, 2 * kMaxWinHalf + 1);
+    MAVD_REQUIRE(f.poly_n >= 1 && f.poly_n <= kMaxPolyN, MAVD_ERR_UNSUPPORTED, "poly_n %d unsupported (1..%d)",
+                 f.poly_n, kMaxPolyN);
+    MAVD_REQUIRE((f.flags & ~MAVD_FARNEBACK_GAUSSIAN) == 0, MAVD_ERR_UNSUPPORTED,
+                 "flags 0x%x unsupported (only OPTFLOW_FARNEBACK_GAUSSIAN)", f.flags);
+    return MAVD_OK;
+}
+
+int mavd_create(const mavd_config* cfg, mavd_handle* out) {
+    MAVD_REQUIRE(out != nullptr, MAVD_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    TRY(validate(cfg));
+    int ndev = 0;
+    MAVD_CUDA(cudaGetDeviceCount(&ndev));
+    MAVD_REQUIRE(cfg->device >= 0 && cfg->device < ndev, MAVD_ERR_CUDA, "CUDA device %d not available (%d devices)",
+                 cfg->device, ndev);
+    MAVD_CUDA(cudaSetDevice(cfg->device));
+    mavd_handle_full* H = new (std::nothrow) mavd_handle_full();
+    MAVD_REQUIRE(H != nullptr, MAVD_ERR_NOMEM, "out of host memory");
+    H->cfg = *cfg;
+    const mavd_farneback_params& fp = cfg->farneback;
+    const int W = cfg->width, Hh = cfg->height, B = cfg->max_pairs;
+    const int F = 2 * B;  // worst case: independent pairs
+    H->max_frames = F;
+    Arena& A = H->arena;
+    int rc = MAVD_OK;
+    auto fail = [&](int code) {
+        for (void* p : A.ptrs) cudaFree(p);
+        delete H;
+        return code;
+    };
+#define C_TRY(x) do { rc = (x); if (rc != MAVD_OK) return fail(rc); } while (0)
+
+    // level schedule: levels = N -> up to N+1 images, 32-pixel cap
+    int k = 0;
+    double sc = 1.0;
+    while (k < fp.levels) {
+        sc *= fp.pyr_scale;
+        if (W * sc < 32 || Hh * sc < 32) break;
+        ++k;
+    }
+    if (k + 1 > kMaxLevels) {
+        set_error("too many pyramid levels (%d)", k + 1);
+        return fail(MAVD_ERR_UNSUPPORTED);
+    }
+    H->n_levels = k + 1;
+    for (int li = 0; li < H->n_levels; ++li) {
+        Level& L = H->lv[li];
+        L.k = li;
+        double s = 1.0;
+        for (int i = 0; i < li; ++i) s *= fp.pyr_scale;
+        L.scale = s;
+        const double sigma = (1. / s - 1) * 0.5;
+        L.sigma = (float)sigma;
+        L.ksz = std::max(cv_round(sigma * 5) | 1, 3);
+        L.w = cv_round(W * s);
+        L.h = cv_round(Hh * s);
+        L.pitch = round_up(L.w, 64);
+        L.plane = (size_t)L.pitch * L.h;
+        std::vector<int> i0;
+        std::vector<float> a;
+        resize_tables(W, L.w, i0, a);
+        C_TRY(A.upload(&L.xi0, i0));
+        C_TRY(A.upload(&L.xa, a));
+        resize_tables(Hh, L.h, i0, a);
+        C_TRY(A.upload(&L.yi0, i0));
+        C_TRY(A.upload(&L.ya, a));
+        C_TRY(A.upload(&L.ktab, gaussian_kernel(L.ksz, sigma)));
+        C_TRY(A.alloc(&L.img, (size_t)F * L.plane));
+        C_TRY(A.alloc(&L.R, (size_t)F * 5 * L.plane));
+        C_TRY(A.alloc(&L.M[0], (size_t)B * 5 * L.plane));
+        C_TRY(A.alloc(&L.M[1], (size_t)B * 5 * L.plane));
+        if (li > 0) C_TRY(A.alloc(&L.flow, (size_t)B * 2 * L.plane));
+        // padded columns of R/M are read by vector loads of edge tiles: keep them finite
+        cudaMemset(L.img, 0, (size_t)F * L.plane * sizeof(float));
+        cudaMemset(L.R, 0, (size_t)F * 5 * L.plane * sizeof(float));
+        cudaMemset(L.M[0], 0, (size_t)B * 5 * L.plane * sizeof(float));
+        cudaMemset(L.M[1], 0, (size_t)B * 5 * L.plane * sizeof(float));
+    }
+    for (int li = 0; li + 1 < H->n_levels; ++li) {
+        Level& L = H->lv[li];
+        const Level& C = H->lv[li + 1];
+        std::vector<int> i0;
+        std::vector<float> a;
+        resize_tables(C.w, L.w, i0, a);
+        C_TRY(A.upload(&L.fxi0, i0));
+        C_TRY(A.upload(&L.fxa, a));
+        resize_tables(C.h, L.h, i0, a);
+        C_TRY(A.upload(&L.fyi0, i0));
+        C_TRY(A.upload(&L.fya, a));
+    }
+    H->tmp_frame_stride = (size_t)Hh * H->lv[0].pitch;
+    C_TRY(A.alloc(&H->tmp, (size_t)F * H->tmp_frame_stride));
+    C_TRY(poly_setup(fp.poly_n, fp.poly_sigma, H->poly));
+    {
+        // FarnebackUpdateFlow_GaussianBlur half kernel
+        const int m = fp.winsize / 2;
+        const double sigma = m * 0.3;
+        std::vector<float> kf(m + 1);
+        double s = 0;
+        for (int i = 0; i <= m; ++i) {
+            kf[i] = (float)exp(-i * i / (2 * sigma * sigma));
+            s += (i == 0 ? 1.0 : 2.0) * kf[i];
+        }
+        for (int i = 0; i <= m; ++i) kf[i] = (float)(kf[i] * (1.0 / s));
+        C_TRY(A.upload(&H->gauss_win, kf));
+    }
+    // detection workspace
+    const size_t npx = (size_t)W * Hh;
+    C_TRY(A.alloc(&H->d_imu, B));
+    C_TRY(A.alloc(&H->d_foe, 2 * (size_t)B));
+    C_TRY(A.alloc(&H->d_ninter, B));
+    C_TRY(A.alloc(&H->d_labels, B * npx));
+    C_TRY(A.alloc(&H->d_scan, B * npx + (size_t)B * (npx / 4096 + 2) + 64));
+    C_TRY(A.alloc(&H->d_total, B * npx));
+    C_TRY(A.alloc(&H->d_fixed, B * npx));
+    C_TRY(A.alloc(&H->d_flow, B * npx * 2));
+    C_TRY(A.alloc(&H->d_frames, (size_t)F * npx));
+    C_TRY(A.alloc(&H->d_samples, (size_t)B * MAVD_SAMPLES_PER_FRAME));
+    C_TRY(A.alloc(&H->d_sky, B * npx));
+    C_TRY(A.alloc(&H->d_seg, B * npx));
+    C_TRY(A.alloc(&H->d_records, B));
+    H->bytes = A.bytes;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_error("device error during create: %s", cudaGetErrorString(e));
+        return fail(MAVD_ERR_CUDA);
+    }
+    *out = H;
+    return MAVD_OK;
+#undef C_TRY
+}
+
+int mavd_destroy(mavd_handle h) {
+    if (!h) return MAVD_OK;
+    mavd_handle_full* H = static_cast<mavd_handle_full*>(h);
+    cudaSetDevice(H->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : H->arena.ptrs) cudaFree(p);
+    delete H;
+    return MAVD_OK;
+}
+
+int mavd_workspace_bytes(mavd_handle h, size_t* out) {
+    MAVD_REQUIRE(h && out, MAVD_ERR_INVALID, "NULL argument");
+    *out = h->bytes;
+    return MAVD_OK;
+}
+
+int mavd_level_info(mavd_handle h, int32_t* n_images, int32_t* widths, int32_t* heights) {
+    MAVD_REQUIRE(h && n_images, MAVD_ERR_INVALID, "NULL argument");
+    *n_images = h->n_levels;
+    for (int i = 0; i < h->n_levels; ++i) {
+        if (widths) widths[i] = h->lv[i].w;
+        if (heights) heights[i] = h->lv[i].h;
+    }
+    return MAVD_OK;
+}
+
+int mavd_bgr2gray(const uint8_t* d_bgr, uint8_t* d_gray, int64_t n_pixels, void* stream) {
+    MAVD_REQUIRE(d_bgr && d_gray && n_pixels >= 0, MAVD_ERR_INVALID, "bgr2gray: bad arguments");
+    if (n_pixels == 0) return MAVD_OK;
+    return bgr2gray_run(d_bgr, d_gray, n_pixels, (cudaStream_t)stream);
+}
+
+static int check_batch(mavd_handle h, int n, const char* what) {
+    MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "%s: handle is NULL", what);
+    MAVD_REQUIRE(n >= 0 && n <= h->cfg.max_pairs, MAVD_ERR_INVALID, "%s: batch %d exceeds max_pairs %d", what, n,
+                 h->cfg.max_pairs);
+    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    return MAVD_OK;
+}
+
+int mavd_farneback(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride, float* d_flow,
+                   void* stream) {
+    TRY(check_batch(h, n_pairs, "farneback"));
+    MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
+    if (n_pairs == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_frames && d_flow, MAVD_ERR_INVALID, "farneback: NULL buffer");
+    return farneback_run(h, d_frames, n_pairs, pair_stride, d_flow, (cudaStream_t)stream);
+}
+
+int mavd_farneback_tap(mavd_handle h, int32_t kind, int32_t level, int32_t index, float* d_out, void* stream) {
+    MAVD_REQUIRE(h && d_out, MAVD_ERR_INVALID, "tap: NULL argument");
+    MAVD_REQUIRE(index >= 0 && index < h->max_frames, MAVD_ERR_INVALID, "tap: index out of range");
+    return farneback_tap(h, kind, level, index, d_out, (cudaStream_t)stream);
+}
+
+static int upload_imu(mavd_handle h, const mavd_imu* h_imu, int n, cudaStream_t s, int* n64, int* n32) {
+    MAVD_REQUIRE(h_imu != nullptr, MAVD_ERR_INVALID, "imu array is NULL");
+    int a = 0, b = 0;
+    for (int i = 0; i < n; ++i) {
+        if (h_imu[i].derotate) {
+            MAVD_REQUIRE(h_imu[i].dt != 0.0, MAVD_ERR_INVALID, "imu[%d].dt is zero", i);
+            ++a;
+        } else {
+            ++b;
+        }
+    }
+    if (n64) *n64 = a;
+    if (n32) *n32 = b;
+    MAVD_CUDA(cudaMemcpyAsync(h->d_imu, h_imu, sizeof(mavd_imu) * n, cudaMemcpyHostToDevice, s));
+    return MAVD_OK;
+}
+
+int mavd_derotate(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, double* d_out, void* stream) {
+    TRY(check_batch(h, n, "derotate"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_flow && d_out, MAVD_ERR_INVALID, "derotate: NULL buffer");
+    TRY(upload_imu(h, h_imu, n, (cudaStream_t)stream, nullptr, nullptr));
+    return derotate_run(h, d_flow, n, h->d_imu, d_out, (cudaStream_t)stream);
+}
+
+int mavd_foe(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,
+             const int32_t* d_samples, double* d_foe, int32_t* d_n_intersections, void* stream) {
+    TRY(check_batch(h, n, "foe"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_flow && d_samples && d_foe, MAVD_ERR_INVALID, "foe: NULL buffer");
+    mavd_detect_params p;
+    if (prm) p = *prm; else mavd_default_detect_params(&p);
+    TRY(upload_imu(h, h_imu, n, (cudaStream_t)stream, nullptr, nullptr));
+    return foe_run(h, d_flow, n, h->d_imu, p, d_samples, d_foe, d_n_intersections ? d_n_intersections : h->d_ninter,
+                   (cudaStream_t)stream);
+}
+
+int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu,
+                        const mavd_detect_params* prm, const double* d_foe, const uint8_t* d_sky, int64_t sky_stride,
+                        const uint8_t* d_seg, int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed,
+                        mavd_frame_stats* d_stats, void* stream) {
+    TRY(check_batch(h, n, "residual_masks"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_flow && d_foe, MAVD_ERR_INVALID, "residual_masks: NULL buffer");
+    mavd_detect_params p;
+    if (prm) p = *prm; else mavd_default_detect_params(&p);
+    int n64 = 0, n32 = 0;
+    TRY(upload_imu(h, h_imu, n, (cudaStream_t)stream, &n64, &n32));
+    return residual_run(h, d_flow, n, h->d_imu, p, d_foe, d_sky, sky_stride, d_seg, seg_stride, d_phi, d_total, d_fixed,
+                        d_stats, sizeof(mavd_frame_stats), n64 > 0, n32 > 0, (cudaStream_t)stream);
+}
+
+int mavd_ccl(mavd_handle h, const uint8_t* d_mask, int32_t n, int32_t* d_labels, int32_t* d_boxes, int32_t max_boxes,
+             int32_t* d_n_labels, void* stream) {
+    TRY(check_batch(h, n, "ccl"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_mask && d_labels && d_n_labels, MAVD_ERR_INVALID, "ccl: NULL buffer");
+    MAVD_REQUIRE(max_boxes >= 0, MAVD_ERR_INVALID, "ccl: max_boxes < 0");
+    return ccl_run(h, d_mask, n, d_labels, max_boxes > 0 ? d_boxes : nullptr, (size_t)max_boxes * 5, max_boxes,
+                   d_n_labels, sizeof(int32_t), (cudaStream_t)stream);
+}
+
+__global__ void records_fill_kernel(mavd_frame_record* rec, const double* foe, const int32_t* ninter, int n) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    rec[f].foe[0] = foe[2 * f];
+    rec[f].foe[1] = foe[2 * f + 1];
+    rec[f].n_intersections = ninter[f];
+}
+
+int mavd_process(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride, const mavd_imu* h_imu,
+                 const mavd_detect_params* prm, const int32_t* d_samples, const uint8_t* d_sky, int64_t sky_stride,
+                 const uint8_t* d_seg, int64_t seg_stride, float* d_flow_out, uint8_t* d_total_out,
+                 uint8_t* d_fixed_out, mavd_frame_record* d_records, void* stream) {
+    TRY(check_batch(h, n_pairs, "process"));
+    MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
+    if (n_pairs == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_frames && d_samples && d_records, MAVD_ERR_INVALID, "process: NULL buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    mavd_detect_params p;
+    if (prm) p = *prm; else mavd_default_detect_params(&p);
+    float* flow = d_flow_out ? d_flow_out : h->d_flow;
+    uint8_t* fixed = d_fixed_out ? d_fixed_out : h->d_fixed;
+    int n64 = 0, n32 = 0;
+    TRY(upload_imu(h, h_imu, n_pairs, s, &n64, &n32));
+    TRY(farneback_run(h, d_frames, n_pairs, pair_stride, flow, s));
+    TRY(foe_run(h, flow, n_pairs, h->d_imu, p, d_samples, h->d_foe, h->d_ninter, s));
+    char* stats0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, stats);
+    TRY(residual_run(h, flow, n_pairs, h->d_imu, p, h->d_foe, d_sky, sky_stride, d_seg, seg_stride, nullptr,
+                     d_total_out, fixed, reinterpret_cast<mavd_frame_stats*>(stats0), sizeof(mavd_frame_record),
+                     n64 > 0, n32 > 0, s));
+    int32_t* boxes0 = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, boxes));
+    char* nl0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, n_labels);
+    TRY(ccl_run(h, fixed, n_pairs, h->d_labels, boxes0, sizeof(mavd_frame_record) / sizeof(int32_t), MAVD_MAX_BOXES,
+                reinterpret_cast<int32_t*>(nl0), sizeof(mavd_frame_record), s));
+    records_fill_kernel<<<ceil_div(n_pairs, 128), 128, 0, s>>>(d_records, h->d_foe, h->d_ninter, n_pairs);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+int mavd_process_host(mavd_handle h, const uint8_t* h_frames, int32_t n_pairs, int32_t pair_stride,
+                      const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
+                      const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
+                      float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+    TRY(check_batch(h, n_pairs, "process_host"));
+    MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
+    if (n_pairs == 0) return MAVD_OK;
+    MAVD_REQUIRE(h_frames && h_samples && h_records, MAVD_ERR_INVALID, "process_host: NULL buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t npx = (size_t)h->cfg.width * h->cfg.height;
+    const int n_frames = pair_stride == 1 ? n_pairs + 1 : 2 * n_pairs;
+    MAVD_CUDA(cudaMemcpyAsync(h->d_frames, h_frames, npx * n_frames, cudaMemcpyHostToDevice, s));
+    MAVD_CUDA(cudaMemcpyAsync(h->d_samples, h_samples, sizeof(int32_t) * MAVD_SAMPLES_PER_FRAME * n_pairs,
+                              cudaMemcpyHostToDevice, s));
+    if (h_sky)
+        MAVD_CUDA(cudaMemcpyAsync(h->d_sky, h_sky, sky_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, s));
+    if (h_seg)
+        MAVD_CUDA(cudaMemcpyAsync(h->d_seg, h_seg, seg_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, s));
+    MAVD_REQUIRE(sky_stride == 0 || sky_stride == (int64_t)npx, MAVD_ERR_INVALID, "sky_stride must be 0 or H*W");
+    MAVD_REQUIRE(seg_stride == 0 || seg_stride == (int64_t)npx, MAVD_ERR_INVALID, "seg_stride must be 0 or H*W");
+    TRY(mavd_process(h, h->d_frames, n_pairs, pair_stride, h_imu, prm, h->d_samples, h_sky ? h->d_sky : nullptr,
+                     sky_stride, h_seg ? h->d_seg : nullptr, seg_stride, h->d_flow, nullptr, h->d_fixed, h->d_records, s));
+    MAVD_CUDA(cudaMemcpyAsync(h_records, h->d_records, sizeof(mavd_frame_record) * n_pairs, cudaMemcpyDeviceToHost, s));
+    if (h_fixed_out) MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, h->d_fixed, npx * n_pairs, cudaMemcpyDeviceToHost, s));
+    if (h_flow_out)
+        MAVD_CUDA(cudaMemcpyAsync(h_flow_out, h->d_flow, sizeof(float) * 2 * npx * n_pairs, cudaMemcpyDeviceToHost, s));
+    MAVD_CUDA(cudaStreamSynchronize(s));
+    return MAVD_OK;
+}
+
+}  // extern "C"

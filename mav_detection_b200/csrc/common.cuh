@@ -1,0 +1,124 @@
+// Shared helpers for libmavd (sm_100a).  Error reporting never throws across the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "mavd.h"
+
+namespace mavd {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define MAVD_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            ::mavd::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return (e__ == cudaErrorMemoryAllocation) ? MAVD_ERR_NOMEM : MAVD_ERR_CUDA;          \
+        }                                                                                       \
+    } while (0)
+
+// Call after every kernel launch: counts the launch and surfaces configuration errors.
+#define MAVD_LAUNCHED()                                                                         \
+    do {                                                                                        \
+        ::mavd::g_launches.fetch_add(1, std::memory_order_relaxed);                             \
+        MAVD_CUDA(cudaGetLastError());                                                          \
+    } while (0)
+
+#define MAVD_REQUIRE(cond, code, ...)                                                           \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            ::mavd::set_error(__VA_ARGS__);                                                     \
+            return (code);                                                                      \
+        }                                                                                       \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+constexpr int kMaxPolyN = 8;
+constexpr int kMaxLevels = 16;
+constexpr int kMaxWinHalf = 31;
+
+// One pyramid level: geometry, resize/blur tables and per-level buffers (all device memory).
+struct Level {
+    int k = 0;
+    double scale = 1.0;
+    int w = 0, h = 0;
+    int pitch = 0;      // floats per row, multiple of 64 so 64-wide tiles never leave the row
+    size_t plane = 0;   // pitch * h
+    int ksz = 3;
+    float sigma = 0.f;
+    // pyramid tables (full-res -> this level)
+    int* xi0 = nullptr;  float* xa = nullptr;   // [w]
+    int* yi0 = nullptr;  float* ya = nullptr;   // [h]
+    float* ktab = nullptr;                      // [ksz]
+    // flow upsample tables (next-coarser level -> this level)
+    int* fxi0 = nullptr; float* fxa = nullptr;  // [w]
+    int* fyi0 = nullptr; float* fya = nullptr;  // [h]
+    // buffers
+    float* img = nullptr;   // [frames][h][pitch]
+    float* R = nullptr;     // [frames][5][h][pitch]
+    float* M[2] = {nullptr, nullptr};  // [pairs][5][h][pitch]
+    float* flow = nullptr;  // [pairs][h][pitch] float2 (unused for level 0: written to the caller's buffer)
+    int last_m = 0;         // which M buffer holds the last update (for taps)
+};
+
+struct PolyConst {
+    float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
+    float ig11, ig03, ig33, ig55;
+    int n;
+};
+
+}  // namespace mavd
+
+struct mavd_handle_s {
+    mavd_config cfg;
+    int n_levels = 0;               // number of pyramid images
+    mavd::Level lv[mavd::kMaxLevels];  // lv[0] = finest (k = 0)
+    mavd::PolyConst poly;
+    float* gauss_win = nullptr;     // [m+1] device, FarnebackUpdateFlow_GaussianBlur half kernel
+    float* tmp = nullptr;           // [frames][H][pitch_max] horizontal pyramid pass
+    size_t tmp_frame_stride = 0;
+    int max_frames = 0;
+    size_t bytes = 0;
+    // detection workspace
+    mavd_imu* d_imu = nullptr;      // [max_pairs]
+    double* d_foe = nullptr;        // [max_pairs][2]
+    int32_t* d_ninter = nullptr;    // [max_pairs]
+    int32_t* d_labels = nullptr;    // [max_pairs][H][W]
+    int32_t* d_scan = nullptr;      // CCL scratch
+    uint8_t* d_total = nullptr;     // [max_pairs][H][W]
+    uint8_t* d_fixed = nullptr;
+    float* d_flow = nullptr;        // [max_pairs][H][W][2] (when the caller does not want the flow)
+    // host-path staging (device side)
+    uint8_t* d_frames = nullptr;    // [max_frames][H][W]
+    int32_t* d_samples = nullptr;   // [max_pairs][4000]
+    uint8_t* d_sky = nullptr;       // [max_pairs][H][W]
+    uint8_t* d_seg = nullptr;
+    mavd_frame_record* d_records = nullptr;
+    // last call bookkeeping for taps
+    int last_pairs = 0, last_stride = 1;
+    float* last_flow0 = nullptr;
+};
+
+namespace mavd {
+// farneback.cu
+int farneback_run(mavd_handle h, const uint8_t* d_frames, int n_pairs, int pair_stride, float* d_flow,
+                  cudaStream_t s);
+int farneback_tap(mavd_handle h, int kind, int level, int index, float* d_out, cudaStream_t s);
+// detect.cu
+int bgr2gray_run(const uint8_t* d_bgr, uint8_t* d_gray, int64_t n, cudaStream_t s);
+int derotate_run(mavd_handle h, const float* d_flow, int n, const mavd_imu* d_imu, double* d_out, cudaStream_t s);
+int foe_run(mavd_handle h, const float* d_flow, int n, const mavd_imu* d_imu, const mavd_detect_params& prm,
+            const int32_t* d_samples, double* d_foe, int32_t* d_ninter, cudaStream_t s);
+int residual_run(mavd_handle h, const float* d_flow, int n, const mavd_imu* d_imu, const mavd_detect_params& prm,
+                 const double* d_foe, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
+                 int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
+                 size_t stats_stride_bytes, int run_f64, int run_f32, cudaStream_t s);
+int ccl_run(mavd_handle h, const uint8_t* d_mask, int n, int32_t* d_labels, int32_t* d_boxes, size_t boxes_stride,
+            int max_boxes, int32_t* d_n_labels, size_t nlabels_stride_bytes, cudaStream_t s);
+}  // namespace mavd

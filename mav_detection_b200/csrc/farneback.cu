@@ -1,0 +1,621 @@
+// Farneback dense optical flow for sm_100a — the arithmetic of cv2.calcOpticalFlowFarneback as
+// called at /root/reference/src/farneback.py:76-80.
+//
+// HBM layout: every per-level field is PLANAR with a row pitch that is a multiple of 64 floats
+// (256 B): image [frame][h][pitch]; R [frame][5][h][pitch]; M [pair][5][h][pitch] (ping-pong);
+// flow [pair][h][pitch] float2.  64-wide tiles therefore never cross a row end and every tile row is
+// 16-byte aligned (float4 / cp.async / TMA friendly).  Batch elements sit in grid.z.
+//
+// Kernels (algorithmic bytes per level pixel P):
+//   pyr_hpass / pyr_vpass  blur+resize from full-res u8, separable              2*(N0 + 4P)/2 per frame
+//   polyexp_kernel         separable polynomial expansion, smem tile            4P -> 20P
+//   matrices_init_kernel   flow upsample (x 1/pyr_scale) fused with UpdateMatrices   (8P' +) 40P -> 20P
+//   iter_kernel            box/Gaussian blur of M + 2x2 solve + UpdateMatrices   88P (28P for the last)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mavd {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {
+    // BORDER_REFLECT_101:  ... c b | a b c ... y z | y x ...
+    while (i < 0 || i >= n) {
+        if (n == 1) return 0;
+        i = (i < 0) ? -i : 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ------------------------------------------------------------------------------------------------
+// Pyramid: I_l = resize(GaussianBlur(f32(img), ksz, sigma), (w_l, h_l)), always from full resolution.
+// Horizontal blur+resize (u8 -> f32 [H][w_l]) then vertical blur+resize ([H][w_l] -> [h_l][w_l]).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pyr_hpass_kernel(const uint8_t* __restrict__ frames, size_t frame_stride,
+                                                       int W, int H, const int* __restrict__ xi0,
+                                                       const float* __restrict__ xa,
+                                                       const float* __restrict__ ktab, int ksz,
+                                                       float* __restrict__ tmp, int w_l, int pitch,
+                                                       size_t tmp_stride) {
+    int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (dx >= w_l) return;
+    const uint8_t* row = frames + (size_t)blockIdx.z * frame_stride + (size_t)y * W;
+    const int r = ksz >> 1;
+    const int i0 = xi0[dx];
+    const float a = xa[dx];
+    float b0 = 0.f;
+    if (i0 - r >= 0 && i0 + r + 1 < W) {
+        for (int i = 0; i < ksz; ++i) b0 += ktab[i] * (float)row[i0 + i - r];
+        float out = b0;
+        if (a != 0.f) {
+            float b1 = 0.f;
+            for (int i = 0; i < ksz; ++i) b1 += ktab[i] * (float)row[i0 + 1 + i - r];
+            out = b0 * (1.f - a) + b1 * a;
+        }
+        tmp[(size_t)blockIdx.z * tmp_stride + (size_t)y * pitch + dx] = out;
+        return;
+    }
+    for (int i = 0; i < ksz; ++i) b0 += ktab[i] * (float)row[reflect101(i0 + i - r, W)];
+    float out = b0;
+    if (a != 0.f) {
+        const int i1 = min(i0 + 1, W - 1);
+        float b1 = 0.f;
+        for (int i = 0; i < ksz; ++i) b1 += ktab[i] * (float)row[reflect101(i1 + i - r, W)];
+        out = b0 * (1.f - a) + b1 * a;
+    }
+    tmp[(size_t)blockIdx.z * tmp_stride + (size_t)y * pitch + dx] = out;
+}
+
+__global__ void __launch_bounds__(128) pyr_vpass_kernel(const float* __restrict__ tmp, size_t tmp_stride, int H,
+                                                       const int* __restrict__ yi0,
+                                                       const float* __restrict__ ya,
+                                                       const float* __restrict__ ktab, int ksz,
+                                                       float* __restrict__ img, int w_l, int h_l, int pitch,
+                                                       size_t img_stride) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int dy = blockIdx.y;
+    if (x >= w_l) return;
+    const float* src = tmp + (size_t)blockIdx.z * tmp_stride + x;
+    const int r = ksz >> 1;
+    const int i0 = yi0[dy];
+    const float a = ya[dy];
+    float b0 = 0.f;
+    for (int i = 0; i < ksz; ++i) b0 += ktab[i] * src[(size_t)reflect101(i0 + i - r, H) * pitch];
+    float out = b0;
+    if (a != 0.f) {
+        const int i1 = min(i0 + 1, H - 1);
+        float b1 = 0.f;
+        for (int i = 0; i < ksz; ++i) b1 += ktab[i] * src[(size_t)reflect101(i1 + i - r, H) * pitch];
+        out = b0 * (1.f - a) + b1 * a;
+    }
+    img[(size_t)blockIdx.z * img_stride + (size_t)dy * pitch + x] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Polynomial expansion (FarnebackPolyExp).  64x32 output tile, halo 8 (poly_n <= 8), 256 threads.
+//   vertical pass   : thread = (column, 4 rows)  -> t0,t1,t2 in smem
+//   horizontal pass : thread = (row, 4 columns)  -> float4 reads, float4 stores per plane
+// ------------------------------------------------------------------------------------------------
+constexpr int PE_TX = 64, PE_TY = 32, PE_H = 8, PE_RW = PE_TX + 2 * PE_H;  // 80
+
+__global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ img, size_t img_stride, int w,
+                                                     int h, int pitch, PolyConst pc, float* __restrict__ R,
+                                                     size_t plane) {
+    __shared__ __align__(16) float raw[(PE_TY + 2 * PE_H) * PE_RW];
+    __shared__ __align__(16) float t[3][PE_TY * PE_RW];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * PE_TX, y0 = blockIdx.y * PE_TY;
+    const float* src = img + (size_t)blockIdx.z * img_stride;
+    const int n = pc.n;
+
+    // stage rows y0-n .. y0+TY+n-1 (replicate), columns x0-8 .. x0+TX+8-1 (replicate)
+    const int rows = PE_TY + 2 * n;
+    for (int idx = tid; idx < rows * PE_RW; idx += 256) {
+        int rr = idx / PE_RW, cc = idx - rr * PE_RW;
+        int gy = clampi(y0 - n + rr, 0, h - 1);
+        int gx = clampi(x0 - PE_H + cc, 0, w - 1);
+        raw[(rr + PE_H - n) * PE_RW + cc] = src[(size_t)gy * pitch + gx];
+    }
+    __syncthreads();
+
+    // vertical pass
+    for (int task = tid; task < PE_RW * (PE_TY / 4); task += 256) {
+        int c = task % PE_RW, g4 = task / PE_RW;
+        float v[4 + 2 * PE_H];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * PE_H; ++j)
+            v[j] = (j >= PE_H - n && j < 4 + PE_H + n) ? raw[(g4 * 4 + j) * PE_RW + c] : 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float a0 = v[PE_H + o] * pc.g[0], a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= kMaxPolyN; ++k) {
+                if (k <= n) {
+                    float up = v[PE_H + o - k], dn = v[PE_H + o + k];
+                    float sum = up + dn;
+                    a0 += pc.g[k] * sum;
+                    a1 += pc.xg[k] * (dn - up);
+                    a2 += pc.xxg[k] * sum;
+                }
+            }
+            int r = g4 * 4 + o;
+            t[0][r * PE_RW + c] = a0;
+            t[1][r * PE_RW + c] = a1;
+            t[2][r * PE_RW + c] = a2;
+        }
+    }
+    __syncthreads();
+
+    // horizontal pass
+    for (int task = tid; task < PE_TY * (PE_TX / 4); task += 256) {
+        int q = task % (PE_TX / 4), r = task / (PE_TX / 4);
+        int y = y0 + r;
+        if (y >= h) continue;
+        float u0[4 + 2 * PE_H], u1[4 + 2 * PE_H], u2[4 + 2 * PE_H];
+        const float4* p0 = reinterpret_cast<const float4*>(&t[0][r * PE_RW + 4 * q]);
+        const float4* p1 = reinterpret_cast<const float4*>(&t[1][r * PE_RW + 4 * q]);
+        const float4* p2 = reinterpret_cast<const float4*>(&t[2][r * PE_RW + 4 * q]);
+#pragma unroll
+        for (int j = 0; j < (4 + 2 * PE_H) / 4; ++j) {
+            float4 a = p0[j], b = p1[j], c = p2[j];
+            u0[4 * j] = a.x; u0[4 * j + 1] = a.y; u0[4 * j + 2] = a.z; u0[4 * j + 3] = a.w;
+            u1[4 * j] = b.x; u1[4 * j + 1] = b.y; u1[4 * j + 2] = b.z; u1[4 * j + 3] = b.w;
+            u2[4 * j] = c.x; u2[4 * j + 1] = c.y; u2[4 * j + 2] = c.z; u2[4 * j + 3] = c.w;
+        }
+        float o0[4], o1[4], o2[4], o3[4], o4[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int c = PE_H + o;
+            float b1 = u0[c] * pc.g[0], b2 = 0.f, b3 = u1[c] * pc.g[0], b4 = 0.f, b5 = u2[c] * pc.g[0], b6 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= kMaxPolyN; ++k) {
+                if (k <= n) {
+                    float tg = u0[c + k] + u0[c - k];
+                    b1 += tg * pc.g[k];
+                    b4 += tg * pc.xxg[k];
+                    b2 += (u0[c + k] - u0[c - k]) * pc.xg[k];
+                    b3 += (u1[c + k] + u1[c - k]) * pc.g[k];
+                    b6 += (u1[c + k] - u1[c - k]) * pc.xg[k];
+                    b5 += (u2[c + k] + u2[c - k]) * pc.g[k];
+                }
+            }
+            o0[o] = b3 * pc.ig11;
+            o1[o] = b2 * pc.ig11;
+            o2[o] = b1 * pc.ig03 + b5 * pc.ig33;
+            o3[o] = b1 * pc.ig03 + b4 * pc.ig33;
+            o4[o] = b6 * pc.ig55;
+        }
+        float* dst = R + (size_t)blockIdx.z * 5 * plane + (size_t)y * pitch + x0 + 4 * q;
+        *reinterpret_cast<float4*>(dst) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        *reinterpret_cast<float4*>(dst + plane) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+        *reinterpret_cast<float4*>(dst + 2 * plane) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+        *reinterpret_cast<float4*>(dst + 3 * plane) = make_float4(o3[0], o3[1], o3[2], o3[3]);
+        *reinterpret_cast<float4*>(dst + 4 * plane) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FarnebackUpdateMatrices for one pixel.  R0/R1 point at plane 0 of the two frames' expansions.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float border_factor(int d) { return d < 2 ? 0.14f : 0.4472f; }
+
+__device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, int pitch, size_t plane, float dx,
+                                                   float dy, const float* __restrict__ R0,
+                                                   const float* __restrict__ R1, float* __restrict__ Mout) {
+    const size_t o = (size_t)y * pitch + x;
+    const float r0y = __ldg(R0 + o), r0x = __ldg(R0 + plane + o), r0yy = __ldg(R0 + 2 * plane + o),
+                r0xx = __ldg(R0 + 3 * plane + o), r0xy = __ldg(R0 + 4 * plane + o);
+    float fx = (float)x + dx, fy = (float)y + dy;
+    const float flx = floorf(fx), fly = floorf(fy);
+    // keep the int conversion safe for wild displacements
+    const int x1 = (int)fminf(fmaxf(flx, -2.f), 1.0e6f), y1 = (int)fminf(fmaxf(fly, -2.f), 1.0e6f);
+    fx -= flx;
+    fy -= fly;
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const float* p = R1 + (size_t)y1 * pitch + x1;
+        r2 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        p += plane;
+        r3 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        p += plane;
+        r4 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        p += plane;
+        r5 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        p += plane;
+        r6 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        r4 = (r0yy + r4) * 0.5f;
+        r5 = (r0xx + r5) * 0.5f;
+        r6 = (r0xy + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = r0yy;
+        r5 = r0xx;
+        r6 = r0xy * 0.5f;
+    }
+    r2 = (r0y - r2) * 0.5f;
+    r3 = (r0x - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float sc = (x < 5 ? border_factor(x) : 1.f) * (x >= w - 5 ? border_factor(w - x - 1) : 1.f) *
+                         (y < 5 ? border_factor(y) : 1.f) * (y >= h - 5 ? border_factor(h - y - 1) : 1.f);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    Mout[o] = r4 * r4 + r6 * r6;
+    Mout[plane + o] = (r4 + r5) * r6;
+    Mout[2 * plane + o] = r5 * r5 + r6 * r6;
+    Mout[3 * plane + o] = r4 * r2 + r6 * r3;
+    Mout[4 * plane + o] = r6 * r2 + r5 * r3;
+}
+
+// Level entry: flow_l = resize(flow_{l+1}) * (1/pyr_scale) (zeros on the coarsest level), then
+// UpdateMatrices.  The upsampled flow itself is never stored: BlurBox rebuilds the flow from M alone.
+__global__ void __launch_bounds__(256) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
+                                                           int pitch, int pair_stride,
+                                                           const float2* __restrict__ cflow, int cw, int ch,
+                                                           int cpitch, size_t cflow_stride,
+                                                           const int* __restrict__ fxi0,
+                                                           const float* __restrict__ fxa,
+                                                           const int* __restrict__ fyi0,
+                                                           const float* __restrict__ fya, float up_scale,
+                                                           float* __restrict__ M, float2* __restrict__ flow_dbg,
+                                                           int flow_dbg_pitch, size_t flow_dbg_stride) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= w || y >= h) return;
+    const int p = blockIdx.z;
+    float dx = 0.f, dy = 0.f;
+    if (cflow) {
+        const float2* cf = cflow + (size_t)p * cflow_stride;
+        const int xa0 = fxi0[x], ya0 = fyi0[y];
+        const int xa1 = min(xa0 + 1, cw - 1), ya1 = min(ya0 + 1, ch - 1);
+        const float ax = fxa[x], ay = fya[y];
+        const float2 f00 = cf[(size_t)ya0 * cpitch + xa0], f01 = cf[(size_t)ya0 * cpitch + xa1];
+        const float2 f10 = cf[(size_t)ya1 * cpitch + xa0], f11 = cf[(size_t)ya1 * cpitch + xa1];
+        const float tx0 = f00.x * (1.f - ax) + f01.x * ax, tx1 = f10.x * (1.f - ax) + f11.x * ax;
+        const float ty0 = f00.y * (1.f - ax) + f01.y * ax, ty1 = f10.y * (1.f - ax) + f11.y * ax;
+        dx = (tx0 * (1.f - ay) + tx1 * ay) * up_scale;
+        dy = (ty0 * (1.f - ay) + ty1 * ay) * up_scale;
+    }
+    if (flow_dbg) flow_dbg[(size_t)p * flow_dbg_stride + (size_t)y * flow_dbg_pitch + x] = make_float2(dx, dy);
+    const float* R0 = R + (size_t)(p * pair_stride) * 5 * plane;
+    update_matrices_px(x, y, w, h, pitch, plane, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused iteration: flow = solve(blur(M));  M' = UpdateMatrices(R0, R1, flow).
+// 64x32 tile, 256 threads.  The five planes of M are blurred one after the other through a small
+// smem staging area (raw tile + vertical sums); the blurred sums land in S[5][32][64]; the final
+// phase is per pixel with x fastest so R0 loads, the R1 gather and the M' stores are coalesced.
+// ------------------------------------------------------------------------------------------------
+constexpr int IT_TX = 64, IT_TY = 32;
+
+struct IterArgs {
+    const float* Min;
+    float* Mout;
+    const float* R;
+    float2* flow;           // nullable
+    int flow_pitch;         // float2 units
+    size_t flow_stride;     // float2 units per pair
+    int w, h, pitch;
+    size_t plane;
+    int m;                  // winsize / 2
+    int hx;                 // column halo, m rounded up to a multiple of 4
+    float scale;            // 1 / winsize^2 (box) or 1 (Gaussian: kernel already normalised)
+    int pair_stride;
+    const float* gk;        // Gaussian half kernel [m+1] (device) or nullptr
+};
+
+template <int M_>
+__device__ __forceinline__ void hsum_box(const float (&u)[20], float (&o)[4]) {
+    // window for output j covers u[8 - M_ + j .. 8 + M_ + j]
+    float s = 0.f;
+#pragma unroll
+    for (int j = 8 - M_; j <= 8 + M_; ++j) s += u[j];
+    o[0] = s;
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+        s += u[8 + M_ + j] - u[8 - M_ + j - 1];
+        o[j] = s;
+    }
+}
+
+template <int M_>
+__device__ __forceinline__ void hsum_gauss(const float (&u)[20], const float* __restrict__ gk, float (&o)[4]) {
+    float k[M_ + 1];
+#pragma unroll
+    for (int i = 0; i <= M_; ++i) k[i] = gk[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float s = u[8 + j] * k[0];
+#pragma unroll
+        for (int i = 1; i <= M_; ++i) s += (u[8 + j - i] + u[8 + j + i]) * k[i];
+        o[j] = s;
+    }
+}
+
+template <bool GAUSS, bool LAST>
+__global__ void __launch_bounds__(256, 3) iter_kernel(IterArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int m = a.m, hx = a.hx;
+    const int RW = IT_TX + 2 * hx;          // staged columns
+    const int RH = IT_TY + 2 * m;           // staged rows
+    float* raw = smem;                      // [RH][RW]
+    float* vs = raw + RH * RW;              // [IT_TY][RW]
+    float* S = vs + IT_TY * RW;             // [5][IT_TY][IT_TX]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * IT_TX, y0 = blockIdx.y * IT_TY;
+    const int p = blockIdx.z;
+    const int w = a.w, h = a.h, pitch = a.pitch;
+    const size_t plane = a.plane;
+    const float* Min = a.Min + (size_t)p * 5 * plane;
+    const bool interior = (x0 - hx >= 0) && (x0 + IT_TX + hx <= w) && (y0 - m >= 0) && (y0 + IT_TY + m <= h);
+
+    for (int c = 0; c < 5; ++c) {
+        const float* src = Min + c * plane;
+        // ---- stage the tile + halo (replicate borders) ----
+        if (interior) {
+            const int n4 = RW >> 2;
+            const float* base = src + (size_t)(y0 - m) * pitch + (x0 - hx);
+            for (int idx = tid; idx < RH * n4; idx += 256) {
+                int rr = idx / n4, q = idx - rr * n4;
+                float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)rr * pitch) + q);
+                *reinterpret_cast<float4*>(raw + rr * RW + 4 * q) = v;
+            }
+        } else {
+            for (int idx = tid; idx < RH * RW; idx += 256) {
+                int rr = idx / RW, cc = idx - rr * RW;
+                int gy = clampi(y0 - m + rr, 0, h - 1);
+                int gx = clampi(x0 - hx + cc, 0, w - 1);
+                raw[idx] = __ldg(src + (size_t)gy * pitch + gx);
+            }
+        }
+        __syncthreads();
+        // ---- vertical pass over the columns that are needed: [hx-m, hx+TX+m) ----
+        const int ncols = IT_TX + 2 * m;
+        if (!GAUSS) {
+            // running sums, 4 segments of 8 rows per column
+            for (int task = tid; task < ncols * 4; task += 256) {
+                int cc = task % ncols + (hx - m), seg = task / ncols;
+                const float* col = raw + (seg * 8) * RW + cc;
+                float s = 0.f;
+                for (int j = 0; j <= 2 * m; ++j) s += col[j * RW];
+                float* dst = vs + (seg * 8) * RW + cc;
+                dst[0] = s;
+#pragma unroll
+                for (int o = 1; o < 8; ++o) {
+                    s += col[(o + 2 * m) * RW] - col[(o - 1) * RW];
+                    dst[o * RW] = s;
+                }
+            }
+        } else {
+            for (int task = tid; task < ncols * IT_TY; task += 256) {
+                int cc = task % ncols + (hx - m), r = task / ncols;
+                const float* col = raw + r * RW + cc;
+                float s = col[m * RW] * __ldg(a.gk);
+                for (int i = 1; i <= m; ++i) s += (col[(m - i) * RW] + col[(m + i) * RW]) * __ldg(a.gk + i);
+                vs[r * RW + cc] = s;
+            }
+        }
+        __syncthreads();
+        // ---- horizontal pass: thread = (row, 4 columns) ----
+        float* Sc = S + c * (IT_TY * IT_TX);
+        if (hx == 8 && m >= 5) {
+            for (int task = tid; task < IT_TY * (IT_TX / 4); task += 256) {
+                int q = task & 15, r = task >> 4;
+                const float4* pv = reinterpret_cast<const float4*>(vs + r * RW + 4 * q);
+                float u[20];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    float4 v = pv[j];
+                    u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w;
+                }
+                float o[4];
+                if (!GAUSS) {
+                    switch (m) {
+                        case 5: hsum_box<5>(u, o); break;
+                        case 6: hsum_box<6>(u, o); break;
+                        case 7: hsum_box<7>(u, o); break;
+                        default: hsum_box<8>(u, o); break;
+                    }
+                } else {
+                    switch (m) {
+                        case 5: hsum_gauss<5>(u, a.gk, o); break;
+                        case 6: hsum_gauss<6>(u, a.gk, o); break;
+                        case 7: hsum_gauss<7>(u, a.gk, o); break;
+                        default: hsum_gauss<8>(u, a.gk, o); break;
+                    }
+                }
+                *reinterpret_cast<float4*>(Sc + r * IT_TX + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        } else {
+            // generic window: one pixel per thread step, conflict-free scalar reads
+            for (int idx = tid; idx < IT_TY * IT_TX; idx += 256) {
+                int cx = idx & 63, r = idx >> 6;
+                const float* row = vs + r * RW + hx + cx;
+                float s;
+                if (!GAUSS) {
+                    s = 0.f;
+                    for (int j = -m; j <= m; ++j) s += row[j];
+                } else {
+                    s = row[0] * __ldg(a.gk);
+                    for (int i = 1; i <= m; ++i) s += (row[-i] + row[i]) * __ldg(a.gk + i);
+                }
+                Sc[idx] = s;
+            }
+        }
+        // the next channel's staging writes `raw` (last read before the previous barrier) and its
+        // vertical pass writes `vs` only after the barrier that follows staging -> no extra barrier
+    }
+    __syncthreads();
+
+    // ---- per-pixel solve + matrix update (x fastest) ----
+    const float* R0 = a.R + (size_t)(p * a.pair_stride) * 5 * plane;
+    const float* R1 = R0 + 5 * plane;
+    float* Mout = LAST ? nullptr : a.Mout + (size_t)p * 5 * plane;
+#pragma unroll 2
+    for (int j = 0; j < (IT_TX * IT_TY) / 256; ++j) {
+        const int idx = j * 256 + tid;
+        const int cx = idx & 63, r = idx >> 6;
+        const int x = x0 + cx, y = y0 + r;
+        if (x >= w || y >= h) continue;
+        const float g11 = S[idx] * a.scale, g12 = S[IT_TX * IT_TY + idx] * a.scale,
+                    g22 = S[2 * IT_TX * IT_TY + idx] * a.scale, h1 = S[3 * IT_TX * IT_TY + idx] * a.scale,
+                    h2 = S[4 * IT_TX * IT_TY + idx] * a.scale;
+        const float idet = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
+        const float fx = (g11 * h2 - g12 * h1) * idet;
+        const float fy = (g22 * h1 - g12 * h2) * idet;
+        if (a.flow) a.flow[(size_t)p * a.flow_stride + (size_t)y * a.flow_pitch + x] = make_float2(fx, fy);
+        if (!LAST) update_matrices_px(x, y, w, h, pitch, plane, fx, fy, R0, R1, Mout);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// taps (tests only): planar pitched -> dense interleaved
+// ------------------------------------------------------------------------------------------------
+__global__ void tap_planar_kernel(const float* __restrict__ src, int w, int h, int pitch, size_t plane, int nch,
+                                  float* __restrict__ dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    for (int c = 0; c < nch; ++c) dst[((size_t)y * w + x) * nch + c] = src[c * plane + (size_t)y * pitch + x];
+}
+__global__ void tap_flow_kernel(const float2* __restrict__ src, int w, int h, int pitch, float2* __restrict__ dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    dst[(size_t)y * w + x] = src[(size_t)y * pitch + x];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side orchestration
+// ------------------------------------------------------------------------------------------------
+template <bool GAUSS, bool LAST>
+static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        MAVD_CUDA(cudaFuncSetAttribute(iter_kernel<GAUSS, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
+        configured = true;
+    }
+    iter_kernel<GAUSS, LAST><<<grid, 256, smem, s>>>(a);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_stride, float* d_flow,
+                  cudaStream_t s) {
+    const mavd_farneback_params& fp = H->cfg.farneback;
+    const int W = H->cfg.width, Hh = H->cfg.height;
+    const int n_frames = pair_stride == 1 ? n_pairs + 1 : 2 * n_pairs;
+    const bool gauss = (fp.flags & MAVD_FARNEBACK_GAUSSIAN) != 0;
+    const int m = fp.winsize / 2;
+    const int hx = round_up(m, 4);
+    const size_t frame_bytes = (size_t)W * Hh;
+
+    for (int li = H->n_levels - 1; li >= 0; --li) {
+        Level& L = H->lv[li];
+        // pyramid images for all frames
+        {
+            dim3 g1(ceil_div(L.w, 128), Hh, n_frames);
+            pyr_hpass_kernel<<<g1, 128, 0, s>>>(d_frames, frame_bytes, W, Hh, L.xi0, L.xa, L.ktab, L.ksz, H->tmp,
+                                                L.w, L.pitch, H->tmp_frame_stride);
+            MAVD_LAUNCHED();
+            dim3 g2(ceil_div(L.w, 128), L.h, n_frames);
+            pyr_vpass_kernel<<<g2, 128, 0, s>>>(H->tmp, H->tmp_frame_stride, Hh, L.yi0, L.ya, L.ktab, L.ksz, L.img,
+                                                L.w, L.h, L.pitch, L.plane);
+            MAVD_LAUNCHED();
+        }
+        // polynomial expansion for all frames
+        {
+            dim3 g(ceil_div(L.w, PE_TX), ceil_div(L.h, PE_TY), n_frames);
+            polyexp_kernel<<<g, 256, 0, s>>>(L.img, L.plane, L.w, L.h, L.pitch, H->poly, L.R, L.plane);
+            MAVD_LAUNCHED();
+        }
+        // matrices from the upsampled coarser flow
+        {
+            dim3 g(ceil_div(L.w, 64), ceil_div(L.h, 4), n_pairs);
+            const bool top = (li == H->n_levels - 1);
+            const Level* C = top ? nullptr : &H->lv[li + 1];
+            matrices_init_kernel<<<g, 256, 0, s>>>(
+                L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,
+                top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,
+                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0);
+            MAVD_LAUNCHED();
+        }
+        // iterations
+        int cur = 0;
+        for (int it = 0; it < fp.iterations; ++it) {
+            const bool last = (it == fp.iterations - 1);
+            IterArgs a;
+            a.Min = L.M[cur];
+            a.Mout = L.M[cur ^ 1];
+            a.R = L.R;
+            a.w = L.w; a.h = L.h; a.pitch = L.pitch; a.plane = L.plane;
+            a.m = m; a.hx = hx;
+            a.scale = gauss ? 1.f : (float)(1.0 / ((double)fp.winsize * fp.winsize));
+            a.pair_stride = pair_stride;
+            a.gk = gauss ? H->gauss_win : nullptr;
+            if (last) {
+                if (li == 0) {
+                    a.flow = (float2*)d_flow; a.flow_pitch = W; a.flow_stride = (size_t)W * Hh;
+                } else {
+                    a.flow = (float2*)L.flow; a.flow_pitch = L.pitch; a.flow_stride = L.plane;
+                }
+            } else {
+                a.flow = nullptr; a.flow_pitch = 0; a.flow_stride = 0;
+            }
+            dim3 g(ceil_div(L.w, IT_TX), ceil_div(L.h, IT_TY), n_pairs);
+            const int RW = IT_TX + 2 * hx, RH = IT_TY + 2 * m;
+            const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
+            int rc;
+            if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, s) : launch_iter<true, false>(a, g, smem, s);
+            else       rc = last ? launch_iter<false, true>(a, g, smem, s) : launch_iter<false, false>(a, g, smem, s);
+            if (rc != MAVD_OK) return rc;
+            if (!last) cur ^= 1;
+        }
+        L.last_m = cur;
+    }
+    H->last_pairs = n_pairs;
+    H->last_stride = pair_stride;
+    H->last_flow0 = d_flow;
+    return MAVD_OK;
+}
+
+int farneback_tap(mavd_handle H, int kind, int level, int index, float* d_out, cudaStream_t s) {
+    MAVD_REQUIRE(level >= 0 && level < H->n_levels, MAVD_ERR_INVALID, "tap: level %d out of range", level);
+    Level& L = H->lv[level];
+    dim3 g(ceil_div(L.w, 128), L.h);
+    switch (kind) {
+        case 0:
+            tap_planar_kernel<<<g, 128, 0, s>>>(L.img + (size_t)index * L.plane, L.w, L.h, L.pitch, L.plane, 1, d_out);
+            break;
+        case 1:
+            tap_planar_kernel<<<g, 128, 0, s>>>(L.R + (size_t)index * 5 * L.plane, L.w, L.h, L.pitch, L.plane, 5, d_out);
+            break;
+        case 2:
+            tap_planar_kernel<<<g, 128, 0, s>>>(L.M[L.last_m] + (size_t)index * 5 * L.plane, L.w, L.h, L.pitch,
+                                                L.plane, 5, d_out);
+            break;
+        case 3:
+            if (level == 0) {
+                MAVD_REQUIRE(H->last_flow0 != nullptr, MAVD_ERR_INVALID, "tap: no farneback call yet");
+                tap_flow_kernel<<<g, 128, 0, s>>>((const float2*)H->last_flow0 + (size_t)index * L.w * L.h, L.w, L.h,
+                                                  L.w, (float2*)d_out);
+            } else {
+                tap_flow_kernel<<<g, 128, 0, s>>>((const float2*)L.flow + (size_t)index * L.plane, L.w, L.h, L.pitch,
+                                                  (float2*)d_out);
+            }
+            break;
+        default:
+            MAVD_REQUIRE(false, MAVD_ERR_INVALID, "tap: unknown kind %d", kind);
+    }
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+}  // namespace mavd

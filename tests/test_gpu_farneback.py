@@ -1,0 +1,145 @@
+"""GPU: the CUDA Farneback path (through the C ABI) against the oracle, stage by stage and end to end.
+Tolerance from BASELINE.json north_star: mean end-point error <= 1e-3 px vs OpenCV's CPU Farneback."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EPE_MEAN_TOL = 1e-3      # north-star bar
+EPE_MEAN_TIGHT = 2e-5    # what fp32 accumulation actually achieves; guards against regressions
+EPE_MAX_TOL = 2e-3
+
+
+def _params(p):
+    return dict(pyr_scale=float(p[0]), levels=int(p[1]), winsize=int(p[2]), iterations=int(p[3]),
+                poly_n=int(p[4]), poly_sigma=float(p[5]), flags=int(p[6]))
+
+
+def _run_pair(prev, nxt, params):
+    import torch
+    from mav_detection_b200 import engine
+    h, w = prev.shape
+    eng = engine.Engine(w, h, params, max_pairs=1)
+    frames = torch.from_numpy(np.stack([prev, nxt])).cuda()
+    flow = eng.farneback(frames, pair_stride=2)
+    torch.cuda.synchronize()
+    return eng, flow[0].cpu().numpy()
+
+
+@pytest.mark.parametrize('name', ['ref', 'c2', 'gauss', 'odd', 'lvl0'])
+def test_flow_matches_golden_cv2(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, 'farneback_%s.npz' % name))
+    eng, flow = _run_pair(g['prev'], g['next'], _params(g['params']))
+    epe = np.linalg.norm(flow - g['flow'], axis=-1)
+    assert epe.mean() < EPE_MEAN_TIGHT and epe.max() < EPE_MAX_TOL, (epe.mean(), epe.max())
+    eng.close()
+
+
+@pytest.mark.parametrize('name', ['c2', 'ref', 'gauss'])
+def test_stages_match_oracle(golden_dir, name):
+    """Every intermediate of every pyramid level: image, R (both frames), last M, level flow."""
+    import torch
+    from oracle import farneback_np as fb
+    g = np.load(os.path.join(golden_dir, 'farneback_%s.npz' % name))
+    p = _params(g['params'])
+    taps = {}
+    fb.calc_optical_flow_farneback(g['prev'], g['next'], None, *[p[k] for k in
+                                   ('pyr_scale', 'levels', 'winsize', 'iterations', 'poly_n', 'poly_sigma', 'flags')],
+                                   tap=lambda n, l, a: taps.__setitem__((n, l), a.copy()))
+    eng, flow = _run_pair(g['prev'], g['next'], p)
+    for lvl in range(len(eng.levels)):
+        for j in (0, 1):
+            img = eng.tap('img', lvl, j).cpu().numpy()
+            assert np.abs(img - taps[('img%d' % j, lvl)]).max() < 5e-4, ('img', lvl, j)   # 0..255 scale
+            R = eng.tap('R', lvl, j).cpu().numpy()
+            ref = taps[('R%d' % j, lvl)]
+            assert np.abs(R - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), ('R', lvl, j)
+        fl = eng.tap('flow', lvl, 0).cpu().numpy()
+        ref = taps[('flow%d' % (p['iterations'] - 1), lvl)]
+        assert np.linalg.norm(fl - ref, axis=-1).mean() < EPE_MEAN_TIGHT, ('flow', lvl)
+    eng.close()
+
+
+def test_live_cv2_640x480_reference_params():
+    """BASELINE config 1: one synthetic 640x480 pair with the reference's parameters."""
+    cv2 = pytest.importorskip('cv2')
+    from mav_detection_b200 import engine, synth
+    s = synth.make_sequence(640, 480, 6, seq=1)
+    a, b = s.frames[4], s.frames[5]
+    ref = cv2.calcOpticalFlowFarneback(a, b, None, 0.4, 1, 12, 10, 8, 1.2, 0)
+    eng, flow = _run_pair(a, b, engine.REFERENCE_PARAMS)
+    epe = np.linalg.norm(flow - ref, axis=-1)
+    assert epe.mean() < EPE_MEAN_TOL and epe.mean() < EPE_MEAN_TIGHT, epe.mean()
+    assert np.linalg.norm(ref, axis=-1).mean() > 0.5     # the test is not vacuous
+    eng.close()
+
+
+@pytest.mark.parametrize('size', [(752, 480), (333, 257), (64, 48)])
+@pytest.mark.parametrize('winsize,poly_n,flags', [(15, 5, 0), (12, 8, 0), (9, 7, 0), (21, 5, 0), (4, 3, 0),
+                                                   (13, 5, 256), (21, 7, 256)])
+def test_ragged_sizes_and_windows_vs_cv2(size, winsize, poly_n, flags):
+    """Odd sizes (edge tiles, pitch padding), generic window path (m<5, m>8), both blur flags."""
+    cv2 = pytest.importorskip('cv2')
+    from mav_detection_b200 import synth
+    w, h = size
+    a, b = synth.make_pair(w, h, seq=7)
+    p = dict(pyr_scale=0.5, levels=3, winsize=winsize, iterations=2, poly_n=poly_n, poly_sigma=1.1, flags=flags)
+    ref = cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 3, winsize, 2, poly_n, 1.1, flags)
+    eng, flow = _run_pair(a, b, p)
+    epe = np.linalg.norm(flow - ref, axis=-1)
+    assert epe.mean() < EPE_MEAN_TIGHT * 5 and epe.max() < 5e-3, (epe.mean(), epe.max())
+    eng.close()
+
+
+def test_sequence_mode_equals_pair_mode_and_batches():
+    """pair_stride=1 shares each frame's expansion between its two pairs; results must be identical."""
+    import torch
+    from mav_detection_b200 import engine, synth
+    s = synth.make_sequence(320, 240, 6, seq=2)
+    eng = engine.Engine(320, 240, engine.SAMPLE_PARAMS, max_pairs=5)
+    frames = torch.from_numpy(s.frames).cuda()
+    seq_flow = eng.farneback(frames, pair_stride=1).cpu().numpy()
+    assert seq_flow.shape == (5, 240, 320, 2)
+    pairs = torch.from_numpy(np.stack([s.frames[[i, i + 1]] for i in range(5)]).reshape(10, 240, 320)).cuda()
+    pair_flow = eng.farneback(pairs, pair_stride=2).cpu().numpy()
+    assert np.array_equal(seq_flow, pair_flow)
+    one = eng.farneback(frames[2:4].contiguous(), pair_stride=2).cpu().numpy()
+    assert np.array_equal(one[0], seq_flow[2])
+    eng.close()
+
+
+def test_1080p_properties():
+    """BASELINE config 2 size: properties that do not need the slow oracle at full size, plus cv2."""
+    cv2 = pytest.importorskip('cv2')
+    import torch
+    from mav_detection_b200 import engine, synth
+    s = synth.make_sequence(1920, 1080, 3, seq=0)
+    eng = engine.Engine(1920, 1080, engine.SAMPLE_PARAMS, max_pairs=2)
+    frames = torch.from_numpy(s.frames).cuda()
+    flow = eng.farneback(frames).cpu().numpy()
+    assert np.isfinite(flow).all()
+    # identical frames -> exactly zero flow (linearity of the expansion: R0 == R1 => h = 0)
+    same = torch.from_numpy(np.stack([s.frames[0], s.frames[0]])).cuda()
+    z = eng.farneback(same, pair_stride=2).cpu().numpy()
+    assert np.abs(z).max() < 1e-4
+    ref = cv2.calcOpticalFlowFarneback(s.frames[0], s.frames[1], None, 0.5, 5, 15, 3, 5, 1.2, 0)
+    epe = np.linalg.norm(flow[0] - ref, axis=-1)
+    assert epe.mean() < EPE_MEAN_TIGHT, epe.mean()
+    eng.close()
+
+
+def test_errors_map_to_python_exceptions():
+    import torch
+    from mav_detection_b200 import engine
+    with pytest.raises(ValueError):
+        engine.Engine(640, 480, dict(poly_n=12))
+    with pytest.raises(ValueError):
+        engine.Engine(640, 480, dict(pyr_scale=1.0))
+    eng = engine.Engine(64, 48, engine.SAMPLE_PARAMS, max_pairs=1)
+    with pytest.raises(ValueError):
+        eng.farneback(torch.zeros((2, 50, 64), dtype=torch.uint8, device='cuda'))
+    with pytest.raises(ValueError):
+        eng.farneback(torch.zeros((4, 48, 64), dtype=torch.uint8, device='cuda'))   # 3 pairs > max_pairs
+    eng.close()
