@@ -185,6 +185,26 @@ int mavd_process_host(mavd_handle h, const uint8_t* h_frames, int32_t n_pairs, i
                       const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
                       float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream);
 
+/* ---- optional per-kernel-class device timing (CUDA events on the launching stream) ---- */
+enum {
+    MAVD_PROF_PYRAMID = 0,       /* pyramid blur+resize passes                       */
+    MAVD_PROF_POLYEXP = 1,       /* polynomial expansion                             */
+    MAVD_PROF_MATRICES = 2,      /* level-entry UpdateMatrices (+ flow upsample)     */
+    MAVD_PROF_ITER_FULL = 3,     /* fused iteration, finest level, not the last one  */
+    MAVD_PROF_ITER_FULL_LAST = 4,/* finest level, last iteration (blur + solve only) */
+    MAVD_PROF_ITER_COARSE = 5,   /* fused iterations on all coarser levels           */
+    MAVD_PROF_FOE = 6,
+    MAVD_PROF_RESIDUAL = 7,
+    MAVD_PROF_CCL = 8,
+    MAVD_PROF_CLASSES = 12
+};
+typedef struct mavd_profile {
+    double ms[MAVD_PROF_CLASSES];        /* summed device time per class since enable */
+    int64_t launches[MAVD_PROF_CLASSES]; /* timed launch groups per class             */
+} mavd_profile;
+int mavd_profile_enable(mavd_handle h, int32_t on); /* also clears the counters */
+int mavd_profile_read(mavd_handle h, mavd_profile* out); /* waits for the recorded events */
+
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t mavd_launch_count(void);
 

@@ -49,6 +49,15 @@ class FrameRecord(C.Structure):
                 ('stats', FrameStats), ('boxes', (C.c_int32 * 5) * MAX_BOXES)]
 
 
+PROF_CLASSES = 12
+PROF_NAMES = ['pyramid', 'polyexp', 'matrices', 'iter_full', 'iter_full_last', 'iter_coarse', 'foe', 'residual',
+              'ccl']
+
+
+class Profile(C.Structure):
+    _fields_ = [('ms', C.c_double * PROF_CLASSES), ('launches', C.c_int64 * PROF_CLASSES)]
+
+
 # every symbol include/mavd.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -72,6 +81,8 @@ SIGNATURES = {
     'mavd_process_host': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
                                     _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
     'mavd_launch_count': (C.c_int64, []),
+    'mavd_profile_enable': (C.c_int, [_P, C.c_int32]),
+    'mavd_profile_read': (C.c_int, [_P, C.POINTER(Profile)]),
 }
 
 _lib: Optional[C.CDLL] = None

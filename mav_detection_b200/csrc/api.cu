@@ -327,7 +327,35 @@ int mavd_destroy(mavd_handle h) {
     cudaSetDevice(H->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : H->arena.ptrs) cudaFree(p);
+    for (auto& r : H->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : H->prof.pool) cudaEventDestroy(e);
     delete H;
+    return MAVD_OK;
+}
+
+int mavd_profile_enable(mavd_handle h, int32_t on) {
+    MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "profile: handle is NULL");
+    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    MAVD_CUDA(cudaDeviceSynchronize());
+    for (auto& r : h->prof.recs) { h->prof.pool.push_back(r.a); h->prof.pool.push_back(r.b); }
+    h->prof.recs.clear();
+    h->prof.on = on != 0;
+    return MAVD_OK;
+}
+
+int mavd_profile_read(mavd_handle h, mavd_profile* out) {
+    MAVD_REQUIRE(h && out, MAVD_ERR_INVALID, "profile: NULL argument");
+    memset(out, 0, sizeof(*out));
+    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    for (auto& r : h->prof.recs) {
+        MAVD_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        MAVD_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.cls >= 0 && r.cls < MAVD_PROF_CLASSES) { out->ms[r.cls] += ms; out->launches[r.cls] += 1; }
+        h->prof.pool.push_back(r.a);
+        h->prof.pool.push_back(r.b);
+    }
+    h->prof.recs.clear();
     return MAVD_OK;
 }
 

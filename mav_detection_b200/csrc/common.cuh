@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
+#include <vector>
 
 #include "mavd.h"
 
@@ -67,6 +68,36 @@ struct Level {
     int last_m = 0;         // which M buffer holds the last update (for taps)
 };
 
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline).
+struct Profiler {
+    struct Rec { int cls; cudaEvent_t a, b; };
+    bool on = false;
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
+struct ProfScope {
+    Profiler* p;
+    cudaStream_t s;
+    size_t idx = 0;
+    ProfScope(Profiler* prof, int cls, cudaStream_t st) : p(prof && prof->on ? prof : nullptr), s(st) {
+        if (!p) return;
+        Profiler::Rec r{cls, p->get(), p->get()};
+        cudaEventRecord(r.a, s);
+        idx = p->recs.size();
+        p->recs.push_back(r);
+    }
+    ~ProfScope() {
+        if (p) cudaEventRecord(p->recs[idx].b, s);
+    }
+};
+
 struct PolyConst {
     float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
     float ig11, ig03, ig33, ig55;
@@ -100,6 +131,7 @@ struct mavd_handle_s {
     uint8_t* d_sky = nullptr;       // [max_pairs][H][W]
     uint8_t* d_seg = nullptr;
     mavd_frame_record* d_records = nullptr;
+    mavd::Profiler prof;
     // last call bookkeeping for taps
     int last_pairs = 0, last_stride = 1;
     float* last_flow0 = nullptr;

@@ -237,6 +237,7 @@ static double sqrt_threshold(double T) {
 
 int foe_run(mavd_handle H, const float* d_flow, int n, const mavd_imu* d_imu, const mavd_detect_params& prm,
             const int32_t* d_samples, double* d_foe, int32_t* d_ninter, cudaStream_t s) {
+    ProfScope ps(&H->prof, MAVD_PROF_FOE, s);
     foe_kernel<<<n, 1024, 0, s>>>((const float2*)d_flow, d_imu, d_samples, H->cfg.width, H->cfg.height,
                                   prm.magnitude_threshold, sqrt_threshold(prm.ransac_threshold), d_foe, d_ninter);
     MAVD_LAUNCHED();
@@ -449,6 +450,7 @@ int residual_run(mavd_handle H, const float* d_flow, int n, const mavd_imu* d_im
                  const double* d_foe, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
                  int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
                  size_t stats_stride, int run_f64, int run_f32, cudaStream_t s) {
+    ProfScope ps(&H->prof, MAVD_PROF_RESIDUAL, s);
     const int w = H->cfg.width, h = H->cfg.height;
     int* seg_max = reinterpret_cast<int*>(H->d_scan);  // scratch: n ints
     if (d_stats) {
@@ -666,6 +668,7 @@ __global__ void ccl_boxes_final_kernel(int32_t* boxes, size_t boxes_stride, int 
 
 int ccl_run(mavd_handle H, const uint8_t* d_mask, int n, int32_t* d_labels, int32_t* d_boxes, size_t boxes_stride,
             int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s) {
+    ProfScope ps(&H->prof, MAVD_PROF_CCL, s);
     const int w = H->cfg.width, h = H->cfg.height, npx = w * h;
     const int n_chunks = ceil_div(npx, CCL_CHUNK);
     int* rank = H->d_scan;                                  // [n][npx]

@@ -521,6 +521,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         Level& L = H->lv[li];
         // pyramid images for all frames
         {
+            ProfScope ps(&H->prof, MAVD_PROF_PYRAMID, s);
             dim3 g1(ceil_div(L.w, 128), Hh, n_frames);
             pyr_hpass_kernel<<<g1, 128, 0, s>>>(d_frames, frame_bytes, W, Hh, L.xi0, L.xa, L.ktab, L.ksz, H->tmp,
                                                 L.w, L.pitch, H->tmp_frame_stride);
@@ -532,12 +533,14 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         }
         // polynomial expansion for all frames
         {
+            ProfScope ps(&H->prof, MAVD_PROF_POLYEXP, s);
             dim3 g(ceil_div(L.w, PE_TX), ceil_div(L.h, PE_TY), n_frames);
             polyexp_kernel<<<g, 256, 0, s>>>(L.img, L.plane, L.w, L.h, L.pitch, H->poly, L.R, L.plane);
             MAVD_LAUNCHED();
         }
         // matrices from the upsampled coarser flow
         {
+            ProfScope ps(&H->prof, MAVD_PROF_MATRICES, s);
             dim3 g(ceil_div(L.w, 64), ceil_div(L.h, 4), n_pairs);
             const bool top = (li == H->n_levels - 1);
             const Level* C = top ? nullptr : &H->lv[li + 1];
@@ -572,6 +575,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             dim3 g(ceil_div(L.w, IT_TX), ceil_div(L.h, IT_TY), n_pairs);
             const int RW = IT_TX + 2 * hx, RH = IT_TY + 2 * m;
             const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
+            ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), s);
             int rc;
             if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, s) : launch_iter<true, false>(a, g, smem, s);
             else       rc = last ? launch_iter<false, true>(a, g, smem, s) : launch_iter<false, false>(a, g, smem, s);

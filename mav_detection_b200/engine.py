@@ -239,5 +239,14 @@ class Engine:
     def stats_to_numpy(stats: torch.Tensor) -> np.ndarray:
         return stats.cpu().numpy().view(STATS_DTYPE).reshape(-1)
 
+    def profile_enable(self, on: bool = True) -> None:
+        check(self.lib.mavd_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel class: (summed device ms, timed launch groups)} since profile_enable()."""
+        prof = _lib.Profile()
+        check(self.lib.mavd_profile_read(self._h, C.byref(prof)))
+        return {n: (prof.ms[i], int(prof.launches[i])) for i, n in enumerate(_lib.PROF_NAMES)}
+
     def launch_count(self) -> int:
         return int(self.lib.mavd_launch_count())
