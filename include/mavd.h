@@ -142,7 +142,7 @@ int mavd_derotate(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu*
                   void* stream);
 
 /* ---- stage 2: FocusOfExpansion.get_FOE_dense + ransac — src/focus_of_expansion.py:32-86 ----
- * d_samples: per frame MAVD_SAMPLES_PER_FRAME/2... see layout: [ry(2000) | rx(2000)] int32, the two
+ * d_samples: per frame MAVD_SAMPLES_PER_FRAME int32 laid out [ry(2000) | rx(2000)], the two
  * np.random.randint draws of focus_of_expansion.py:69-71 made by the host in frame order.
  * Derotation is applied inline to the sampled vectors.  d_foe: n x 2 float64 (x, y); (0,0) = none. */
 int mavd_foe(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu,
@@ -204,6 +204,10 @@ typedef struct mavd_profile {
 } mavd_profile;
 int mavd_profile_enable(mavd_handle h, int32_t on); /* also clears the counters */
 int mavd_profile_read(mavd_handle h, mavd_profile* out); /* waits for the recorded events */
+
+/* Tests: route the Farneback iterations through the generic (non-TMA) kernel, which production uses only
+ * for Gaussian windows and for winsize/2 outside 5..8. */
+int mavd_debug_force_generic_iteration(mavd_handle h, int32_t on);
 
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t mavd_launch_count(void);

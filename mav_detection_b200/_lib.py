@@ -81,6 +81,7 @@ SIGNATURES = {
     'mavd_process_host': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
                                     _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
     'mavd_launch_count': (C.c_int64, []),
+    'mavd_debug_force_generic_iteration': (C.c_int, [_P, C.c_int32]),
     'mavd_profile_enable': (C.c_int, [_P, C.c_int32]),
     'mavd_profile_read': (C.c_int, [_P, C.POINTER(Profile)]),
 }

@@ -119,6 +119,32 @@ static int poly_setup(int n, double sigma, PolyConst& pc) {
     return MAVD_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// TMA descriptor of one M buffer: rank-3 float tensor {pitch, h, planes}, box {80, 32+2m, 5}, zero fill.
+static bool make_m_tensor_map(CUtensorMap* map, float* base, int pitch, int h, int planes, size_t plane, int m) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
+            cudaGetLastError();
+            return false;
+        }
+        fn = (EncodeTiledFn)f;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)h, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)plane * sizeof(float)};
+    cuuint32_t box[3] = {80u, (cuuint32_t)(32 + 2 * m), 5u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 struct Arena {
     std::vector<void*> ptrs;
     size_t bytes = 0;
@@ -266,6 +292,10 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
         cudaMemset(L.R, 0, (size_t)F * 5 * L.plane * sizeof(float));
         cudaMemset(L.M[0], 0, (size_t)B * 5 * L.plane * sizeof(float));
         cudaMemset(L.M[1], 0, (size_t)B * 5 * L.plane * sizeof(float));
+        const int m = fp.winsize / 2;
+        if (m >= 5 && m <= 8)
+            L.has_tmap = make_m_tensor_map(&L.tmapM[0], L.M[0], L.pitch, L.h, B * 5, L.plane, m) &&
+                         make_m_tensor_map(&L.tmapM[1], L.M[1], L.pitch, L.h, B * 5, L.plane, m);
     }
     for (int li = 0; li + 1 < H->n_levels; ++li) {
         Level& L = H->lv[li];
@@ -356,6 +386,12 @@ int mavd_profile_read(mavd_handle h, mavd_profile* out) {
         h->prof.pool.push_back(r.b);
     }
     h->prof.recs.clear();
+    return MAVD_OK;
+}
+
+int mavd_debug_force_generic_iteration(mavd_handle h, int32_t on) {
+    MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "handle is NULL");
+    h->force_generic_iter = on != 0;
     return MAVD_OK;
 }
 

@@ -1,5 +1,6 @@
 // Shared helpers for libmavd (sm_100a).  Error reporting never throws across the C ABI.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -66,6 +67,8 @@ struct Level {
     float* M[2] = {nullptr, nullptr};  // [pairs][5][h][pitch]
     float* flow = nullptr;  // [pairs][h][pitch] float2 (unused for level 0: written to the caller's buffer)
     int last_m = 0;         // which M buffer holds the last update (for taps)
+    CUtensorMap tmapM[2];   // TMA descriptors of M[0] / M[1]: dims {pitch, h, pairs*5}, box {80, 32+2m, 5}
+    bool has_tmap = false;
 };
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline).
@@ -132,6 +135,7 @@ struct mavd_handle_s {
     uint8_t* d_seg = nullptr;
     mavd_frame_record* d_records = nullptr;
     mavd::Profiler prof;
+    bool force_generic_iter = false;  // tests: run the non-TMA iteration kernel
     // last call bookkeeping for taps
     int last_pairs = 0, last_stride = 1;
     float* last_flow0 = nullptr;

@@ -477,6 +477,202 @@ __global__ void __launch_bounds__(256, 3) iter_kernel(IterArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused iteration, TMA-staged (box window, 5 <= m <= 8): the production path.
+//
+// One cp.async.bulk.tensor (TMA) brings the 5 x (32+2m) x 80 float box of M — all five planes of the
+// tile plus halo — into shared memory; everything after that happens IN PLACE in that box:
+//   vertical   thread = (plane, column): running 2m+1 sum marching down the column, window in
+//              registers, the sum for row y overwrites row y after its input has been consumed
+//   horizontal half-warp = one row: 4 outputs per thread from 5 float4 reads, written back over
+//              columns 8..71 after a __syncwarp (rows are private to a half-warp)
+//   pixel      x-fastest mapping: 2x2 solve, then UpdateMatrices with coalesced R0 loads, R1 gather
+//              through the read-only path and coalesced M' stores
+// Out-of-image box cells arrive as zeros (TMA fill) and are overwritten with the replicated edge
+// values for border tiles only.  Three __syncthreads per tile instead of eleven.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+// UpdateMatrices with 32-bit index arithmetic; `edge` is tile-uniform (tile within 5 px of a border).
+__device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h, int pitch, int plane, bool edge,
+                                                     float dx, float dy, const float* __restrict__ R0,
+                                                     const float* __restrict__ R1, float* __restrict__ Mout) {
+    const int o = y * pitch + x;
+    const float r0y = __ldg(R0 + o), r0x = __ldg(R0 + plane + o), r0yy = __ldg(R0 + 2 * plane + o),
+                r0xx = __ldg(R0 + 3 * plane + o), r0xy = __ldg(R0 + 4 * plane + o);
+    float fx = (float)x + dx, fy = (float)y + dy;
+    const float flx = floorf(fx), fly = floorf(fy);
+    const int x1 = (int)fminf(fmaxf(flx, -2.f), 1.0e6f), y1 = (int)fminf(fmaxf(fly, -2.f), 1.0e6f);
+    fx -= flx;
+    fy -= fly;
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float gx = 1.f - fx, gy = 1.f - fy;
+        const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
+        const float* p0 = R1 + (y1 * pitch + x1);
+        const float* p1 = p0 + pitch;
+        r2 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        p0 += plane; p1 += plane;
+        r3 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        p0 += plane; p1 += plane;
+        r4 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        p0 += plane; p1 += plane;
+        r5 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        p0 += plane; p1 += plane;
+        r6 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        r4 = (r0yy + r4) * 0.5f;
+        r5 = (r0xx + r5) * 0.5f;
+        r6 = (r0xy + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = r0yy;
+        r5 = r0xx;
+        r6 = r0xy * 0.5f;
+    }
+    r2 = (r0y - r2) * 0.5f;
+    r3 = (r0x - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if (edge && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
+        const float sc = (x < 5 ? border_factor(x) : 1.f) * (x >= w - 5 ? border_factor(w - x - 1) : 1.f) *
+                         (y < 5 ? border_factor(y) : 1.f) * (y >= h - 5 ? border_factor(h - y - 1) : 1.f);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    Mout[o] = r4 * r4 + r6 * r6;
+    Mout[plane + o] = (r4 + r5) * r6;
+    Mout[2 * plane + o] = r5 * r5 + r6 * r6;
+    Mout[3 * plane + o] = r4 * r2 + r6 * r3;
+    Mout[4 * plane + o] = r6 * r2 + r5 * r3;
+}
+
+template <int M_, bool LAST>
+__global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap, IterArgs a) {
+    constexpr int RW = IT_TX + 16;          // 80 staged columns (halo 8 each side, 16-byte aligned)
+    constexpr int RH = IT_TY + 2 * M_;      // staged rows
+    constexpr int CH = RH * RW;             // floats per plane box
+    constexpr int NC = IT_TX + 2 * M_;      // columns the vertical pass must produce
+    extern __shared__ __align__(128) float box[];   // [5][RH][RW]
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * IT_TX, y0 = blockIdx.y * IT_TY;
+    const int p = blockIdx.z;
+    const int w = a.w, h = a.h, pitch = a.pitch;
+    const int plane = (int)a.plane;
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, 5 * CH * (uint32_t)sizeof(float));
+        tma_load_3d(box, &tmap, x0 - 8, y0 - M_, p * 5, &bar);
+    }
+    const bool interior = (x0 - 8 >= 0) && (x0 + IT_TX + 8 <= w) && (y0 - M_ >= 0) && (y0 + IT_TY + M_ <= h);
+    mbar_wait(&bar, 0);
+
+    if (!interior) {
+        // replicate borders: every out-of-image cell takes the value of the clamped (in-image) cell
+        for (int idx = tid; idx < 5 * CH; idx += 256) {
+            const int c = idx / CH, rem = idx - c * CH;
+            const int rr = rem / RW, cc = rem - rr * RW;
+            const int y = y0 - M_ + rr, x = x0 - 8 + cc;
+            const int yc = clampi(y, 0, h - 1), xc = clampi(x, 0, w - 1);
+            if (yc != y || xc != x) box[idx] = box[c * CH + (yc - (y0 - M_)) * RW + (xc - (x0 - 8))];
+        }
+        __syncthreads();
+    }
+
+    // ---- vertical running sums, in place: 15 warp-tasks (plane, 32-column block) over 8 warps ----
+    for (int t = warp; t < 15; t += 8) {
+        const int c = t / 3, col = (t - 3 * c) * 32 + lane;
+        if (col < NC) {
+            float* q = box + c * CH + (8 - M_) + col;
+            float in[RH];
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j <= 2 * M_; ++j) {
+                in[j] = q[j * RW];
+                s += in[j];
+            }
+#pragma unroll
+            for (int y = 0; y < IT_TY; ++y) {
+                q[y * RW] = s;
+                if (y < IT_TY - 1) {
+                    in[y + 2 * M_ + 1] = q[(y + 2 * M_ + 1) * RW];
+                    s += in[y + 2 * M_ + 1] - in[y];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- horizontal sums, in place: half-warp = one row, thread = 4 outputs ----
+    {
+        const int q4 = tid & 15, rsub = tid >> 4;
+#pragma unroll 2
+        for (int it = 0; it < 10; ++it) {
+            const int c = it >> 1, r = (it & 1) * 16 + rsub;
+            float* row = box + c * CH + r * RW + 4 * q4;
+            float u[20];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(row + 4 * j);
+                u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w;
+            }
+            float o[4];
+            hsum_box<M_>(u, o);
+            __syncwarp();
+            *reinterpret_cast<float4*>(row + 8) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- per pixel: solve, then UpdateMatrices ----
+    const float* R0 = a.R + (size_t)(p * a.pair_stride) * 5 * a.plane;
+    const float* R1 = R0 + 5 * a.plane;
+    float* Mout = LAST ? nullptr : a.Mout + (size_t)p * 5 * a.plane;
+    float2* fl = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
+    const bool edge = (x0 < 5) || (y0 < 5) || (x0 + IT_TX > w - 5) || (y0 + IT_TY > h - 5);
+    const float scale = a.scale;
+#pragma unroll 2
+    for (int j = 0; j < (IT_TX * IT_TY) / 256; ++j) {
+        const int idx = j * 256 + tid;
+        const int cx = idx & 63, r = idx >> 6;
+        const int x = x0 + cx, y = y0 + r;
+        if (x >= w || y >= h) continue;
+        const float* sp = box + r * RW + 8 + cx;
+        const float g11 = sp[0] * scale, g12 = sp[CH] * scale, g22 = sp[2 * CH] * scale, h1 = sp[3 * CH] * scale,
+                    h2 = sp[4 * CH] * scale;
+        const float idet = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
+        const float fx = (g11 * h2 - g12 * h1) * idet;
+        const float fy = (g22 * h1 - g12 * h2) * idet;
+        if (fl) fl[y * a.flow_pitch + x] = make_float2(fx, fy);
+        if (!LAST) update_matrices_fast(x, y, w, h, pitch, plane, edge, fx, fy, R0, R1, Mout);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // taps (tests only): planar pitched -> dense interleaved
 // ------------------------------------------------------------------------------------------------
 __global__ void tap_planar_kernel(const float* __restrict__ src, int w, int h, int pitch, size_t plane, int nch,
@@ -505,6 +701,30 @@ static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s
     iter_kernel<GAUSS, LAST><<<grid, 256, smem, s>>>(a);
     MAVD_LAUNCHED();
     return MAVD_OK;
+}
+
+template <int M_, bool LAST>
+static int launch_iter_tma(const CUtensorMap& map, const IterArgs& a, dim3 grid, cudaStream_t s) {
+    constexpr size_t smem = sizeof(float) * 5 * (IT_TY + 2 * M_) * (IT_TX + 16);
+    static bool configured = false;
+    if (!configured) {
+        MAVD_CUDA(cudaFuncSetAttribute(iter_box_tma_kernel<M_, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        configured = true;
+    }
+    iter_box_tma_kernel<M_, LAST><<<grid, 256, smem, s>>>(map, a);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+template <bool LAST>
+static int launch_iter_tma_m(int m, const CUtensorMap& map, const IterArgs& a, dim3 grid, cudaStream_t s) {
+    switch (m) {
+        case 5: return launch_iter_tma<5, LAST>(map, a, grid, s);
+        case 6: return launch_iter_tma<6, LAST>(map, a, grid, s);
+        case 7: return launch_iter_tma<7, LAST>(map, a, grid, s);
+        default: return launch_iter_tma<8, LAST>(map, a, grid, s);
+    }
 }
 
 int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_stride, float* d_flow,
@@ -577,7 +797,9 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
             ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), s);
             int rc;
-            if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, s) : launch_iter<true, false>(a, g, smem, s);
+            if (!gauss && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter)
+                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], a, g, s) : launch_iter_tma_m<false>(m, L.tmapM[cur], a, g, s);
+            else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, s) : launch_iter<true, false>(a, g, smem, s);
             else       rc = last ? launch_iter<false, true>(a, g, smem, s) : launch_iter<false, false>(a, g, smem, s);
             if (rc != MAVD_OK) return rc;
             if (!last) cur ^= 1;

@@ -239,6 +239,10 @@ class Engine:
     def stats_to_numpy(stats: torch.Tensor) -> np.ndarray:
         return stats.cpu().numpy().view(STATS_DTYPE).reshape(-1)
 
+    def force_generic_iteration(self, on: bool = True) -> None:
+        """Tests only: use the non-TMA iteration kernel even where the TMA kernel applies."""
+        check(self.lib.mavd_debug_force_generic_iteration(self._h, 1 if on else 0))
+
     def profile_enable(self, on: bool = True) -> None:
         check(self.lib.mavd_profile_enable(self._h, 1 if on else 0))
 

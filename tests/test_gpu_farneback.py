@@ -94,6 +94,24 @@ def test_ragged_sizes_and_windows_vs_cv2(size, winsize, poly_n, flags):
     eng.close()
 
 
+@pytest.mark.parametrize('winsize', [11, 12, 15, 17])
+def test_tma_and_generic_iteration_kernels_agree(winsize):
+    """winsize/2 in 5..8 runs the TMA-staged kernel; the generic kernel must give (nearly) the same flow."""
+    import torch
+    from mav_detection_b200 import engine, synth
+    s = synth.make_sequence(700, 500, 3, seq=5)
+    p = dict(pyr_scale=0.5, levels=3, winsize=winsize, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+    eng = engine.Engine(700, 500, p, max_pairs=2)
+    frames = torch.from_numpy(s.frames).cuda()
+    a = eng.farneback(frames).cpu().numpy()
+    eng.force_generic_iteration(True)
+    b = eng.farneback(frames).cpu().numpy()
+    eng.force_generic_iteration(False)
+    epe = np.linalg.norm(a - b, axis=-1)
+    assert epe.mean() < EPE_MEAN_TIGHT and epe.max() < EPE_MAX_TOL, (epe.mean(), epe.max())
+    eng.close()
+
+
 def test_sequence_mode_equals_pair_mode_and_batches():
     """pair_stride=1 shares each frame's expansion between its two pairs; results must be identical."""
     import torch
