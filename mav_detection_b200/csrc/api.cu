@@ -273,15 +273,29 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
         L.h = cv_round(Hh * s);
         L.pitch = round_up(L.w, 64);
         L.plane = (size_t)L.pitch * L.h;
-        std::vector<int> i0;
-        std::vector<float> a;
-        resize_tables(W, L.w, i0, a);
-        C_TRY(A.upload(&L.xi0, i0));
-        C_TRY(A.upload(&L.xa, a));
-        resize_tables(Hh, L.h, i0, a);
-        C_TRY(A.upload(&L.yi0, i0));
-        C_TRY(A.upload(&L.ya, a));
-        C_TRY(A.upload(&L.ktab, gaussian_kernel(L.ksz, sigma)));
+        if (li > 0) {
+            // combined blur + bilinear-resize filter per output sample: c_j = (1-a) k_j + a k_{j-1}
+            const std::vector<float> kk = gaussian_kernel(L.ksz, sigma);
+            const int taps = L.ksz + 1, r = L.ksz / 2;
+            for (int axis = 0; axis < 2; ++axis) {
+                const int src = axis == 0 ? W : Hh, dst = axis == 0 ? L.w : L.h;
+                std::vector<int> i0;
+                std::vector<float> a;
+                resize_tables(src, dst, i0, a);
+                std::vector<int> base(dst);
+                std::vector<float> tab((size_t)dst * taps);
+                for (int d = 0; d < dst; ++d) {
+                    base[d] = i0[d] - r;
+                    for (int j = 0; j < taps; ++j) {
+                        const float k0 = j < L.ksz ? kk[j] : 0.f, k1 = j >= 1 ? kk[j - 1] : 0.f;
+                        tab[(size_t)d * taps + j] = (1.f - a[d]) * k0 + a[d] * k1;
+                    }
+                }
+                if (axis == 0) { C_TRY(A.upload(&L.xbase, base)); C_TRY(A.upload(&L.xtab, tab)); }
+                else           { C_TRY(A.upload(&L.ybase, base)); C_TRY(A.upload(&L.ytab, tab)); }
+            }
+            C_TRY(A.alloc(&L.tmp, (size_t)F * Hh * L.pitch));
+        }
         C_TRY(A.alloc(&L.img, (size_t)F * L.plane));
         C_TRY(A.alloc(&L.R, (size_t)F * 5 * L.plane));
         C_TRY(A.alloc(&L.M[0], (size_t)B * 5 * L.plane));
@@ -309,8 +323,15 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
         C_TRY(A.upload(&L.fyi0, i0));
         C_TRY(A.upload(&L.fya, a));
     }
-    H->tmp_frame_stride = (size_t)Hh * H->lv[0].pitch;
-    C_TRY(A.alloc(&H->tmp, (size_t)F * H->tmp_frame_stride));
+    {
+        int rp = round_up(W, 4);
+        if (((rp / 4) & 1) == 0) rp += 4;   // odd word pitch: lane = row reads hit 32 distinct banks
+        H->pyr_row_pitch = rp;
+        if (H->n_levels > 1 && 32 * rp > 220 * 1024) {
+            set_error("width %d too large for the pyramid row staging (max ~7000)", W);
+            return fail(MAVD_ERR_UNSUPPORTED);
+        }
+    }
     C_TRY(poly_setup(fp.poly_n, fp.poly_sigma, H->poly));
     {
         // FarnebackUpdateFlow_GaussianBlur half kernel

@@ -54,10 +54,10 @@ struct Level {
     size_t plane = 0;   // pitch * h
     int ksz = 3;
     float sigma = 0.f;
-    // pyramid tables (full-res -> this level)
-    int* xi0 = nullptr;  float* xa = nullptr;   // [w]
-    int* yi0 = nullptr;  float* ya = nullptr;   // [h]
-    float* ktab = nullptr;                      // [ksz]
+    // pyramid tables (full-res -> this level): combined blur+resize filter of ksz+1 taps per output sample
+    int* xbase = nullptr;  float* xtab = nullptr;   // [w], [w][ksz+1]
+    int* ybase = nullptr;  float* ytab = nullptr;   // [h], [h][ksz+1]
+    float* tmp = nullptr;                           // [frames][H][pitch] horizontal pass output (levels >= 1)
     // flow upsample tables (next-coarser level -> this level)
     int* fxi0 = nullptr; float* fxa = nullptr;  // [w]
     int* fyi0 = nullptr; float* fya = nullptr;  // [h]
@@ -115,8 +115,7 @@ struct mavd_handle_s {
     mavd::Level lv[mavd::kMaxLevels];  // lv[0] = finest (k = 0)
     mavd::PolyConst poly;
     float* gauss_win = nullptr;     // [m+1] device, FarnebackUpdateFlow_GaussianBlur half kernel
-    float* tmp = nullptr;           // [frames][H][pitch_max] horizontal pyramid pass
-    size_t tmp_frame_stride = 0;
+    int pyr_row_pitch = 0;          // bytes per staged u8 row in pyr_hpass_all (word pitch odd)
     int max_frames = 0;
     size_t bytes = 0;
     // detection workspace
@@ -139,6 +138,7 @@ struct mavd_handle_s {
     // last call bookkeeping for taps
     int last_pairs = 0, last_stride = 1;
     float* last_flow0 = nullptr;
+    const uint8_t* last_frames = nullptr;
 };
 
 namespace mavd {

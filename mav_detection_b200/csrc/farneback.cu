@@ -7,8 +7,8 @@
 // 16-byte aligned (float4 / cp.async / TMA friendly).  Batch elements sit in grid.z.
 //
 // Kernels (algorithmic bytes per level pixel P):
-//   pyr_hpass / pyr_vpass  blur+resize from full-res u8, separable              2*(N0 + 4P)/2 per frame
-//   polyexp_kernel         separable polynomial expansion, smem tile            4P -> 20P
+//   pyr_hpass_all / pyr_vpass_all  blur+resize from full-res u8 for all coarse levels, two launches
+//   polyexp_kernel         separable polynomial expansion, smem tile            4P -> 20P (level 0: 1P -> 20P)
 //   matrices_init_kernel   flow upsample (x 1/pyr_scale) fused with UpdateMatrices   (8P' +) 40P -> 20P
 //   iter_kernel            box/Gaussian blur of M + 2x2 solve + UpdateMatrices   88P (28P for the last)
 #include <math.h>
@@ -33,93 +33,187 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 // ------------------------------------------------------------------------------------------------
 // Pyramid: I_l = resize(GaussianBlur(f32(img), ksz, sigma), (w_l, h_l)), always from full resolution.
-// Horizontal blur+resize (u8 -> f32 [H][w_l]) then vertical blur+resize ([H][w_l] -> [h_l][w_l]).
+// Blur and bilinear resize are both linear and separable, so per axis they collapse into ONE filter of
+// ksz+1 taps per output sample: c_j = (1-a) k_j + a k_{j-1} at source index i0 - r + j (REFLECT_101).
+// Level 0 (sigma 0 -> [1/4 1/2 1/4], identity resize) is fused into the polynomial expansion's tile
+// staging and never touches HBM.  All coarser levels share two launches:
+//   pyr_hpass_all  CTA = 32 full-res rows staged once in smem (u8); lane = row (odd word pitch, no bank
+//                  conflicts), warp = output column; writes tmp_l [H][w_l] for every level
+//   pyr_vpass_all  thread = (x, dy) of tmp_l -> img_l, x fastest
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) pyr_hpass_kernel(const uint8_t* __restrict__ frames, size_t frame_stride,
-                                                       int W, int H, const int* __restrict__ xi0,
-                                                       const float* __restrict__ xa,
-                                                       const float* __restrict__ ktab, int ksz,
-                                                       float* __restrict__ tmp, int w_l, int pitch,
-                                                       size_t tmp_stride) {
-    int dx = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (dx >= w_l) return;
-    const uint8_t* row = frames + (size_t)blockIdx.z * frame_stride + (size_t)y * W;
-    const int r = ksz >> 1;
-    const int i0 = xi0[dx];
-    const float a = xa[dx];
-    float b0 = 0.f;
-    if (i0 - r >= 0 && i0 + r + 1 < W) {
-        for (int i = 0; i < ksz; ++i) b0 += ktab[i] * (float)row[i0 + i - r];
-        float out = b0;
-        if (a != 0.f) {
-            float b1 = 0.f;
-            for (int i = 0; i < ksz; ++i) b1 += ktab[i] * (float)row[i0 + 1 + i - r];
-            out = b0 * (1.f - a) + b1 * a;
+struct PyrLevel {
+    int w, h, pitch, taps;
+    const int* xbase; const float* xtab;   // [w], [w][taps]
+    const int* ybase; const float* ytab;   // [h], [h][taps]
+    float* tmp; float* img;
+    size_t tmp_stride, img_stride;          // floats per frame
+    int vblk0, vtiles_x;                    // first vpass block of this level, tiles per row
+};
+struct PyrDesc {
+    int n;
+    PyrLevel lv[kMaxLevels];
+};
+
+__global__ void __launch_bounds__(256) pyr_hpass_all_kernel(const uint8_t* __restrict__ frames, size_t frame_stride,
+                                                           int W, int H, int rp, const __grid_constant__ PyrDesc d) {
+    extern __shared__ __align__(16) uint8_t srow[];   // [32][rp]
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const int y0 = blockIdx.x * 32;
+    const uint8_t* src = frames + (size_t)blockIdx.y * frame_stride;
+    const int nrows = min(32, H - y0);
+    if (((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+        const int w4 = W >> 2;
+        for (int idx = tid; idx < nrows * w4; idx += 256) {
+            const int rr = idx / w4, q = idx - rr * w4;
+            reinterpret_cast<uint32_t*>(srow + rr * rp)[q] =
+                __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(y0 + rr) * W) + q);
         }
-        tmp[(size_t)blockIdx.z * tmp_stride + (size_t)y * pitch + dx] = out;
-        return;
+    } else {
+        for (int idx = tid; idx < nrows * W; idx += 256) {
+            const int rr = idx / W, q = idx - rr * W;
+            srow[rr * rp + q] = src[(size_t)(y0 + rr) * W + q];
+        }
     }
-    for (int i = 0; i < ksz; ++i) b0 += ktab[i] * (float)row[reflect101(i0 + i - r, W)];
-    float out = b0;
-    if (a != 0.f) {
-        const int i1 = min(i0 + 1, W - 1);
-        float b1 = 0.f;
-        for (int i = 0; i < ksz; ++i) b1 += ktab[i] * (float)row[reflect101(i1 + i - r, W)];
-        out = b0 * (1.f - a) + b1 * a;
+    __syncthreads();
+    if (lane >= nrows) return;
+    const uint8_t* row = srow + lane * rp;
+    const int y = y0 + lane;
+    for (int l = 0; l < d.n; ++l) {
+        const PyrLevel& L = d.lv[l];
+        float* out = L.tmp + (size_t)blockIdx.y * L.tmp_stride + (size_t)y * L.pitch;
+        const int taps = L.taps;
+        for (int dx = g; dx < L.w; dx += 8) {
+            const int base = __ldg(L.xbase + dx);
+            const float* tab = L.xtab + dx * taps;
+            float acc = 0.f;
+            if (base >= 0 && base + taps <= W) {
+#pragma unroll 4
+                for (int j = 0; j < taps; ++j) acc += __ldg(tab + j) * (float)row[base + j];
+            } else {
+                for (int j = 0; j < taps; ++j) acc += __ldg(tab + j) * (float)row[reflect101(base + j, W)];
+            }
+            out[dx] = acc;
+        }
     }
-    tmp[(size_t)blockIdx.z * tmp_stride + (size_t)y * pitch + dx] = out;
 }
 
-__global__ void __launch_bounds__(128) pyr_vpass_kernel(const float* __restrict__ tmp, size_t tmp_stride, int H,
-                                                       const int* __restrict__ yi0,
-                                                       const float* __restrict__ ya,
-                                                       const float* __restrict__ ktab, int ksz,
-                                                       float* __restrict__ img, int w_l, int h_l, int pitch,
-                                                       size_t img_stride) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int dy = blockIdx.y;
-    if (x >= w_l) return;
-    const float* src = tmp + (size_t)blockIdx.z * tmp_stride + x;
-    const int r = ksz >> 1;
-    const int i0 = yi0[dy];
-    const float a = ya[dy];
-    float b0 = 0.f;
-    for (int i = 0; i < ksz; ++i) b0 += ktab[i] * src[(size_t)reflect101(i0 + i - r, H) * pitch];
-    float out = b0;
-    if (a != 0.f) {
-        const int i1 = min(i0 + 1, H - 1);
-        float b1 = 0.f;
-        for (int i = 0; i < ksz; ++i) b1 += ktab[i] * src[(size_t)reflect101(i1 + i - r, H) * pitch];
-        out = b0 * (1.f - a) + b1 * a;
+__global__ void __launch_bounds__(256) pyr_vpass_all_kernel(int H, const __grid_constant__ PyrDesc d) {
+    int l = 0;
+    while (l + 1 < d.n && (int)blockIdx.x >= d.lv[l + 1].vblk0) ++l;
+    const PyrLevel& L = d.lv[l];
+    const int b = blockIdx.x - L.vblk0;
+    const int bx = b % L.vtiles_x, by = b / L.vtiles_x;
+    const int x = bx * 64 + (threadIdx.x & 63), dy = by * 4 + (threadIdx.x >> 6);
+    if (x >= L.w || dy >= L.h) return;
+    const float* src = L.tmp + (size_t)blockIdx.y * L.tmp_stride + x;
+    const int base = __ldg(L.ybase + dy);
+    const float* tab = L.ytab + dy * L.taps;
+    const int taps = L.taps, pitch = L.pitch;
+    float acc = 0.f;
+    if (base >= 0 && base + taps <= H) {
+#pragma unroll 4
+        for (int j = 0; j < taps; ++j) acc += __ldg(tab + j) * src[(size_t)(base + j) * pitch];
+    } else {
+        for (int j = 0; j < taps; ++j) acc += __ldg(tab + j) * src[(size_t)reflect101(base + j, H) * pitch];
     }
-    img[(size_t)blockIdx.z * img_stride + (size_t)dy * pitch + x] = out;
+    L.img[(size_t)blockIdx.y * L.img_stride + (size_t)dy * pitch + x] = acc;
+}
+
+// level-0 image on its own (tests / taps only): 3x3 [1/4 1/2 1/4] blur of the u8 frame, REFLECT_101
+__global__ void pyr0_kernel(const uint8_t* __restrict__ frame, int W, int H, float* __restrict__ img, int pitch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const float k[3] = {0.25f, 0.5f, 0.25f};
+    float acc = 0.f;
+    for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx)
+            acc += k[dy] * k[dx] * (float)frame[(size_t)reflect101(y + dy - 1, H) * W + reflect101(x + dx - 1, W)];
+    img[(size_t)y * pitch + x] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Polynomial expansion (FarnebackPolyExp).  64x32 output tile, halo 8 (poly_n <= 8), 256 threads.
+//   staging         : float level image, or (U8) the raw u8 frame with the level-0 3x3 blur applied on
+//                     the fly — all its products and sums are exact in float32, so the staged values are
+//                     bit-identical to a separately blurred image
 //   vertical pass   : thread = (column, 4 rows)  -> t0,t1,t2 in smem
 //   horizontal pass : thread = (row, 4 columns)  -> float4 reads, float4 stores per plane
 // ------------------------------------------------------------------------------------------------
 constexpr int PE_TX = 64, PE_TY = 32, PE_H = 8, PE_RW = PE_TX + 2 * PE_H;  // 80
 
-__global__ void __launch_bounds__(256) polyexp_kernel(const float* __restrict__ img, size_t img_stride, int w,
-                                                     int h, int pitch, PolyConst pc, float* __restrict__ R,
-                                                     size_t plane) {
+__device__ __forceinline__ void blur3_row4(const uint8_t* __restrict__ p, float (&hv)[4]) {
+    // p is 4-byte aligned and points 4 bytes left of the first of four output cells
+    const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(p) + 1);
+    const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(p) + 2);
+    const float v3 = (float)(a >> 24), v4 = (float)(b & 255u), v5 = (float)((b >> 8) & 255u),
+                v6 = (float)((b >> 16) & 255u), v7 = (float)(b >> 24), v8 = (float)(c & 255u);
+    hv[0] = 0.25f * v3 + 0.5f * v4 + 0.25f * v5;
+    hv[1] = 0.25f * v4 + 0.5f * v5 + 0.25f * v6;
+    hv[2] = 0.25f * v5 + 0.5f * v6 + 0.25f * v7;
+    hv[3] = 0.25f * v6 + 0.5f * v7 + 0.25f * v8;
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(256) polyexp_kernel(const void* __restrict__ src_base, size_t src_stride, int w,
+                                                     int h, int pitch, int u8_aligned, PolyConst pc,
+                                                     float* __restrict__ R, size_t plane) {
     __shared__ __align__(16) float raw[(PE_TY + 2 * PE_H) * PE_RW];
     __shared__ __align__(16) float t[3][PE_TY * PE_RW];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * PE_TX, y0 = blockIdx.y * PE_TY;
-    const float* src = img + (size_t)blockIdx.z * img_stride;
     const int n = pc.n;
 
     // stage rows y0-n .. y0+TY+n-1 (replicate), columns x0-8 .. x0+TX+8-1 (replicate)
     const int rows = PE_TY + 2 * n;
-    for (int idx = tid; idx < rows * PE_RW; idx += 256) {
-        int rr = idx / PE_RW, cc = idx - rr * PE_RW;
-        int gy = clampi(y0 - n + rr, 0, h - 1);
-        int gx = clampi(x0 - PE_H + cc, 0, w - 1);
-        raw[(rr + PE_H - n) * PE_RW + cc] = src[(size_t)gy * pitch + gx];
+    if (!U8) {
+        const float* src = reinterpret_cast<const float*>(src_base) + (size_t)blockIdx.z * src_stride;
+        for (int idx = tid; idx < rows * PE_RW; idx += 256) {
+            int rr = idx / PE_RW, cc = idx - rr * PE_RW;
+            int gy = clampi(y0 - n + rr, 0, h - 1);
+            int gx = clampi(x0 - PE_H + cc, 0, w - 1);
+            raw[(rr + PE_H - n) * PE_RW + cc] = src[(size_t)gy * pitch + gx];
+        }
+    } else {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base) + (size_t)blockIdx.z * src_stride;
+        const bool fast = u8_aligned && (x0 - PE_H - 4 >= 0) && (x0 + PE_TX + PE_H + 4 <= w) && (y0 - n - 1 >= 0) &&
+                          (y0 + PE_TY + n + 1 <= h);
+        if (fast) {
+            // 20 groups of 4 cells x 12 row segments; each thread marches down its rows with a 3-row window
+            const int g = tid % 20, seg = tid / 20;
+            const int rps = (rows + 11) / 12;
+            const int r0 = seg * rps, r1 = min(rows, r0 + rps);
+            if (seg < 12 && r0 < r1) {
+                const uint8_t* p = src + (size_t)(y0 - n + r0 - 1) * w + (x0 - PE_H + 4 * g - 4);
+                float hp[4], hc[4], hn[4];
+                blur3_row4(p, hp);
+                blur3_row4(p + w, hc);
+                for (int rr = r0; rr < r1; ++rr) {
+                    blur3_row4(p + (size_t)(rr - r0 + 2) * w, hn);
+                    float4 v;
+                    v.x = 0.25f * hp[0] + 0.5f * hc[0] + 0.25f * hn[0];
+                    v.y = 0.25f * hp[1] + 0.5f * hc[1] + 0.25f * hn[1];
+                    v.z = 0.25f * hp[2] + 0.5f * hc[2] + 0.25f * hn[2];
+                    v.w = 0.25f * hp[3] + 0.5f * hc[3] + 0.25f * hn[3];
+                    *reinterpret_cast<float4*>(&raw[(rr + PE_H - n) * PE_RW + 4 * g]) = v;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { hp[i] = hc[i]; hc[i] = hn[i]; }
+                }
+            }
+        } else {
+            for (int idx = tid; idx < rows * PE_RW; idx += 256) {
+                int rr = idx / PE_RW, cc = idx - rr * PE_RW;
+                int gy = clampi(y0 - n + rr, 0, h - 1);
+                int gx = clampi(x0 - PE_H + cc, 0, w - 1);
+                const int ym = reflect101(gy - 1, h), yp = reflect101(gy + 1, h);
+                const int xm = reflect101(gx - 1, w), xp = reflect101(gx + 1, w);
+                const uint8_t *q0 = src + (size_t)ym * w, *q1 = src + (size_t)gy * w, *q2 = src + (size_t)yp * w;
+                const float h0 = 0.25f * q0[xm] + 0.5f * q0[gx] + 0.25f * q0[xp];
+                const float h1 = 0.25f * q1[xm] + 0.5f * q1[gx] + 0.25f * q1[xp];
+                const float h2 = 0.25f * q2[xm] + 0.5f * q2[gx] + 0.25f * q2[xp];
+                raw[(rr + PE_H - n) * PE_RW + cc] = 0.25f * h0 + 0.5f * h1 + 0.25f * h2;
+            }
+        }
     }
     __syncthreads();
 
@@ -737,25 +831,45 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
     const int hx = round_up(m, 4);
     const size_t frame_bytes = (size_t)W * Hh;
 
+    // pyramid images of every coarser level for all frames: two launches
+    if (H->n_levels > 1) {
+        ProfScope ps(&H->prof, MAVD_PROF_PYRAMID, s);
+        static bool configured = false;
+        if (!configured) {
+            MAVD_CUDA(cudaFuncSetAttribute(pyr_hpass_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            configured = true;
+        }
+        PyrDesc d;
+        d.n = H->n_levels - 1;
+        int vb = 0;
+        for (int li = 1; li < H->n_levels; ++li) {
+            const Level& L = H->lv[li];
+            PyrLevel& P = d.lv[li - 1];
+            P.w = L.w; P.h = L.h; P.pitch = L.pitch; P.taps = L.ksz + 1;
+            P.xbase = L.xbase; P.xtab = L.xtab; P.ybase = L.ybase; P.ytab = L.ytab;
+            P.tmp = L.tmp; P.img = L.img; P.tmp_stride = (size_t)Hh * L.pitch; P.img_stride = L.plane;
+            P.vblk0 = vb; P.vtiles_x = ceil_div(L.w, 64);
+            vb += P.vtiles_x * ceil_div(L.h, 4);
+        }
+        pyr_hpass_all_kernel<<<dim3(ceil_div(Hh, 32), n_frames), 256, 32 * H->pyr_row_pitch, s>>>(
+            d_frames, frame_bytes, W, Hh, H->pyr_row_pitch, d);
+        MAVD_LAUNCHED();
+        pyr_vpass_all_kernel<<<dim3(vb, n_frames), 256, 0, s>>>(Hh, d);
+        MAVD_LAUNCHED();
+    }
     for (int li = H->n_levels - 1; li >= 0; --li) {
         Level& L = H->lv[li];
-        // pyramid images for all frames
-        {
-            ProfScope ps(&H->prof, MAVD_PROF_PYRAMID, s);
-            dim3 g1(ceil_div(L.w, 128), Hh, n_frames);
-            pyr_hpass_kernel<<<g1, 128, 0, s>>>(d_frames, frame_bytes, W, Hh, L.xi0, L.xa, L.ktab, L.ksz, H->tmp,
-                                                L.w, L.pitch, H->tmp_frame_stride);
-            MAVD_LAUNCHED();
-            dim3 g2(ceil_div(L.w, 128), L.h, n_frames);
-            pyr_vpass_kernel<<<g2, 128, 0, s>>>(H->tmp, H->tmp_frame_stride, Hh, L.yi0, L.ya, L.ktab, L.ksz, L.img,
-                                                L.w, L.h, L.pitch, L.plane);
-            MAVD_LAUNCHED();
-        }
-        // polynomial expansion for all frames
+        // polynomial expansion for all frames (level 0 reads the u8 frames and blurs on the fly)
         {
             ProfScope ps(&H->prof, MAVD_PROF_POLYEXP, s);
             dim3 g(ceil_div(L.w, PE_TX), ceil_div(L.h, PE_TY), n_frames);
-            polyexp_kernel<<<g, 256, 0, s>>>(L.img, L.plane, L.w, L.h, L.pitch, H->poly, L.R, L.plane);
+            if (li == 0) {
+                const int aligned = ((reinterpret_cast<uintptr_t>(d_frames) & 3) == 0 && (W & 3) == 0) ? 1 : 0;
+                polyexp_kernel<true><<<g, 256, 0, s>>>(d_frames, frame_bytes, L.w, L.h, L.pitch, aligned, H->poly, L.R,
+                                                       L.plane);
+            } else {
+                polyexp_kernel<false><<<g, 256, 0, s>>>(L.img, L.plane, L.w, L.h, L.pitch, 0, H->poly, L.R, L.plane);
+            }
             MAVD_LAUNCHED();
         }
         // matrices from the upsampled coarser flow
@@ -809,6 +923,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
     H->last_pairs = n_pairs;
     H->last_stride = pair_stride;
     H->last_flow0 = d_flow;
+    H->last_frames = d_frames;
     return MAVD_OK;
 }
 
@@ -818,6 +933,12 @@ int farneback_tap(mavd_handle H, int kind, int level, int index, float* d_out, c
     dim3 g(ceil_div(L.w, 128), L.h);
     switch (kind) {
         case 0:
+            if (level == 0) {
+                MAVD_REQUIRE(H->last_frames != nullptr, MAVD_ERR_INVALID, "tap: no farneback call yet");
+                pyr0_kernel<<<g, 128, 0, s>>>(H->last_frames + (size_t)index * L.w * L.h, L.w, L.h,
+                                              L.img + (size_t)index * L.plane, L.pitch);
+                MAVD_LAUNCHED();
+            }
             tap_planar_kernel<<<g, 128, 0, s>>>(L.img + (size_t)index * L.plane, L.w, L.h, L.pitch, L.plane, 1, d_out);
             break;
         case 1:

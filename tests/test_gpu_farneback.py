@@ -25,6 +25,7 @@ def _run_pair(prev, nxt, params):
     frames = torch.from_numpy(np.stack([prev, nxt])).cuda()
     flow = eng.farneback(frames, pair_stride=2)
     torch.cuda.synchronize()
+    eng._keep_alive = (frames, flow)     # the level-0 taps read the caller's buffers of the last call
     return eng, flow[0].cpu().numpy()
 
 
