@@ -42,6 +42,7 @@ enum {
 #define MAVD_N_SAMPLE_PAIRS 1000  /* focus_of_expansion.py:65 (N) */
 #define MAVD_SAMPLES_PER_FRAME (4 * MAVD_N_SAMPLE_PAIRS) /* 2000 row draws then 2000 column draws */
 #define MAVD_MAX_BOXES 32         /* component boxes kept per frame record */
+#define MAVD_HOST_SLOTS 3         /* batches that may be in flight through mavd_submit_host */
 
 /* Arguments of cv2.calcOpticalFlowFarneback as called at src/farneback.py:76-80. */
 typedef struct mavd_farneback_params {
@@ -149,12 +150,31 @@ int mavd_foe(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_im
              const mavd_detect_params* prm, const int32_t* d_samples, double* d_foe,
              int32_t* d_n_intersections, void* stream);
 
+/* FocusOfExpansion.get_FOE_dense(flow_uv) taken literally (src/focus_of_expansion.py:56-86): the flow is
+ * used as given — float32 (flow_is_f64 == 0) or float64 (an already derotated field) — no IMU. */
+int mavd_foe_dense(mavd_handle h, const void* d_flow, int32_t flow_is_f64, int32_t n,
+                   const mavd_detect_params* prm, const int32_t* d_samples, double* d_foe,
+                   int32_t* d_n_intersections, void* stream);
+
+/* FocusOfExpansion.ransac(estimates) (src/focus_of_expansion.py:32-54): d_estimates is (k, 2) float64;
+ * d_foe receives the winning estimate, (0, 0) when no estimate has another one within the threshold. */
+int mavd_ransac(mavd_handle h, const double* d_estimates, int32_t k, double ransac_threshold, double* d_foe,
+                void* stream);
+
+/* FocusOfExpansion.get_phi(flow, FoE) (src/focus_of_expansion.py:150-184) on the flow as given: d_phi has
+ * the flow's dtype, (n, H, W) dense.  d_max_phi (nullable, n float64) is the max_flow side effect (:179). */
+int mavd_get_phi(mavd_handle h, const void* d_flow, int32_t flow_is_f64, int32_t n, const double* d_foe,
+                 void* d_phi, double* d_max_phi, void* stream);
+
 /* ---- stage 3: FocusOfExpansion.get_phi + mask block — focus_of_expansion.py:150-184,
  *      processor.py:307,333-341 (+ the reductions of processor.py:343-362 when d_seg is given) ----
  * d_sky / d_seg: (H, W) uint8 per frame (stride 0 = one image shared by all frames), nullable.
  * d_phi: nullable; float64 (H, W) per frame when imu.derotate != 0, float32 otherwise (the dtype
  * the reference returns); the buffer is always n * H * W * 8 bytes, float32 results use the front.
- * d_total / d_fixed: (H, W) uint8 0/1 masks (total_mask, estimate_fixed); either may be NULL. */
+ * d_total / d_fixed: (H, W) uint8 0/1 masks (total_mask, estimate_fixed); either may be NULL.
+ * When d_phi is NULL the masks are pre-decided from a float32 estimate with guard bands and only
+ * borderline pixels take the float64 path (results stay bit-exact); stats.max_phi is then -1 for the
+ * derotated frames (not evaluated). */
 int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu,
                         const mavd_detect_params* prm, const double* d_foe,
                         const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg, int64_t seg_stride,
@@ -163,13 +183,22 @@ int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mav
 
 /* ---- stage 4 (not in the reference): 8-connected components of a mask ----
  * Labels are numbered 1..n by first appearance in a raster scan (0 = background).
- * d_boxes: n x max_boxes x 5 int32 [left, top, width, height, area]; d_n_labels: n int32 (true count). */
+ * d_boxes: n x max_boxes x 5 int32 [left, top, width, height, area]; d_n_labels: n int32 (true count).
+ * d_labels may be NULL when only the count and the boxes are wanted. */
 int mavd_ccl(mavd_handle h, const uint8_t* d_mask, int32_t n, int32_t* d_labels, int32_t* d_boxes,
              int32_t max_boxes, int32_t* d_n_labels, void* stream);
 
+/* ---- detection from a given flow field, device buffers: derotate -> FoE -> phi/masks -> components ----
+ * One iteration of Processor.run_detection (src/processor.py:305-362) per frame, starting from the
+ * flow that Dataset.get_flow_uv returns (src/datasets/dataset.py:205-212).  d_total_out / d_fixed_out
+ * nullable.  d_records: n mavd_frame_record. */
+int mavd_detect(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu,
+                const mavd_detect_params* prm, const int32_t* d_samples, const uint8_t* d_sky, int64_t sky_stride,
+                const uint8_t* d_seg, int64_t seg_stride, uint8_t* d_total_out, uint8_t* d_fixed_out,
+                mavd_frame_record* d_records, void* stream);
+
 /* ---- whole path, device buffers: flow -> derotate -> FoE -> phi/masks -> components ----
- * Equivalent to one iteration of Processor.run_detection (src/processor.py:305-362) per pair.
- * d_flow_out / d_fixed_out / d_total_out nullable.  d_records: n_pairs mavd_frame_record. */
+ * mavd_farneback followed by mavd_detect.  d_flow_out / d_fixed_out / d_total_out nullable. */
 int mavd_process(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride,
                  const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* d_samples,
                  const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg, int64_t seg_stride,
@@ -179,11 +208,28 @@ int mavd_process(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_
 /* ---- whole path, HOST buffers (the end-to-end call): copies frames/samples/sky/seg in, runs
  * mavd_process, copies the records (and, when non-NULL, estimate_fixed masks and flow) back.
  * Host buffers should be pinned for the copies to be asynchronous; the call returns after the
- * results have landed (it synchronises `stream`). */
+ * results have landed (it synchronises). */
 int mavd_process_host(mavd_handle h, const uint8_t* h_frames, int32_t n_pairs, int32_t pair_stride,
                       const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
                       const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
                       float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream);
+
+/* The same, split into an asynchronous submit and a wait so that a caller can keep up to
+ * MAVD_HOST_SLOTS batches in flight: batch k+1's host->device copies run on a copy stream while batch k
+ * computes on `stream` and batch k-1's results return on a third stream.  `slot` in [0, MAVD_HOST_SLOTS)
+ * names the staging buffers used; a slot must be waited on before it is submitted again.  All host
+ * buffers of a submit must stay valid (and unmodified) until its wait returns. */
+int mavd_submit_host(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32_t n_pairs, int32_t pair_stride,
+                     const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
+                     const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
+                     float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream);
+int mavd_wait_host(mavd_handle h, int32_t slot);
+
+/* Detection from a HOST flow field (n x H x W x 2 float32), the Dataset.get_flow_uv seam end to end. */
+int mavd_detect_host(mavd_handle h, const float* h_flow, int32_t n, const mavd_imu* h_imu,
+                     const mavd_detect_params* prm, const int32_t* h_samples, const uint8_t* h_sky,
+                     int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride, uint8_t* h_fixed_out,
+                     mavd_frame_record* h_records, void* stream);
 
 /* ---- optional per-kernel-class device timing (CUDA events on the launching stream) ---- */
 enum {
@@ -208,6 +254,9 @@ int mavd_profile_read(mavd_handle h, mavd_profile* out); /* waits for the record
 /* Tests: route the Farneback iterations through the generic (non-TMA) kernel, which production uses only
  * for Gaussian windows and for winsize/2 outside 5..8. */
 int mavd_debug_force_generic_iteration(mavd_handle h, int32_t on);
+
+/* Tests: evaluate every pixel of the residual stage in float64 even when phi is not requested. */
+int mavd_debug_force_exact_residual(mavd_handle h, int32_t on);
 
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t mavd_launch_count(void);

@@ -13,6 +13,7 @@ MAVD_OK, MAVD_ERR_INVALID, MAVD_ERR_CUDA, MAVD_ERR_UNSUPPORTED, MAVD_ERR_NOMEM =
 N_SAMPLE_PAIRS = 1000
 SAMPLES_PER_FRAME = 4 * N_SAMPLE_PAIRS
 MAX_BOXES = 32
+HOST_SLOTS = 3
 OPTFLOW_FARNEBACK_GAUSSIAN = 256
 
 
@@ -73,6 +74,9 @@ SIGNATURES = {
     'mavd_farneback_tap': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'mavd_derotate': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), _P, _P]),
     'mavd_foe': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P, _P, _P, _P]),
+    'mavd_foe_dense': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(DetectParams), _P, _P, _P, _P]),
+    'mavd_ransac': (C.c_int, [_P, _P, C.c_int32, C.c_double, _P, _P]),
+    'mavd_get_phi': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     'mavd_residual_masks': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
                                       _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P]),
     'mavd_ccl': (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P]),
@@ -80,8 +84,16 @@ SIGNATURES = {
                                _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P]),
     'mavd_process_host': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
                                     _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
+    'mavd_detect': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P, _P, C.c_int64, _P, C.c_int64,
+                              _P, _P, _P, _P]),
+    'mavd_submit_host': (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
+                                   _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
+    'mavd_wait_host': (C.c_int, [_P, C.c_int32]),
+    'mavd_detect_host': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P, _P, C.c_int64, _P,
+                                   C.c_int64, _P, _P, _P]),
     'mavd_launch_count': (C.c_int64, []),
     'mavd_debug_force_generic_iteration': (C.c_int, [_P, C.c_int32]),
+    'mavd_debug_force_exact_residual': (C.c_int, [_P, C.c_int32]),
     'mavd_profile_enable': (C.c_int, [_P, C.c_int32]),
     'mavd_profile_read': (C.c_int, [_P, C.POINTER(Profile)]),
 }

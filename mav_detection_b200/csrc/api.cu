@@ -172,6 +172,20 @@ struct Arena {
     }
 };
 
+static int alloc_slot(Arena& A, mavd_handle_s::HostSlot& S, int F, int B, size_t npx) {
+    int rc;
+    if ((rc = A.alloc(&S.d_frames, (size_t)F * npx)) != MAVD_OK) return rc;
+    if ((rc = A.alloc(&S.d_samples, (size_t)B * MAVD_SAMPLES_PER_FRAME)) != MAVD_OK) return rc;
+    if ((rc = A.alloc(&S.d_sky, B * npx)) != MAVD_OK) return rc;
+    if ((rc = A.alloc(&S.d_seg, B * npx)) != MAVD_OK) return rc;
+    if ((rc = A.alloc(&S.d_records, (size_t)B)) != MAVD_OK) return rc;
+    if ((rc = A.alloc(&S.d_fixed, B * npx)) != MAVD_OK) return rc;
+    MAVD_CUDA(cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming));
+    MAVD_CUDA(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+    MAVD_CUDA(cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming));
+    return MAVD_OK;
+}
+
 }  // namespace mavd
 
 using namespace mavd;
@@ -356,11 +370,20 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
     C_TRY(A.alloc(&H->d_total, B * npx));
     C_TRY(A.alloc(&H->d_fixed, B * npx));
     C_TRY(A.alloc(&H->d_flow, B * npx * 2));
-    C_TRY(A.alloc(&H->d_frames, (size_t)F * npx));
-    C_TRY(A.alloc(&H->d_samples, (size_t)B * MAVD_SAMPLES_PER_FRAME));
-    C_TRY(A.alloc(&H->d_sky, B * npx));
-    C_TRY(A.alloc(&H->d_seg, B * npx));
-    C_TRY(A.alloc(&H->d_records, B));
+    for (int k = 0; k < MAVD_HOST_SLOTS; ++k) {
+        mavd_handle_s::HostSlot& S = H->slot[k];
+        // slot 0 is always there (mavd_process_host); further slots appear on their first submit
+        if (k == 0) C_TRY(alloc_slot(A, S, F, B, npx));
+    }
+    C_TRY(A.alloc(&H->d_stats_tmp, B));
+    {
+        // detector.py:90-91 evaluated with host IEEE doubles: division, subtraction, exact doubling
+        std::vector<double> xn(W), yn(Hh);
+        for (int x = 0; x < W; ++x) { volatile double q = (double)x / (double)W; volatile double d = q - 0.5; xn[x] = -d * 2.0; }
+        for (int y = 0; y < Hh; ++y) { volatile double q = (double)y / (double)Hh; volatile double d = q - 0.5; yn[y] = -d * 2.0; }
+        C_TRY(A.upload(&H->d_xn, xn));
+        C_TRY(A.upload(&H->d_yn, yn));
+    }
     H->bytes = A.bytes;
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -378,6 +401,13 @@ int mavd_destroy(mavd_handle h) {
     cudaSetDevice(H->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : H->arena.ptrs) cudaFree(p);
+    for (auto& S : H->slot) {
+        if (S.ev_in) cudaEventDestroy(S.ev_in);
+        if (S.ev_done) cudaEventDestroy(S.ev_done);
+        if (S.ev_out) cudaEventDestroy(S.ev_out);
+    }
+    if (H->s_in) cudaStreamDestroy(H->s_in);
+    if (H->s_out) cudaStreamDestroy(H->s_out);
     for (auto& r : H->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : H->prof.pool) cudaEventDestroy(e);
     delete H;
@@ -494,8 +524,46 @@ int mavd_foe(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_im
     mavd_detect_params p;
     if (prm) p = *prm; else mavd_default_detect_params(&p);
     TRY(upload_imu(h, h_imu, n, (cudaStream_t)stream, nullptr, nullptr));
-    return foe_run(h, d_flow, n, h->d_imu, p, d_samples, d_foe, d_n_intersections ? d_n_intersections : h->d_ninter,
+    return foe_run(h, d_flow, 0, n, h->d_imu, p, d_samples, d_foe, d_n_intersections ? d_n_intersections : h->d_ninter,
                    (cudaStream_t)stream);
+}
+
+int mavd_foe_dense(mavd_handle h, const void* d_flow, int32_t flow_is_f64, int32_t n, const mavd_detect_params* prm,
+                   const int32_t* d_samples, double* d_foe, int32_t* d_n_intersections, void* stream) {
+    TRY(check_batch(h, n, "foe_dense"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_flow && d_samples && d_foe, MAVD_ERR_INVALID, "foe_dense: NULL buffer");
+    mavd_detect_params p;
+    if (prm) p = *prm; else mavd_default_detect_params(&p);
+    return foe_run(h, d_flow, flow_is_f64 ? 2 : 1, n, nullptr, p, d_samples, d_foe,
+                   d_n_intersections ? d_n_intersections : h->d_ninter, (cudaStream_t)stream);
+}
+
+int mavd_ransac(mavd_handle h, const double* d_estimates, int32_t k, double ransac_threshold, double* d_foe,
+                void* stream) {
+    MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "ransac: handle is NULL");
+    MAVD_REQUIRE(k >= 0 && d_foe && (k == 0 || d_estimates), MAVD_ERR_INVALID, "ransac: bad arguments");
+    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    return ransac_run(d_estimates, k, ransac_threshold, d_foe, (cudaStream_t)stream);
+}
+
+int mavd_get_phi(mavd_handle h, const void* d_flow, int32_t flow_is_f64, int32_t n, const double* d_foe, void* d_phi,
+                 double* d_max_phi, void* stream) {
+    TRY(check_batch(h, n, "get_phi"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_flow && d_foe && d_phi, MAVD_ERR_INVALID, "get_phi: NULL buffer");
+    mavd_detect_params p;
+    mavd_default_detect_params(&p);
+    TRY(residual_run(h, d_flow, flow_is_f64 ? 2 : 1, n, nullptr, p, d_foe, nullptr, 0, nullptr, 0, d_phi, nullptr, nullptr,
+                     h->d_stats_tmp, sizeof(mavd_frame_stats), 0, 0, (cudaStream_t)stream));
+    if (d_max_phi) TRY(gather_max_phi_run(h->d_stats_tmp, n, d_max_phi, (cudaStream_t)stream));
+    return MAVD_OK;
+}
+
+int mavd_debug_force_exact_residual(mavd_handle h, int32_t on) {
+    MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "handle is NULL");
+    h->force_exact_residual = on != 0;
+    return MAVD_OK;
 }
 
 int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu,
@@ -509,7 +577,7 @@ int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mav
     if (prm) p = *prm; else mavd_default_detect_params(&p);
     int n64 = 0, n32 = 0;
     TRY(upload_imu(h, h_imu, n, (cudaStream_t)stream, &n64, &n32));
-    return residual_run(h, d_flow, n, h->d_imu, p, d_foe, d_sky, sky_stride, d_seg, seg_stride, d_phi, d_total, d_fixed,
+    return residual_run(h, d_flow, 0, n, h->d_imu, p, d_foe, d_sky, sky_stride, d_seg, seg_stride, d_phi, d_total, d_fixed,
                         d_stats, sizeof(mavd_frame_stats), n64 > 0, n32 > 0, (cudaStream_t)stream);
 }
 
@@ -517,7 +585,7 @@ int mavd_ccl(mavd_handle h, const uint8_t* d_mask, int32_t n, int32_t* d_labels,
              int32_t* d_n_labels, void* stream) {
     TRY(check_batch(h, n, "ccl"));
     if (n == 0) return MAVD_OK;
-    MAVD_REQUIRE(d_mask && d_labels && d_n_labels, MAVD_ERR_INVALID, "ccl: NULL buffer");
+    MAVD_REQUIRE(d_mask && d_n_labels, MAVD_ERR_INVALID, "ccl: NULL buffer");
     MAVD_REQUIRE(max_boxes >= 0, MAVD_ERR_INVALID, "ccl: max_boxes < 0");
     return ccl_run(h, d_mask, n, d_labels, max_boxes > 0 ? d_boxes : nullptr, (size_t)max_boxes * 5, max_boxes,
                    d_n_labels, sizeof(int32_t), (cudaStream_t)stream);
@@ -529,6 +597,39 @@ __global__ void records_fill_kernel(mavd_frame_record* rec, const double* foe, c
     rec[f].foe[0] = foe[2 * f];
     rec[f].foe[1] = foe[2 * f + 1];
     rec[f].n_intersections = ninter[f];
+}
+
+static int detect_run(mavd_handle h, const float* flow, int n, const mavd_detect_params& p, int n64, int n32,
+                      const int32_t* d_samples, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
+                      int64_t seg_stride, uint8_t* d_total_out, uint8_t* fixed, mavd_frame_record* d_records,
+                      cudaStream_t s) {
+    TRY(foe_run(h, flow, 0, n, h->d_imu, p, d_samples, h->d_foe, h->d_ninter, s));
+    char* stats0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, stats);
+    TRY(residual_run(h, flow, 0, n, h->d_imu, p, h->d_foe, d_sky, sky_stride, d_seg, seg_stride, nullptr, d_total_out,
+                     fixed, reinterpret_cast<mavd_frame_stats*>(stats0), sizeof(mavd_frame_record), n64 > 0, n32 > 0, s));
+    int32_t* boxes0 = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, boxes));
+    char* nl0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, n_labels);
+    TRY(ccl_run(h, fixed, n, nullptr, boxes0, sizeof(mavd_frame_record) / sizeof(int32_t), MAVD_MAX_BOXES,
+                reinterpret_cast<int32_t*>(nl0), sizeof(mavd_frame_record), s));
+    records_fill_kernel<<<ceil_div(n, 128), 128, 0, s>>>(d_records, h->d_foe, h->d_ninter, n);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+int mavd_detect(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,
+                const int32_t* d_samples, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
+                int64_t seg_stride, uint8_t* d_total_out, uint8_t* d_fixed_out, mavd_frame_record* d_records,
+                void* stream) {
+    TRY(check_batch(h, n, "detect"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_flow && d_samples && d_records, MAVD_ERR_INVALID, "detect: NULL buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    mavd_detect_params p;
+    if (prm) p = *prm; else mavd_default_detect_params(&p);
+    int n64 = 0, n32 = 0;
+    TRY(upload_imu(h, h_imu, n, s, &n64, &n32));
+    return detect_run(h, d_flow, n, p, n64, n32, d_samples, d_sky, sky_stride, d_seg, seg_stride, d_total_out,
+                      d_fixed_out ? d_fixed_out : h->d_fixed, d_records, s);
 }
 
 int mavd_process(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride, const mavd_imu* h_imu,
@@ -543,21 +644,77 @@ int mavd_process(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_
     mavd_detect_params p;
     if (prm) p = *prm; else mavd_default_detect_params(&p);
     float* flow = d_flow_out ? d_flow_out : h->d_flow;
-    uint8_t* fixed = d_fixed_out ? d_fixed_out : h->d_fixed;
     int n64 = 0, n32 = 0;
     TRY(upload_imu(h, h_imu, n_pairs, s, &n64, &n32));
     TRY(farneback_run(h, d_frames, n_pairs, pair_stride, flow, s));
-    TRY(foe_run(h, flow, n_pairs, h->d_imu, p, d_samples, h->d_foe, h->d_ninter, s));
-    char* stats0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, stats);
-    TRY(residual_run(h, flow, n_pairs, h->d_imu, p, h->d_foe, d_sky, sky_stride, d_seg, seg_stride, nullptr,
-                     d_total_out, fixed, reinterpret_cast<mavd_frame_stats*>(stats0), sizeof(mavd_frame_record),
-                     n64 > 0, n32 > 0, s));
-    int32_t* boxes0 = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, boxes));
-    char* nl0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, n_labels);
-    TRY(ccl_run(h, fixed, n_pairs, h->d_labels, boxes0, sizeof(mavd_frame_record) / sizeof(int32_t), MAVD_MAX_BOXES,
-                reinterpret_cast<int32_t*>(nl0), sizeof(mavd_frame_record), s));
-    records_fill_kernel<<<ceil_div(n_pairs, 128), 128, 0, s>>>(d_records, h->d_foe, h->d_ninter, n_pairs);
-    MAVD_LAUNCHED();
+    return detect_run(h, flow, n_pairs, p, n64, n32, d_samples, d_sky, sky_stride, d_seg, seg_stride, d_total_out,
+                      d_fixed_out ? d_fixed_out : h->d_fixed, d_records, s);
+}
+
+static int ensure_slot(mavd_handle h, int slot, bool want_flow_out, bool want_flow_in) {
+    mavd_handle_full* H = static_cast<mavd_handle_full*>(h);
+    mavd_handle_s::HostSlot& S = H->slot[slot];
+    const size_t npx = (size_t)h->cfg.width * h->cfg.height;
+    const int B = h->cfg.max_pairs;
+    if (!S.d_frames) TRY(alloc_slot(H->arena, S, h->max_frames, B, npx));
+    if (want_flow_out && !S.d_flow) TRY(H->arena.alloc(&S.d_flow, B * npx * 2));
+    if (want_flow_in && !S.d_flow_in) TRY(H->arena.alloc(&S.d_flow_in, B * npx * 2));
+    if (!H->s_in) MAVD_CUDA(cudaStreamCreateWithFlags(&H->s_in, cudaStreamNonBlocking));
+    if (!H->s_out) MAVD_CUDA(cudaStreamCreateWithFlags(&H->s_out, cudaStreamNonBlocking));
+    H->bytes = H->arena.bytes;
+    return MAVD_OK;
+}
+
+int mavd_submit_host(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32_t n_pairs, int32_t pair_stride,
+                     const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
+                     const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
+                     float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+    TRY(check_batch(h, n_pairs, "submit_host"));
+    MAVD_REQUIRE(slot >= 0 && slot < MAVD_HOST_SLOTS, MAVD_ERR_INVALID, "slot %d out of range", slot);
+    MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
+    MAVD_REQUIRE(n_pairs >= 1, MAVD_ERR_INVALID, "submit_host: empty batch");
+    MAVD_REQUIRE(h_frames && h_samples && h_records, MAVD_ERR_INVALID, "submit_host: NULL buffer");
+    const size_t npx = (size_t)h->cfg.width * h->cfg.height;
+    MAVD_REQUIRE(sky_stride == 0 || sky_stride == (int64_t)npx, MAVD_ERR_INVALID, "sky_stride must be 0 or H*W");
+    MAVD_REQUIRE(seg_stride == 0 || seg_stride == (int64_t)npx, MAVD_ERR_INVALID, "seg_stride must be 0 or H*W");
+    TRY(ensure_slot(h, slot, h_flow_out != nullptr, false));
+    mavd_handle_s::HostSlot& S = h->slot[slot];
+    MAVD_REQUIRE(!S.busy, MAVD_ERR_INVALID, "slot %d is still in flight: call mavd_wait_host first", slot);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n_frames = pair_stride == 1 ? n_pairs + 1 : 2 * n_pairs;
+    // copy-in stream
+    MAVD_CUDA(cudaMemcpyAsync(S.d_frames, h_frames, npx * n_frames, cudaMemcpyHostToDevice, h->s_in));
+    MAVD_CUDA(cudaMemcpyAsync(S.d_samples, h_samples, sizeof(int32_t) * MAVD_SAMPLES_PER_FRAME * n_pairs,
+                              cudaMemcpyHostToDevice, h->s_in));
+    if (h_sky) MAVD_CUDA(cudaMemcpyAsync(S.d_sky, h_sky, sky_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, h->s_in));
+    if (h_seg) MAVD_CUDA(cudaMemcpyAsync(S.d_seg, h_seg, seg_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, h->s_in));
+    MAVD_CUDA(cudaEventRecord(S.ev_in, h->s_in));
+    // compute stream (the caller's)
+    MAVD_CUDA(cudaStreamWaitEvent(s, S.ev_in, 0));
+    TRY(mavd_process(h, S.d_frames, n_pairs, pair_stride, h_imu, prm, S.d_samples, h_sky ? S.d_sky : nullptr, sky_stride,
+                     h_seg ? S.d_seg : nullptr, seg_stride, h_flow_out ? S.d_flow : nullptr, nullptr, S.d_fixed,
+                     S.d_records, s));
+    MAVD_CUDA(cudaEventRecord(S.ev_done, s));
+    // copy-out stream
+    MAVD_CUDA(cudaStreamWaitEvent(h->s_out, S.ev_done, 0));
+    MAVD_CUDA(cudaMemcpyAsync(h_records, S.d_records, sizeof(mavd_frame_record) * n_pairs, cudaMemcpyDeviceToHost, h->s_out));
+    if (h_fixed_out) MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, S.d_fixed, npx * n_pairs, cudaMemcpyDeviceToHost, h->s_out));
+    if (h_flow_out)
+        MAVD_CUDA(cudaMemcpyAsync(h_flow_out, S.d_flow, sizeof(float) * 2 * npx * n_pairs, cudaMemcpyDeviceToHost, h->s_out));
+    MAVD_CUDA(cudaEventRecord(S.ev_out, h->s_out));
+    // the next batch's copy-in must not overwrite staging a kernel still reads: ordered by slot reuse rule
+    S.busy = true;
+    return MAVD_OK;
+}
+
+int mavd_wait_host(mavd_handle h, int32_t slot) {
+    MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "wait_host: handle is NULL");
+    MAVD_REQUIRE(slot >= 0 && slot < MAVD_HOST_SLOTS, MAVD_ERR_INVALID, "slot %d out of range", slot);
+    mavd_handle_s::HostSlot& S = h->slot[slot];
+    if (!S.busy) return MAVD_OK;
+    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    S.busy = false;
+    MAVD_CUDA(cudaEventSynchronize(S.ev_out));
     return MAVD_OK;
 }
 
@@ -566,27 +723,34 @@ int mavd_process_host(mavd_handle h, const uint8_t* h_frames, int32_t n_pairs, i
                       const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
                       float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
     TRY(check_batch(h, n_pairs, "process_host"));
-    MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
     if (n_pairs == 0) return MAVD_OK;
-    MAVD_REQUIRE(h_frames && h_samples && h_records, MAVD_ERR_INVALID, "process_host: NULL buffer");
-    cudaStream_t s = (cudaStream_t)stream;
+    TRY(mavd_wait_host(h, 0));
+    TRY(mavd_submit_host(h, 0, h_frames, n_pairs, pair_stride, h_imu, prm, h_samples, h_sky, sky_stride, h_seg,
+                         seg_stride, h_flow_out, h_fixed_out, h_records, stream));
+    return mavd_wait_host(h, 0);
+}
+
+int mavd_detect_host(mavd_handle h, const float* h_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,
+                     const int32_t* h_samples, const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg,
+                     int64_t seg_stride, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+    TRY(check_batch(h, n, "detect_host"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(h_flow && h_samples && h_records, MAVD_ERR_INVALID, "detect_host: NULL buffer");
     const size_t npx = (size_t)h->cfg.width * h->cfg.height;
-    const int n_frames = pair_stride == 1 ? n_pairs + 1 : 2 * n_pairs;
-    MAVD_CUDA(cudaMemcpyAsync(h->d_frames, h_frames, npx * n_frames, cudaMemcpyHostToDevice, s));
-    MAVD_CUDA(cudaMemcpyAsync(h->d_samples, h_samples, sizeof(int32_t) * MAVD_SAMPLES_PER_FRAME * n_pairs,
-                              cudaMemcpyHostToDevice, s));
-    if (h_sky)
-        MAVD_CUDA(cudaMemcpyAsync(h->d_sky, h_sky, sky_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, s));
-    if (h_seg)
-        MAVD_CUDA(cudaMemcpyAsync(h->d_seg, h_seg, seg_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, s));
     MAVD_REQUIRE(sky_stride == 0 || sky_stride == (int64_t)npx, MAVD_ERR_INVALID, "sky_stride must be 0 or H*W");
     MAVD_REQUIRE(seg_stride == 0 || seg_stride == (int64_t)npx, MAVD_ERR_INVALID, "seg_stride must be 0 or H*W");
-    TRY(mavd_process(h, h->d_frames, n_pairs, pair_stride, h_imu, prm, h->d_samples, h_sky ? h->d_sky : nullptr,
-                     sky_stride, h_seg ? h->d_seg : nullptr, seg_stride, h->d_flow, nullptr, h->d_fixed, h->d_records, s));
-    MAVD_CUDA(cudaMemcpyAsync(h_records, h->d_records, sizeof(mavd_frame_record) * n_pairs, cudaMemcpyDeviceToHost, s));
-    if (h_fixed_out) MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, h->d_fixed, npx * n_pairs, cudaMemcpyDeviceToHost, s));
-    if (h_flow_out)
-        MAVD_CUDA(cudaMemcpyAsync(h_flow_out, h->d_flow, sizeof(float) * 2 * npx * n_pairs, cudaMemcpyDeviceToHost, s));
+    TRY(mavd_wait_host(h, 0));
+    TRY(ensure_slot(h, 0, false, true));
+    mavd_handle_s::HostSlot& S = h->slot[0];
+    cudaStream_t s = (cudaStream_t)stream;
+    MAVD_CUDA(cudaMemcpyAsync(S.d_flow_in, h_flow, sizeof(float) * 2 * npx * n, cudaMemcpyHostToDevice, s));
+    MAVD_CUDA(cudaMemcpyAsync(S.d_samples, h_samples, sizeof(int32_t) * MAVD_SAMPLES_PER_FRAME * n, cudaMemcpyHostToDevice, s));
+    if (h_sky) MAVD_CUDA(cudaMemcpyAsync(S.d_sky, h_sky, sky_stride ? npx * n : npx, cudaMemcpyHostToDevice, s));
+    if (h_seg) MAVD_CUDA(cudaMemcpyAsync(S.d_seg, h_seg, seg_stride ? npx * n : npx, cudaMemcpyHostToDevice, s));
+    TRY(mavd_detect(h, S.d_flow_in, n, h_imu, prm, S.d_samples, h_sky ? S.d_sky : nullptr, sky_stride,
+                    h_seg ? S.d_seg : nullptr, seg_stride, nullptr, S.d_fixed, S.d_records, s));
+    MAVD_CUDA(cudaMemcpyAsync(h_records, S.d_records, sizeof(mavd_frame_record) * n, cudaMemcpyDeviceToHost, s));
+    if (h_fixed_out) MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, S.d_fixed, npx * n, cudaMemcpyDeviceToHost, s));
     MAVD_CUDA(cudaStreamSynchronize(s));
     return MAVD_OK;
 }

@@ -30,6 +30,12 @@ extern std::atomic<int64_t> g_launches;
         MAVD_CUDA(cudaGetLastError());                                                          \
     } while (0)
 
+#define TRY_RC(...)                                                                             \
+    do {                                                                                        \
+        int rc__ = (__VA_ARGS__);                                                                       \
+        if (rc__ != MAVD_OK) return rc__;                                                       \
+    } while (0)
+
 #define MAVD_REQUIRE(cond, code, ...)                                                           \
     do {                                                                                        \
         if (!(cond)) {                                                                          \
@@ -124,15 +130,28 @@ struct mavd_handle_s {
     int32_t* d_ninter = nullptr;    // [max_pairs]
     int32_t* d_labels = nullptr;    // [max_pairs][H][W]
     int32_t* d_scan = nullptr;      // CCL scratch
+    double* d_xn = nullptr;         // [W] -(x/w - 0.5)*2, detector.py:90 (host-built, IEEE identical to NumPy)
+    double* d_yn = nullptr;         // [H] -(y/h - 0.5)*2, detector.py:91
+    mavd_frame_stats* d_stats_tmp = nullptr;  // [max_pairs] scratch for mavd_get_phi
+    bool force_exact_residual = false;        // tests: disable the float32 pre-decision
     uint8_t* d_total = nullptr;     // [max_pairs][H][W]
     uint8_t* d_fixed = nullptr;
     float* d_flow = nullptr;        // [max_pairs][H][W][2] (when the caller does not want the flow)
-    // host-path staging (device side)
-    uint8_t* d_frames = nullptr;    // [max_frames][H][W]
-    int32_t* d_samples = nullptr;   // [max_pairs][4000]
-    uint8_t* d_sky = nullptr;       // [max_pairs][H][W]
-    uint8_t* d_seg = nullptr;
-    mavd_frame_record* d_records = nullptr;
+    // host-path staging: MAVD_HOST_SLOTS independent sets of device buffers + the streams/events that let
+    // the H2D of one batch, the compute of the previous one and the D2H of the one before overlap
+    struct HostSlot {
+        uint8_t* d_frames = nullptr;    // [max_frames][H][W]
+        int32_t* d_samples = nullptr;   // [max_pairs][4000]
+        uint8_t* d_sky = nullptr;       // [max_pairs][H][W]
+        uint8_t* d_seg = nullptr;
+        float* d_flow_in = nullptr;     // [max_pairs][H][W][2], mavd_detect_host only (allocated on first use)
+        mavd_frame_record* d_records = nullptr;
+        uint8_t* d_fixed = nullptr;     // [max_pairs][H][W] estimate_fixed masks of the batch
+        float* d_flow = nullptr;        // [max_pairs][H][W][2] flow of the batch (allocated on first request)
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+        bool busy = false;
+    } slot[MAVD_HOST_SLOTS];
+    cudaStream_t s_in = nullptr, s_out = nullptr;
     mavd::Profiler prof;
     bool force_generic_iter = false;  // tests: run the non-TMA iteration kernel
     // last call bookkeeping for taps
@@ -149,9 +168,11 @@ int farneback_tap(mavd_handle h, int kind, int level, int index, float* d_out, c
 // detect.cu
 int bgr2gray_run(const uint8_t* d_bgr, uint8_t* d_gray, int64_t n, cudaStream_t s);
 int derotate_run(mavd_handle h, const float* d_flow, int n, const mavd_imu* d_imu, double* d_out, cudaStream_t s);
-int foe_run(mavd_handle h, const float* d_flow, int n, const mavd_imu* d_imu, const mavd_detect_params& prm,
-            const int32_t* d_samples, double* d_foe, int32_t* d_ninter, cudaStream_t s);
-int residual_run(mavd_handle h, const float* d_flow, int n, const mavd_imu* d_imu, const mavd_detect_params& prm,
+int foe_run(mavd_handle h, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu,
+            const mavd_detect_params& prm, const int32_t* d_samples, double* d_foe, int32_t* d_ninter, cudaStream_t s);
+int ransac_run(const double* d_estimates, int K, double threshold, double* d_out, cudaStream_t s);
+int gather_max_phi_run(const mavd_frame_stats* d_stats, int n, double* d_out, cudaStream_t s);
+int residual_run(mavd_handle h, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu, const mavd_detect_params& prm,
                  const double* d_foe, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
                  int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
                  size_t stats_stride_bytes, int run_f64, int run_f32, cudaStream_t s);

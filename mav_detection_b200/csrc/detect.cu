@@ -116,7 +116,10 @@ int derotate_run(mavd_handle H, const float* d_flow, int n, const mavd_imu* d_im
 // ------------------------------------------------------------------------------------------------
 constexpr int kNP = MAVD_N_SAMPLE_PAIRS;
 
-__global__ void __launch_bounds__(1024) foe_kernel(const float2* __restrict__ flow, const mavd_imu* __restrict__ imu,
+// kind 0: float32 flow, per-frame imu (derotation applied inline); 1: float32 flow as given;
+// 2: float64 flow as given (get_FOE_dense on an already derotated field)
+__global__ void __launch_bounds__(1024) foe_kernel(const void* __restrict__ flow, int kind,
+                                                  const mavd_imu* __restrict__ imu,
                                                   const int32_t* __restrict__ samples, int w, int h,
                                                   double mag_thr, double sq_thr, double* __restrict__ foe,
                                                   int32_t* __restrict__ ninter) {
@@ -124,18 +127,31 @@ __global__ void __launch_bounds__(1024) foe_kernel(const float2* __restrict__ fl
     __shared__ int warp_cnt[32];
     __shared__ unsigned long long warp_best[32];
     const int f = blockIdx.x, i = threadIdx.x, lane = i & 31, wid = i >> 5;
-    const Derot d = make_derot(imu[f], w, h);
-    const float2* fl = flow + (size_t)f * w * h;
+    Derot d;
+    d.on = 0;
+    if (kind == 0) d = make_derot(imu[f], w, h);
     const int32_t* sm = samples + (size_t)f * MAVD_SAMPLES_PER_FRAME;
 
     bool valid = false;
     double ex = 0.0, ey = 0.0;
     if (i < kNP) {
         const int y1 = sm[i], y2 = sm[i + kNP], x1 = sm[2 * kNP + i], x2 = sm[3 * kNP + i];
-        const float2 a = fl[(size_t)y1 * w + x1], b = fl[(size_t)y2 * w + x2];
+        float2 a = make_float2(0.f, 0.f), b = a;
         double f1x, f1y, f2x, f2y;
         bool keep;
-        if (d.on) {
+        if (kind == 2) {
+            const double2* fl = reinterpret_cast<const double2*>(flow) + (size_t)f * w * h;
+            const double2 a2 = fl[(size_t)y1 * w + x1], b2 = fl[(size_t)y2 * w + x2];
+            f1x = a2.x; f1y = a2.y; f2x = b2.x; f2y = b2.y;
+            const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(f2x, f2x), __dmul_rn(f2y, f2y)));
+            keep = !(mag < mag_thr);
+        } else {
+            const float2* fl = reinterpret_cast<const float2*>(flow) + (size_t)f * w * h;
+            a = fl[(size_t)y1 * w + x1];
+            b = fl[(size_t)y2 * w + x2];
+        }
+        if (kind == 2) {
+        } else if (d.on) {
             double r0, r1;
             derot_at(d, x1, y1, r0, r1);
             f1x = __dsub_rn((double)a.x, r0); f1y = __dsub_rn((double)a.y, r1);
@@ -235,194 +251,441 @@ static double sqrt_threshold(double T) {
     return s;
 }
 
-int foe_run(mavd_handle H, const float* d_flow, int n, const mavd_imu* d_imu, const mavd_detect_params& prm,
-            const int32_t* d_samples, double* d_foe, int32_t* d_ninter, cudaStream_t s) {
+int foe_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu,
+            const mavd_detect_params& prm, const int32_t* d_samples, double* d_foe, int32_t* d_ninter, cudaStream_t s) {
     ProfScope ps(&H->prof, MAVD_PROF_FOE, s);
-    foe_kernel<<<n, 1024, 0, s>>>((const float2*)d_flow, d_imu, d_samples, H->cfg.width, H->cfg.height,
+    foe_kernel<<<n, 1024, 0, s>>>(d_flow, flow_kind, d_imu, d_samples, H->cfg.width, H->cfg.height,
                                   prm.magnitude_threshold, sqrt_threshold(prm.ransac_threshold), d_foe, d_ninter);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+// FocusOfExpansion.ransac on a caller-supplied (K, 2) float64 array (focus_of_expansion.py:32-54):
+// one CTA, thread i scores estimates i, i + 1024, ...; first strict maximum wins.
+__global__ void __launch_bounds__(1024) ransac_kernel(const double2* __restrict__ E, int K, double sq_thr,
+                                                     double* __restrict__ out) {
+    __shared__ unsigned long long warp_best[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long key = 0ull;
+    for (int i = threadIdx.x; i < K; i += 1024) {
+        const double2 me = E[i];
+        int cnt = 0;
+        for (int j = 0; j < K; ++j) {
+            const double2 o = __ldg(E + j);
+            const double dx = __dsub_rn(o.x, me.x), dy = __dsub_rn(o.y, me.y);
+            cnt += (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < sq_thr) ? 1 : 0;
+        }
+        const int score = cnt - 1;
+        const unsigned long long k = (score > 0) ? (((unsigned long long)(unsigned)score << 32) | (unsigned)(0x7fffffff - i)) : 0ull;
+        key = k > key ? k : key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
+        key = t > key ? t : key;
+    }
+    if (lane == 0) warp_best[wid] = key;
+    __syncthreads();
+    if (wid == 0) {
+        key = warp_best[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
+            key = t > key ? t : key;
+        }
+        if (lane == 0) {
+            double bx = 0.0, by = 0.0;
+            if (key != 0ull) {
+                const int best = 0x7fffffff - (int)(key & 0xffffffffu);
+                bx = E[best].x;
+                by = E[best].y;
+            }
+            out[0] = bx;
+            out[1] = by;
+        }
+    }
+}
+
+int ransac_run(const double* d_estimates, int K, double threshold, double* d_out, cudaStream_t s) {
+    ransac_kernel<<<1, 1024, 0, s>>>((const double2*)d_estimates, K, sqrt_threshold(threshold), d_out);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+__global__ void gather_max_phi_kernel(const char* stats_base, size_t stats_stride, int n, double* out) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n) out[f] = reinterpret_cast<const mavd_frame_stats*>(stats_base + (size_t)f * stats_stride)->max_phi;
+}
+
+int gather_max_phi_run(const mavd_frame_stats* d_stats, int n, double* d_out, cudaStream_t s) {
+    gather_max_phi_kernel<<<ceil_div(n, 128), 128, 0, s>>>((const char*)d_stats, sizeof(mavd_frame_stats), n, d_out);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Residual angle phi + the two masks + the integer reductions behind FrameResult.
+//
+// MODE 0  float32 flow + IMU derotation, all arithmetic in float64 (frames with imu.derotate != 0)
+// MODE 1  float32 flow passed through (frame_index < 1): NumPy keeps every temporary in float32
+// MODE 2  float64 flow given by the caller, no derotation (FocusOfExpansion.get_phi on any array)
+//
+// Derotation uses host-built tables xn[x] = -(x/w - 0.5)*2, yn[y] = -(y/h - 0.5)*2 (IEEE doubles, the
+// same values NumPy computes), so the per-pixel float64 work has no division.
+//
+// FAST (MODE 0/2, phi not requested): the masks are decided from a float32 estimate of phi
+// (atan2 of cross and dot product, well conditioned at every angle) whenever the estimate is further
+// from every threshold than a conservative error bound; only pixels inside the guard bands (and any
+// non-finite or degenerate input) take the exact float64 path below.  Masks and counts stay
+// bit-exact; max_phi is not evaluated on this path (reported as -1).
 // ------------------------------------------------------------------------------------------------
 struct ResidualPrm {
     double dyn_offset, dyn_base, dyn_gain, dyn_min_mag, fixed_min_mag, fixed_angle;
 };
 
+struct ResidualArgs {
+    const void* flow;
+    const mavd_imu* imu;     // NULL for flow kinds that ignore the IMU
+    const double* foe;
+    const double* xn;
+    const double* yn;
+    int w, h;
+    ResidualPrm prm;
+    const uint8_t* sky; int64_t sky_stride;
+    const uint8_t* seg; int64_t seg_stride;
+    const int* seg_max;
+    void* phi_out;
+    uint8_t* total_out;
+    uint8_t* fixed_out;
+    char* stats_base; size_t stats_stride;
+};
+
 __device__ __forceinline__ unsigned long long dmax_key(double v) { return (unsigned long long)__double_as_longlong(v); }
 
+// max over a uint8 image, 16 bytes per load where the alignment allows
 __global__ void __launch_bounds__(256) seg_max_kernel(const uint8_t* __restrict__ seg, int64_t seg_stride, int64_t npx,
                                                      int* __restrict__ seg_max) {
     const int f = blockIdx.y;
     const uint8_t* p = seg + (size_t)f * seg_stride;
+    unsigned mx4 = 0;
     int mx = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (int64_t)gridDim.x * blockDim.x)
-        mx = max(mx, (int)p[i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const int64_t n16 = npx >> 4;
+        const uint4* p16 = reinterpret_cast<const uint4*>(p);
+        for (int64_t i = tid; i < n16; i += nthr) {
+            const uint4 v = __ldg(p16 + i);
+            mx4 = __vmaxu4(mx4, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+        }
+        for (int64_t i = (n16 << 4) + tid; i < npx; i += nthr) mx = max(mx, (int)p[i]);
+    } else {
+        for (int64_t i = tid; i < npx; i += nthr) mx = max(mx, (int)p[i]);
+    }
+    mx = max(mx, (int)max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24)));
+    mx = __reduce_max_sync(0xffffffffu, mx);
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(seg_max + f, mx);
 }
 
-struct BlockStats {
-    long long n_total, n_fixed, pos, neg, tp_t, fp_t, tp_f, fp_f;
-    int x0, y0, x1, y1;
-    double sfx, sfy, maxphi;
+struct DerotRow {   // per-frame, per-row constants of detector.py:93-101 (NumPy operation order)
+    double o0, o1, o2, s0, s1;
+    int on;
 };
 
-__device__ __forceinline__ long long warp_sum(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+__device__ __forceinline__ void derot_tab(const DerotRow& d, double xn, double yn, double& r0, double& r1) {
+    double t = __dmul_rn(__dmul_rn(d.o0, xn), yn);
+    t = __dsub_rn(t, __dmul_rn(d.o1, __dmul_rn(xn, xn)));
+    t = __dsub_rn(t, d.o1);
+    t = __dadd_rn(t, __dmul_rn(d.o2, yn));
+    r0 = __dmul_rn(t, d.s0);
+    double u = __dmul_rn(-d.o2, xn);
+    u = __dadd_rn(u, d.o0);
+    u = __dadd_rn(u, __dmul_rn(d.o0, __dmul_rn(yn, yn)));
+    u = __dsub_rn(u, __dmul_rn(__dmul_rn(d.o1, xn), yn));
+    r1 = __dmul_rn(u, d.s1);
 }
 
-template <bool F64>
-__global__ void __launch_bounds__(256) residual_kernel(const float2* __restrict__ flow, const mavd_imu* __restrict__ imu,
-                                                      const double* __restrict__ foe, int w, int h, ResidualPrm prm,
-                                                      const uint8_t* __restrict__ sky, int64_t sky_stride,
-                                                      const uint8_t* __restrict__ seg, int64_t seg_stride,
-                                                      const int* __restrict__ seg_max, void* __restrict__ phi_out,
-                                                      uint8_t* __restrict__ total_out, uint8_t* __restrict__ fixed_out,
-                                                      char* __restrict__ stats_base, size_t stats_stride) {
-    const int f = blockIdx.z;
-    const mavd_imu im = imu[f];
-    // both precisions are launched for every batch; each handles only its own frames
-    if ((im.derotate != 0) != F64) return;
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    const bool in = (x < w && y < h);
-    const size_t o = in ? ((size_t)y * w + x) : 0;
-    const size_t fo = (size_t)f * w * h + o;
-    bool m_total = false, m_fixed = false;
-    double phi_d = 0.0, fdx = 0.0, fdy = 0.0;
-    if (in) {
-        const float2 v = flow[fo];
-        const bool not_sky = sky ? (sky[(size_t)f * sky_stride + o] == 0) : true;
-        const double foex = foe[2 * f], foey = foe[2 * f + 1];
-        if (F64) {
-            const Derot d = make_derot(im, w, h);
-            double r0, r1;
-            derot_at(d, x, y, r0, r1);
-            fdx = __dsub_rn((double)v.x, r0);
-            fdy = __dsub_rn((double)v.y, r1);
-            const double d2x = __dsub_rn((double)x, foex), d2y = __dsub_rn((double)y, foey);
-            const double a = __dsqrt_rn(__dadd_rn(__dmul_rn(fdx, fdx), __dmul_rn(fdy, fdy)));
-            const double b = __dsqrt_rn(__dadd_rn(__dmul_rn(d2x, d2x), __dmul_rn(d2y, d2y)));
-            const double ab = __dmul_rn(a, b);
-            const double norm = (ab != ab) ? ab : fmax(1e-6, ab);
-            double c = __ddiv_rn(__dadd_rn(__dmul_rn(fdx, d2x), __dmul_rn(fdy, d2y)), norm);
-            if (c == c) c = fmin(fmax(c, -1.0), 1.0);
-            double ang = acos(c);
-            if (ang != ang) ang = 0.0;
-            const double phi = __dmul_rn(ang, 180.0 / 3.141592653589793238462643383279502884);
-            phi_d = phi;
-            const double t = __dadd_rn(prm.dyn_base, __ddiv_rn(prm.dyn_gain, a));
-            const bool amax = phi > __dadd_rn(prm.dyn_offset, t);
-            const bool amin = phi < __dsub_rn(prm.dyn_offset, t);
-            m_total = (a > prm.dyn_min_mag) && not_sky && (amin || amax);
-            m_fixed = (phi > prm.fixed_angle) && (a > prm.fixed_min_mag) && not_sky;
-            if (phi_out) reinterpret_cast<double*>(phi_out)[fo] = phi;
-        } else {
-            // frame_index < 1: the flow stays float32 and so does every NumPy temporary
-            const float fx = v.x, fy = v.y;
-            fdx = fx; fdy = fy;
-            const float d2x = (float)__dsub_rn((double)x, foex), d2y = (float)__dsub_rn((double)y, foey);
-            const float a = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
-            const float b = __fsqrt_rn(__fadd_rn(__fmul_rn(d2x, d2x), __fmul_rn(d2y, d2y)));
-            const float ab = __fmul_rn(a, b);
-            const float norm = (ab != ab) ? ab : fmaxf(1e-6f, ab);
-            float c = __fdiv_rn(__fadd_rn(__fmul_rn(fx, d2x), __fmul_rn(fy, d2y)), norm);
-            if (c == c) c = fminf(fmaxf(c, -1.f), 1.f);
-            float ang = (float)acos((double)c);
-            if (ang != ang) ang = 0.f;
-            const float phi = __fmul_rn(ang, 180.0f / 3.141592653589793238462643383279502884f);
-            phi_d = phi;
-            const float t = __fadd_rn((float)prm.dyn_base, __fdiv_rn((float)prm.dyn_gain, a));
-            const bool amax = phi > __fadd_rn((float)prm.dyn_offset, t);
-            const bool amin = phi < __fsub_rn((float)prm.dyn_offset, t);
-            m_total = (a > (float)prm.dyn_min_mag) && not_sky && (amin || amax);
-            m_fixed = (phi > (float)prm.fixed_angle) && (a > (float)prm.fixed_min_mag) && not_sky;
-            if (phi_out) reinterpret_cast<float*>(reinterpret_cast<double*>(phi_out) + (size_t)f * w * h)[o] = phi;
-        }
-        if (total_out) total_out[fo] = m_total ? 1 : 0;
-        if (fixed_out) fixed_out[fo] = m_fixed ? 1 : 0;
-    }
-    if (!stats_base) return;
+// exact float64 evaluation of focus_of_expansion.py:165-178 and processor.py:333-341 for one pixel
+__device__ __forceinline__ void pixel_exact_f64(double fdx, double fdy, int x, int y, double foex, double foey,
+                                                const ResidualPrm& prm, bool not_sky, bool& m_total, bool& m_fixed,
+                                                double& phi) {
+    const double d2x = __dsub_rn((double)x, foex), d2y = __dsub_rn((double)y, foey);
+    const double a = __dsqrt_rn(__dadd_rn(__dmul_rn(fdx, fdx), __dmul_rn(fdy, fdy)));
+    const double b = __dsqrt_rn(__dadd_rn(__dmul_rn(d2x, d2x), __dmul_rn(d2y, d2y)));
+    const double ab = __dmul_rn(a, b);
+    const double norm = (ab != ab) ? ab : fmax(1e-6, ab);
+    double c = __ddiv_rn(__dadd_rn(__dmul_rn(fdx, d2x), __dmul_rn(fdy, d2y)), norm);
+    if (c == c) c = fmin(fmax(c, -1.0), 1.0);
+    double ang = acos(c);
+    if (ang != ang) ang = 0.0;
+    phi = __dmul_rn(ang, 180.0 / 3.141592653589793238462643383279502884);
+    const double t = __dadd_rn(prm.dyn_base, __ddiv_rn(prm.dyn_gain, a));
+    const bool amax = phi > __dadd_rn(prm.dyn_offset, t);
+    const bool amin = phi < __dsub_rn(prm.dyn_offset, t);
+    m_total = (a > prm.dyn_min_mag) && not_sky && (amin || amax);
+    m_fixed = (((a > prm.fixed_min_mag) && not_sky) ? phi : 0.0) > prm.fixed_angle;
+}
 
-    // ---- block reduction of the integer statistics ----
-    long long c_tot = m_total, c_fix = m_fixed, c_pos = 0, c_neg = 0, c_tpt = 0, c_fpt = 0, c_tpf = 0, c_fpf = 0;
+__device__ __forceinline__ void pixel_exact_f32(float fx, float fy, int x, int y, double foex, double foey,
+                                                const ResidualPrm& prm, bool not_sky, bool& m_total, bool& m_fixed,
+                                                float& phi) {
+    // the flow stays float32 and so does every NumPy temporary (diff2 = zeros_like(flow))
+    const float d2x = (float)__dsub_rn((double)x, foex), d2y = (float)__dsub_rn((double)y, foey);
+    const float a = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+    const float b = __fsqrt_rn(__fadd_rn(__fmul_rn(d2x, d2x), __fmul_rn(d2y, d2y)));
+    const float ab = __fmul_rn(a, b);
+    const float norm = (ab != ab) ? ab : fmaxf(1e-6f, ab);
+    float c = __fdiv_rn(__fadd_rn(__fmul_rn(fx, d2x), __fmul_rn(fy, d2y)), norm);
+    if (c == c) c = fminf(fmaxf(c, -1.f), 1.f);
+    float ang = (float)acos((double)c);
+    if (ang != ang) ang = 0.f;
+    phi = __fmul_rn(ang, 180.0f / 3.141592653589793238462643383279502884f);
+    const float t = __fadd_rn((float)prm.dyn_base, __fdiv_rn((float)prm.dyn_gain, a));
+    const bool amax = phi > __fadd_rn((float)prm.dyn_offset, t);
+    const bool amin = phi < __fsub_rn((float)prm.dyn_offset, t);
+    m_total = (a > (float)prm.dyn_min_mag) && not_sky && (amin || amax);
+    m_fixed = (((a > (float)prm.fixed_min_mag) && not_sky) ? phi : 0.f) > (float)prm.fixed_angle;
+}
+
+// float32 pre-decision.  Returns false when the pixel must take the exact path.
+// Error budget of the estimate: the inputs are float64 values rounded once to float32 (direction error
+// < 3e-7 rad per vector), cross/dot carry < 2 ulp of |f||d|, atan2f < 4 ulp: together < 3e-4 degrees
+// for every angle in [0, 180]; the guard band is 2e-3 degrees plus 1e-5 relative on the dynamic
+// threshold, and 1e-5 relative on the magnitude gates (sqrtf error 2e-7 relative).
+struct FastPrm {
+    float dyn_offset, dyn_base, dyn_gain, dyn_min_mag, fixed_min_mag, fixed_angle;
+};
+
+__device__ __forceinline__ bool pixel_fast(double fdx, double fdy, int x, int y, double foex, double foey,
+                                           const FastPrm& p, bool& m_total, bool& m_fixed) {
+    const float fx = (float)fdx, fy = (float)fdy;
+    const float a2 = fx * fx + fy * fy;
+    if (!(a2 < 1e30f)) return false;                       // NaN / inf / huge: exact path
+    const float a = sqrtf(a2);
+    const float gd = fabsf(a - p.dyn_min_mag), gf = fabsf(a - p.fixed_min_mag);
+    if (gd <= 1e-5f * fmaxf(1.f, p.dyn_min_mag) || gf <= 1e-5f * fmaxf(1.f, p.fixed_min_mag)) return false;
+    const bool gt_dyn = a > p.dyn_min_mag, gt_fix = a > p.fixed_min_mag;
+    m_total = m_fixed = false;
+    if (!gt_dyn && !gt_fix) return true;
+    const float dx = (float)((double)x - foex), dy = (float)((double)y - foey);
+    const float b2 = dx * dx + dy * dy;
+    if (!(b2 < 1e30f) || a2 * b2 < 1e-8f) return false;    // |f||d| near the 1e-6 clamp of the norm: exact path
+    const float dot = fx * dx + fy * dy;
+    const float crs = fabsf(fx * dy - fy * dx);
+    const float phi = atan2f(crs, dot) * 57.29577951308232f;
+    if (gt_fix) {
+        if (fabsf(phi - p.fixed_angle) <= 2e-3f) return false;
+        m_fixed = phi > p.fixed_angle;
+    }
+    if (gt_dyn) {
+        const float thr = p.dyn_offset + (p.dyn_base + p.dyn_gain / a);
+        if (fabsf(phi - thr) <= 2e-3f + 1e-5f * thr) return false;
+        m_total = phi > thr;      // amin is impossible: the host enables FAST only when offset - base < 0
+    }
+    return true;
+}
+
+constexpr int RES_ITEMS = 4;     // pixel groups per thread
+
+template <int MODE, bool FAST, int VEC>
+__global__ void __launch_bounds__(256) residual_kernel(const ResidualArgs A, const FastPrm fp) {
+    const int f = blockIdx.y;
+    DerotRow dr;
+    dr.on = 0;
+    if (MODE != 2) {
+        mavd_imu im;
+        im.derotate = 0;
+        if (A.imu) im = A.imu[f];
+        // every mode is launched over the whole batch; each handles only its own frames
+        if ((im.derotate != 0) != (MODE == 0)) return;
+        if (MODE == 0) {
+            dr.o0 = __ddiv_rn(im.ang[0], im.dt);
+            dr.o1 = __ddiv_rn(im.ang[1], im.dt);
+            dr.o2 = __ddiv_rn(im.ang[2], im.dt);
+            dr.s0 = __ddiv_rn(__dmul_rn((double)A.w, im.dt), 2.0);
+            dr.s1 = __ddiv_rn(__dmul_rn((double)A.h, im.dt), 2.0);
+            // omega == 0 and finite scales: the derotation field is exactly (+-)0 and flow - 0 == flow
+            dr.on = !(dr.o0 == 0.0 && dr.o1 == 0.0 && dr.o2 == 0.0 && fabs(dr.s0) < 1e300 && fabs(dr.s1) < 1e300);
+        }
+    }
+    const int w = A.w, h = A.h;
+    const int npx = w * h;
+    const int ngrp = npx / VEC;                 // VEC == 4 only when w % 4 == 0
+    const double foex = A.foe[2 * f], foey = A.foe[2 * f + 1];
+    const size_t fbase = (size_t)f * npx;
+    const uint8_t* sky = A.sky ? A.sky + (size_t)f * A.sky_stride : nullptr;
+    const uint8_t* seg = A.seg ? A.seg + (size_t)f * A.seg_stride : nullptr;
+    const bool want_stats = A.stats_base != nullptr;
+    const double seg_thr = seg && want_stats ? 0.1 * (double)A.seg_max[f] : 0.0;
+
+    int c_tot = 0, c_fix = 0, c_pos = 0, c_neg = 0, c_tpt = 0, c_fpt = 0, c_tpf = 0, c_fpf = 0;
     int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;
-    double sfx = 0.0, sfy = 0.0;
-    if (in && seg) {
-        const int g = seg[(size_t)f * seg_stride + o];
-        c_pos = g > 127;
-        c_neg = (255 - g) > 127;
-        c_tpt = m_total && g >= 1;
-        c_fpt = m_total && g <= 254;
-        c_tpf = m_fixed && g >= 1;
-        c_fpf = m_fixed && g <= 254;
-        const double thr = 0.1 * (double)seg_max[f];
-        if ((double)g > thr) { bx0 = bx1 = x; by0 = by1 = y; }
-        if (g > 127) { sfx = fdx; sfy = fdy; }
-    }
-    __shared__ BlockStats red[8];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    c_tot = warp_sum(c_tot); c_fix = warp_sum(c_fix);
-    unsigned long long mk = dmax_key(phi_d);
+    double sfx = 0.0, sfy = 0.0, maxphi = 0.0;
+
+#pragma unroll 1
+    for (int it = 0; it < RES_ITEMS; ++it) {
+        const int q = (blockIdx.x * RES_ITEMS + it) * 256 + threadIdx.x;
+        if (q >= ngrp) break;
+        const int i0 = q * VEC;
+        const int y = i0 / w, x0 = i0 - y * w;
+        // ---- loads ----
+        double vx[VEC], vy[VEC];
+        float vfx[VEC], vfy[VEC];
+        if (MODE == 2) {
+            const double2* fl = reinterpret_cast<const double2*>(A.flow) + fbase + i0;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        unsigned long long t = __shfl_xor_sync(0xffffffffu, mk, s);
-        mk = t > mk ? t : mk;
+            for (int k = 0; k < VEC; ++k) { const double2 v = fl[k]; vx[k] = v.x; vy[k] = v.y; }
+        } else if (VEC == 4) {
+            const float4* fl = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(A.flow) + fbase + i0);
+            const float4 u0 = __ldg(fl), u1 = __ldg(fl + 1);
+            vfx[0] = u0.x; vfy[0] = u0.y; vfx[1] = u0.z; vfy[1] = u0.w;
+            vfx[2] = u1.x; vfy[2] = u1.y; vfx[3] = u1.z; vfy[3] = u1.w;
+        } else {
+            const float2 v = reinterpret_cast<const float2*>(A.flow)[fbase + i0];
+            vfx[0] = v.x; vfy[0] = v.y;
+        }
+        unsigned skyw = 0, segw = 0;
+        if (VEC == 4) {
+            if (sky) skyw = __ldg(reinterpret_cast<const unsigned*>(sky + i0));
+            if (seg) segw = __ldg(reinterpret_cast<const unsigned*>(seg + i0));
+        } else {
+            if (sky) skyw = sky[i0];
+            if (seg) segw = seg[i0];
+        }
+        double yn = 0.0;
+        if (MODE == 0 && dr.on) yn = __ldg(A.yn + y);
+        unsigned totw = 0, fixw = 0;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const int x = x0 + k;
+            const bool not_sky = ((skyw >> (8 * k)) & 255u) == 0;
+            bool mt = false, mf = false;
+            double fdx = 0.0, fdy = 0.0;
+            if (MODE == 1) {
+                float phi;
+                pixel_exact_f32(vfx[k], vfy[k], x, y, foex, foey, A.prm, not_sky, mt, mf, phi);
+                fdx = vfx[k]; fdy = vfy[k];
+                maxphi = fmax(maxphi, (double)phi);
+                if (A.phi_out) reinterpret_cast<float*>(reinterpret_cast<double*>(A.phi_out) + fbase)[i0 + k] = phi;
+            } else {
+                if (MODE == 0) {
+                    fdx = vfx[k]; fdy = vfy[k];
+                    if (dr.on) {
+                        double r0, r1;
+                        derot_tab(dr, __ldg(A.xn + x), yn, r0, r1);
+                        fdx = __dsub_rn(fdx, r0);
+                        fdy = __dsub_rn(fdy, r1);
+                    }
+                } else {
+                    fdx = vx[k]; fdy = vy[k];
+                }
+                bool decided = false;
+                if (FAST) {
+                    if (!not_sky) decided = true;          // both masks are multiplied by ~sky
+                    else decided = pixel_fast(fdx, fdy, x, y, foex, foey, fp, mt, mf);
+                }
+                if (!decided) {
+                    double phi;
+                    pixel_exact_f64(fdx, fdy, x, y, foex, foey, A.prm, not_sky, mt, mf, phi);
+                    if (!FAST) {
+                        maxphi = fmax(maxphi, phi);
+                        if (A.phi_out) reinterpret_cast<double*>(A.phi_out)[fbase + i0 + k] = phi;
+                    }
+                }
+            }
+            totw |= (mt ? 1u : 0u) << (8 * k);
+            fixw |= (mf ? 1u : 0u) << (8 * k);
+            if (want_stats) {
+                c_tot += mt; c_fix += mf;
+                if (seg) {
+                    const int g = (segw >> (8 * k)) & 255u;
+                    c_pos += g > 127;
+                    c_neg += (255 - g) > 127;
+                    c_tpt += mt && g >= 1;
+                    c_fpt += mt && g <= 254;
+                    c_tpf += mf && g >= 1;
+                    c_fpf += mf && g <= 254;
+                    if ((double)g > seg_thr) { bx0 = min(bx0, x); bx1 = max(bx1, x); by0 = min(by0, y); by1 = max(by1, y); }
+                    if (g > 127) { sfx += fdx; sfy += fdy; }
+                }
+            }
+        }
+        if (VEC == 4) {
+            if (A.total_out) *reinterpret_cast<unsigned*>(A.total_out + fbase + i0) = totw;
+            if (A.fixed_out) *reinterpret_cast<unsigned*>(A.fixed_out + fbase + i0) = fixw;
+        } else {
+            if (A.total_out) A.total_out[fbase + i0] = (uint8_t)totw;
+            if (A.fixed_out) A.fixed_out[fbase + i0] = (uint8_t)fixw;
+        }
     }
-    if (seg) {
-        c_pos = warp_sum(c_pos); c_neg = warp_sum(c_neg); c_tpt = warp_sum(c_tpt); c_fpt = warp_sum(c_fpt);
-        c_tpf = warp_sum(c_tpf); c_fpf = warp_sum(c_fpf);
+    if (!want_stats) return;
+
+    // ---- block reduction: warp redux -> shared atomics -> one set of global atomics per block ----
+    __shared__ int s_cnt[8];
+    __shared__ int s_bb[4];
+    __shared__ double s_sum[2];
+    __shared__ unsigned long long s_max;
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 8) { s_bb[0] = s_bb[1] = 0x7fffffff; s_bb[2] = s_bb[3] = -1; s_sum[0] = s_sum[1] = 0.0; s_max = 0ull; }
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    c_tot = __reduce_add_sync(FULL, c_tot); c_fix = __reduce_add_sync(FULL, c_fix);
+    if (lane == 0) { if (c_tot) atomicAdd(&s_cnt[0], c_tot); if (c_fix) atomicAdd(&s_cnt[1], c_fix); }
+    if (!FAST) {
+        unsigned long long mk = dmax_key(maxphi);
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
-            bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, s));
-            by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, s));
-            bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, s));
-            by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, s));
-            sfx += __shfl_xor_sync(0xffffffffu, sfx, s);
-            sfy += __shfl_xor_sync(0xffffffffu, sfy, s);
+            const unsigned long long t = __shfl_xor_sync(FULL, mk, s);
+            mk = t > mk ? t : mk;
         }
+        if (lane == 0 && mk) atomicMax(&s_max, mk);
     }
-    if (lane == 0) {
-        BlockStats& b = red[wid];
-        b.n_total = c_tot; b.n_fixed = c_fix; b.pos = c_pos; b.neg = c_neg; b.tp_t = c_tpt; b.fp_t = c_fpt;
-        b.tp_f = c_tpf; b.fp_f = c_fpf; b.x0 = bx0; b.y0 = by0; b.x1 = bx1; b.y1 = by1; b.sfx = sfx; b.sfy = sfy;
-        b.maxphi = __longlong_as_double((long long)mk);
+    if (seg) {
+        c_pos = __reduce_add_sync(FULL, c_pos); c_neg = __reduce_add_sync(FULL, c_neg);
+        c_tpt = __reduce_add_sync(FULL, c_tpt); c_fpt = __reduce_add_sync(FULL, c_fpt);
+        c_tpf = __reduce_add_sync(FULL, c_tpf); c_fpf = __reduce_add_sync(FULL, c_fpf);
+        bx0 = __reduce_min_sync(FULL, bx0); by0 = __reduce_min_sync(FULL, by0);
+        bx1 = __reduce_max_sync(FULL, bx1); by1 = __reduce_max_sync(FULL, by1);
+        const bool any_sum = __any_sync(FULL, sfx != 0.0 || sfy != 0.0);
+        if (any_sum) {
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                sfx += __shfl_xor_sync(FULL, sfx, s);
+                sfy += __shfl_xor_sync(FULL, sfy, s);
+            }
+        }
+        if (lane == 0) {
+            if (c_pos) atomicAdd(&s_cnt[2], c_pos);
+            if (c_neg) atomicAdd(&s_cnt[3], c_neg);
+            if (c_tpt) atomicAdd(&s_cnt[4], c_tpt);
+            if (c_fpt) atomicAdd(&s_cnt[5], c_fpt);
+            if (c_tpf) atomicAdd(&s_cnt[6], c_tpf);
+            if (c_fpf) atomicAdd(&s_cnt[7], c_fpf);
+            if (bx1 >= 0) { atomicMin(&s_bb[0], bx0); atomicMin(&s_bb[1], by0); atomicMax(&s_bb[2], bx1); atomicMax(&s_bb[3], by1); }
+            if (any_sum) { atomicAdd(&s_sum[0], sfx); atomicAdd(&s_sum[1], sfy); }
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        BlockStats t = red[0];
-        for (int k = 1; k < 8; ++k) {
-            const BlockStats& b = red[k];
-            t.n_total += b.n_total; t.n_fixed += b.n_fixed; t.pos += b.pos; t.neg += b.neg; t.tp_t += b.tp_t;
-            t.fp_t += b.fp_t; t.tp_f += b.tp_f; t.fp_f += b.fp_f;
-            t.x0 = min(t.x0, b.x0); t.y0 = min(t.y0, b.y0); t.x1 = max(t.x1, b.x1); t.y1 = max(t.y1, b.y1);
-            t.sfx += b.sfx; t.sfy += b.sfy; t.maxphi = fmax(t.maxphi, b.maxphi);
-        }
-        mavd_frame_stats* st = reinterpret_cast<mavd_frame_stats*>(stats_base + (size_t)f * stats_stride);
+        mavd_frame_stats* st = reinterpret_cast<mavd_frame_stats*>(A.stats_base + (size_t)f * A.stats_stride);
         typedef unsigned long long ull;
-        if (t.n_total) atomicAdd((ull*)&st->n_total, (ull)t.n_total);
-        if (t.n_fixed) atomicAdd((ull*)&st->n_fixed, (ull)t.n_fixed);
-        if (t.maxphi > 0.0) atomicMax((ull*)&st->max_phi, dmax_key(t.maxphi));
+        if (s_cnt[0]) atomicAdd((ull*)&st->n_total, (ull)s_cnt[0]);
+        if (s_cnt[1]) atomicAdd((ull*)&st->n_fixed, (ull)s_cnt[1]);
+        if (!FAST && s_max) atomicMax((ull*)&st->max_phi, s_max);
         if (seg) {
-            if (t.pos) atomicAdd((ull*)&st->positives, (ull)t.pos);
-            if (t.neg) atomicAdd((ull*)&st->negatives, (ull)t.neg);
-            if (t.tp_t) atomicAdd((ull*)&st->tp_total, (ull)t.tp_t);
-            if (t.fp_t) atomicAdd((ull*)&st->fp_total, (ull)t.fp_t);
-            if (t.tp_f) atomicAdd((ull*)&st->tp_fixed, (ull)t.tp_f);
-            if (t.fp_f) atomicAdd((ull*)&st->fp_fixed, (ull)t.fp_f);
-            if (t.x1 >= 0) {
+            if (s_cnt[2]) atomicAdd((ull*)&st->positives, (ull)s_cnt[2]);
+            if (s_cnt[3]) atomicAdd((ull*)&st->negatives, (ull)s_cnt[3]);
+            if (s_cnt[4]) atomicAdd((ull*)&st->tp_total, (ull)s_cnt[4]);
+            if (s_cnt[5]) atomicAdd((ull*)&st->fp_total, (ull)s_cnt[5]);
+            if (s_cnt[6]) atomicAdd((ull*)&st->tp_fixed, (ull)s_cnt[6]);
+            if (s_cnt[7]) atomicAdd((ull*)&st->fp_fixed, (ull)s_cnt[7]);
+            if (s_bb[2] >= 0) {
                 // seg_bbox was initialised to {INT_MAX, INT_MAX, -1, -1} by stats_init_kernel
-                atomicMin(&st->seg_bbox[0], t.x0); atomicMin(&st->seg_bbox[1], t.y0);
-                atomicMax(&st->seg_bbox[2], t.x1); atomicMax(&st->seg_bbox[3], t.y1);
+                atomicMin(&st->seg_bbox[0], s_bb[0]); atomicMin(&st->seg_bbox[1], s_bb[1]);
+                atomicMax(&st->seg_bbox[2], s_bb[2]); atomicMax(&st->seg_bbox[3], s_bb[3]);
             }
-            if (t.sfx != 0.0) atomicAdd(&st->seg_flow_sum[0], t.sfx);
-            if (t.sfy != 0.0) atomicAdd(&st->seg_flow_sum[1], t.sfy);
+            if (s_sum[0] != 0.0) atomicAdd(&st->seg_flow_sum[0], s_sum[0]);
+            if (s_sum[1] != 0.0) atomicAdd(&st->seg_flow_sum[1], s_sum[1]);
         }
     }
 }
@@ -439,43 +702,77 @@ __global__ void stats_init_kernel(char* stats_base, size_t stats_stride, int n, 
     if (seg_max) seg_max[f] = 0;
 }
 
-__global__ void stats_final_kernel(char* stats_base, size_t stats_stride, int n) {
+// no_max_phi: the FAST path ran (for the frames with imu.derotate != 0, or for all frames when imu is NULL)
+__global__ void stats_final_kernel(char* stats_base, size_t stats_stride, int n, int no_max_phi, const mavd_imu* imu) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
     mavd_frame_stats* st = reinterpret_cast<mavd_frame_stats*>(stats_base + (size_t)f * stats_stride);
     if (st->seg_bbox[2] < 0) st->seg_bbox[0] = st->seg_bbox[1] = st->seg_bbox[2] = st->seg_bbox[3] = -1;
+    if (no_max_phi && (imu == nullptr || imu[f].derotate != 0)) st->max_phi = -1.0;
 }
 
-int residual_run(mavd_handle H, const float* d_flow, int n, const mavd_imu* d_imu, const mavd_detect_params& p,
-                 const double* d_foe, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
-                 int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
-                 size_t stats_stride, int run_f64, int run_f32, cudaStream_t s) {
+template <int MODE, bool FAST>
+static int launch_residual(const ResidualArgs& A, const FastPrm& fp, int n, bool vec4, cudaStream_t s) {
+    const int npx = A.w * A.h;
+    if (vec4) {
+        dim3 g(ceil_div(npx / 4, 256 * RES_ITEMS), n);
+        residual_kernel<MODE, FAST, 4><<<g, 256, 0, s>>>(A, fp);
+    } else {
+        dim3 g(ceil_div(npx, 256 * RES_ITEMS), n);
+        residual_kernel<MODE, FAST, 1><<<g, 256, 0, s>>>(A, fp);
+    }
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+// flow_kind: 0 = float32 flow with the per-frame imu deciding between MODE 0 and MODE 1,
+//            1 = float32 flow, no derotation for any frame (MODE 1), 2 = float64 flow, no derotation (MODE 2)
+int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu,
+                 const mavd_detect_params& p, const double* d_foe, const uint8_t* d_sky, int64_t sky_stride,
+                 const uint8_t* d_seg, int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed,
+                 mavd_frame_stats* d_stats, size_t stats_stride, int run_f64, int run_f32, cudaStream_t s) {
     ProfScope ps(&H->prof, MAVD_PROF_RESIDUAL, s);
     const int w = H->cfg.width, h = H->cfg.height;
+    const int64_t npx = (int64_t)w * h;
     int* seg_max = reinterpret_cast<int*>(H->d_scan);  // scratch: n ints
+    // FAST needs: phi not requested, and the parameter ranges its guard bands were derived for
+    const bool fast = !H->force_exact_residual && d_phi == nullptr && p.fixed_angle >= 0.0 && p.dyn_gain >= 0.0 &&
+                      p.dyn_offset - p.dyn_base < -1e-2 && p.dyn_min_mag >= 0.0 && p.fixed_min_mag >= 0.0 &&
+                      p.fixed_angle < 1e3 && p.dyn_offset + p.dyn_base < 1e3 && p.dyn_gain < 1e6 &&
+                      p.dyn_min_mag < 1e6 && p.fixed_min_mag < 1e6;
     if (d_stats) {
         stats_init_kernel<<<ceil_div(n, 128), 128, 0, s>>>((char*)d_stats, stats_stride, n, d_seg ? seg_max : nullptr);
         MAVD_LAUNCHED();
         if (d_seg) {
-            dim3 g(148 * 2, n);
-            seg_max_kernel<<<g, 256, 0, s>>>(d_seg, seg_stride, (int64_t)w * h, seg_max);
+            dim3 g(32, n);
+            seg_max_kernel<<<g, 256, 0, s>>>(d_seg, seg_stride, npx, seg_max);
             MAVD_LAUNCHED();
         }
     }
-    ResidualPrm rp{p.dyn_offset, p.dyn_base, p.dyn_gain, p.dyn_min_mag, p.fixed_min_mag, p.fixed_angle};
-    dim3 g(ceil_div(w, 64), ceil_div(h, 4), n);
-    if (run_f64) {
-        residual_kernel<true><<<g, 256, 0, s>>>((const float2*)d_flow, d_imu, d_foe, w, h, rp, d_sky, sky_stride, d_seg,
-                                                seg_stride, seg_max, d_phi, d_total, d_fixed, (char*)d_stats, stats_stride);
-        MAVD_LAUNCHED();
+    ResidualArgs A;
+    A.flow = d_flow; A.imu = flow_kind == 0 ? d_imu : nullptr; A.foe = d_foe; A.xn = H->d_xn; A.yn = H->d_yn; A.w = w; A.h = h;
+    A.prm = ResidualPrm{p.dyn_offset, p.dyn_base, p.dyn_gain, p.dyn_min_mag, p.fixed_min_mag, p.fixed_angle};
+    A.sky = d_sky; A.sky_stride = sky_stride; A.seg = d_seg; A.seg_stride = seg_stride; A.seg_max = seg_max;
+    A.phi_out = d_phi; A.total_out = d_total; A.fixed_out = d_fixed;
+    A.stats_base = (char*)d_stats; A.stats_stride = stats_stride;
+    const FastPrm fp{(float)p.dyn_offset, (float)p.dyn_base, (float)p.dyn_gain, (float)p.dyn_min_mag,
+                     (float)p.fixed_min_mag, (float)p.fixed_angle};
+    auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+    const bool vec4 = (w % 4 == 0) && al(d_flow, 16) && al(d_sky, 4) && al(d_seg, 4) && al(d_total, 4) && al(d_fixed, 4) &&
+                      (sky_stride % 4 == 0) && (seg_stride % 4 == 0);
+    bool used_fast = false;
+    if (flow_kind == 2) {
+        if (fast) { used_fast = true; TRY_RC(launch_residual<2, true>(A, fp, n, vec4, s)); }
+        else      TRY_RC(launch_residual<2, false>(A, fp, n, vec4, s));
+    } else {
+        if (flow_kind == 0 && run_f64) {
+            if (fast) { used_fast = true; TRY_RC(launch_residual<0, true>(A, fp, n, vec4, s)); }
+            else      TRY_RC(launch_residual<0, false>(A, fp, n, vec4, s));
+        }
+        if (flow_kind == 1 || run_f32) TRY_RC(launch_residual<1, false>(A, fp, n, vec4, s));
     }
-    if (run_f32) {
-        residual_kernel<false><<<g, 256, 0, s>>>((const float2*)d_flow, d_imu, d_foe, w, h, rp, d_sky, sky_stride, d_seg,
-                                                 seg_stride, seg_max, d_phi, d_total, d_fixed, (char*)d_stats, stats_stride);
-        MAVD_LAUNCHED();
-    }
-    if (d_stats && d_seg) {
-        stats_final_kernel<<<ceil_div(n, 128), 128, 0, s>>>((char*)d_stats, stats_stride, n);
+    if (d_stats) {
+        stats_final_kernel<<<ceil_div(n, 128), 128, 0, s>>>((char*)d_stats, stats_stride, n, used_fast ? 1 : 0, A.imu);
         MAVD_LAUNCHED();
     }
     return MAVD_OK;
@@ -484,6 +781,13 @@ int residual_run(mavd_handle H, const float* d_flow, int n, const mavd_imu* d_im
 // ------------------------------------------------------------------------------------------------
 // Connected components (8-connectivity), union-find with the smaller raster index as the root, so a
 // component's root is its first pixel in raster order and ranking the roots gives canonical labels.
+//
+// Detection masks are sparse, so every pass scans the uint8 mask one 32-bit word (4 pixels) per
+// thread and does nothing for all-zero words; parent[] is only ever touched at foreground pixels
+// (background entries are never initialised nor read).  Passes: init -> merge -> flatten+count roots
+// per 4096-pixel chunk -> scan -> rank roots -> relabel (+ per-component boxes).  The label image is
+// written only when the caller asks for it.  VEC = 1 (one pixel per thread) covers widths that are
+// not a multiple of 4 and unaligned masks.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int uf_find(int* parent, int i) {
     int p = parent[i];
@@ -506,51 +810,78 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int npx) {
-    const size_t base = (size_t)blockIdx.y * npx;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x)
-        parent[base + i] = mask[base + i] ? i : -1;
+template <int VEC>
+__device__ __forceinline__ unsigned load_mask_word(const uint8_t* __restrict__ m, int i0) {
+    if (VEC == 4) return __ldg(reinterpret_cast<const unsigned*>(m + i0));
+    return m[i0];
 }
 
+template <int VEC>
+__global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int npx) {
+    const size_t base = (size_t)blockIdx.y * npx;
+    const int ngrp = npx / VEC;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ngrp; q += gridDim.x * blockDim.x) {
+        const int i0 = q * VEC;
+        const unsigned wv = load_mask_word<VEC>(mask + base, i0);
+        if (wv == 0) continue;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+            if ((wv >> (8 * k)) & 255u) parent[base + i0 + k] = i0 + k;
+    }
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w, int h) {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= w || y >= h) return;
-    const size_t base = (size_t)blockIdx.z * w * h;
+    const int npx = w * h;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npx / VEC) return;
+    const size_t base = (size_t)blockIdx.y * npx;
     const uint8_t* m = mask + base;
+    const int i0 = q * VEC;
+    const unsigned wv = load_mask_word<VEC>(m, i0);
+    if (wv == 0) return;
     int* par = parent + base;
-    const int i = y * w + x;
-    if (!m[i]) return;
-    if (x > 0 && m[i - 1]) uf_union(par, i, i - 1);
-    if (y > 0) {
-        if (m[i - w]) uf_union(par, i, i - w);
-        else {
-            // with the pixel above set, both diagonals are already joined through it
-            if (x > 0 && m[i - w - 1]) uf_union(par, i, i - w - 1);
-            if (x + 1 < w && m[i - w + 1]) uf_union(par, i, i - w + 1);
+    const int y = i0 / w, x0 = i0 - y * w;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        if (!((wv >> (8 * k)) & 255u)) continue;
+        const int i = i0 + k, x = x0 + k;
+        const bool left = (k > 0) ? (((wv >> (8 * (k - 1))) & 255u) != 0) : (x > 0 && m[i - 1]);
+        if (left) uf_union(par, i, i - 1);
+        if (y > 0) {
+            if (m[i - w]) uf_union(par, i, i - w);
+            else {
+                // with the pixel above set, both diagonals are already joined through it
+                if (x > 0 && m[i - w - 1]) uf_union(par, i, i - w - 1);
+                if (x + 1 < w && m[i - w + 1]) uf_union(par, i, i - w + 1);
+            }
         }
     }
 }
 
 constexpr int CCL_CHUNK = 4096;  // pixels per block in the root-ranking passes
 
-__global__ void __launch_bounds__(256) ccl_flatten_count_kernel(int* __restrict__ parent, int npx, int* __restrict__ chunk_cnt,
-                                                               int n_chunks) {
+template <int VEC>
+__global__ void __launch_bounds__(256) ccl_flatten_count_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent,
+                                                               int npx, int* __restrict__ chunk_cnt, int n_chunks) {
     const size_t base = (size_t)blockIdx.y * npx;
     int* par = parent + base;
-    const int c0 = blockIdx.x * CCL_CHUNK;
+    const int c0 = blockIdx.x * CCL_CHUNK, c1 = min(c0 + CCL_CHUNK, npx);
     int cnt = 0;
-    for (int i = c0 + threadIdx.x; i < min(c0 + CCL_CHUNK, npx); i += 256) {
-        int p = par[i];
-        if (p >= 0) {
-            int r = uf_find(par, i);
+    for (int i0 = c0 + threadIdx.x * VEC; i0 < c1; i0 += 256 * VEC) {
+        const unsigned wv = load_mask_word<VEC>(mask + base, i0);
+        if (wv == 0) continue;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            if (!((wv >> (8 * k)) & 255u)) continue;
+            const int i = i0 + k;
+            const int r = uf_find(par, i);
             par[i] = r;   // benign race: every writer stores a valid ancestor, roots never change here
             cnt += (r == i);
         }
     }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
     __shared__ int wsum[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -599,27 +930,47 @@ __global__ void __launch_bounds__(1024) ccl_scan_kernel(int* __restrict__ chunk_
     if (threadIdx.x == 0) *reinterpret_cast<int32_t*>(nlabels_base + (size_t)blockIdx.x * nlabels_stride) = carry_s;
 }
 
-// rank[root] = canonical label of the component rooted at `root`
-__global__ void __launch_bounds__(256) ccl_rank_kernel(const int* __restrict__ parent, int npx, const int* __restrict__ chunk_off,
-                                                      int n_chunks, int* __restrict__ rank) {
+// rank[root] = canonical label of the component rooted at `root` (roots ordered by raster index)
+template <int VEC>
+__global__ void __launch_bounds__(256) ccl_rank_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ parent,
+                                                      int npx, const int* __restrict__ chunk_off, int n_chunks,
+                                                      int* __restrict__ rank) {
     const size_t base = (size_t)blockIdx.y * npx;
     const int* par = parent + base;
     int* rk = rank + base;
-    const int c0 = blockIdx.x * CCL_CHUNK;
+    const int c0 = blockIdx.x * CCL_CHUNK, c1 = min(c0 + CCL_CHUNK, npx);
     __shared__ int wsum[8];
     __shared__ int running;
     if (threadIdx.x == 0) running = chunk_off[(size_t)blockIdx.y * n_chunks + blockIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int s0 = c0; s0 < min(c0 + CCL_CHUNK, npx); s0 += 256) {
-        const int i = s0 + threadIdx.x;
-        const bool root = (i < npx) && (par[i] == i);
-        const unsigned bal = __ballot_sync(0xffffffffu, root);
-        if (lane == 0) wsum[wid] = __popc(bal);
+    for (int s0 = c0; s0 < c1; s0 += 256 * VEC) {
+        const int i0 = s0 + threadIdx.x * VEC;
+        unsigned roots = 0;   // bit k: pixel i0 + k is a root
+        if (i0 < c1) {
+            const unsigned wv = load_mask_word<VEC>(mask + base, i0);
+            if (wv) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    if (((wv >> (8 * k)) & 255u) && par[i0 + k] == i0 + k) roots |= 1u << k;
+            }
+        }
+        const int mine = __popc(roots);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[wid] = incl;
         __syncthreads();
-        int off = running;
-        for (int k = 0; k < wid; ++k) off += wsum[k];
-        if (root) rk[i] = off + __popc(bal & ((1u << lane) - 1u)) + 1;
+        if (mine) {
+            int off = running + incl - mine;
+            for (int k = 0; k < wid; ++k) off += wsum[k];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if (roots & (1u << k)) rk[i0 + k] = ++off;
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = 0;
@@ -638,23 +989,38 @@ __global__ void ccl_boxes_init_kernel(int32_t* boxes, size_t boxes_stride, int m
     p[0] = 0x7fffffff; p[1] = 0x7fffffff; p[2] = -1; p[3] = -1; p[4] = 0;
 }
 
-__global__ void __launch_bounds__(256) ccl_relabel_kernel(int* __restrict__ labels, const int* __restrict__ rank, int w, int h,
+// labels_out may alias parent (each thread reads only its own parent entries before writing them)
+template <int VEC>
+__global__ void __launch_bounds__(256) ccl_relabel_kernel(const uint8_t* __restrict__ mask, const int* parent,
+                                                         const int* __restrict__ rank, int w, int h, int* labels_out,
                                                          int32_t* __restrict__ boxes, size_t boxes_stride, int max_boxes) {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= w || y >= h) return;
-    const size_t base = (size_t)blockIdx.z * w * h;
-    const int i = y * w + x;
-    const int r = labels[base + i];
-    int lab = 0;
-    if (r >= 0) {
-        lab = rank[base + r];
-        if (boxes && lab <= max_boxes) {
-            int32_t* b = boxes + (size_t)blockIdx.z * boxes_stride + (lab - 1) * 5;
-            atomicMin(b + 0, x); atomicMin(b + 1, y); atomicMax(b + 2, x); atomicMax(b + 3, y); atomicAdd(b + 4, 1);
+    const int npx = w * h;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npx / VEC) return;
+    const size_t base = (size_t)blockIdx.y * npx;
+    const int i0 = q * VEC;
+    const unsigned wv = load_mask_word<VEC>(mask + base, i0);
+    int lab[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) lab[k] = 0;
+    if (wv) {
+        const int y = i0 / w, x0 = i0 - y * w;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            if (!((wv >> (8 * k)) & 255u)) continue;
+            const int l = rank[base + parent[base + i0 + k]];
+            lab[k] = l;
+            if (boxes && l <= max_boxes) {
+                int32_t* b = boxes + (size_t)blockIdx.y * boxes_stride + (l - 1) * 5;
+                const int x = x0 + k;
+                atomicMin(b + 0, x); atomicMin(b + 1, y); atomicMax(b + 2, x); atomicMax(b + 3, y); atomicAdd(b + 4, 1);
+            }
         }
     }
-    labels[base + i] = lab;
+    if (labels_out) {
+        if (VEC == 4) *reinterpret_cast<int4*>(labels_out + base + i0) = make_int4(lab[0], lab[1], lab[2], lab[3]);
+        else labels_out[base + i0] = lab[0];
+    }
 }
 
 __global__ void ccl_boxes_final_kernel(int32_t* boxes, size_t boxes_stride, int max_boxes, int n) {
@@ -666,35 +1032,51 @@ __global__ void ccl_boxes_final_kernel(int32_t* boxes, size_t boxes_stride, int 
     else { p[2] = p[2] - p[0] + 1; p[3] = p[3] - p[1] + 1; }
 }
 
-int ccl_run(mavd_handle H, const uint8_t* d_mask, int n, int32_t* d_labels, int32_t* d_boxes, size_t boxes_stride,
-            int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s) {
-    ProfScope ps(&H->prof, MAVD_PROF_CCL, s);
+template <int VEC>
+static int ccl_launch(mavd_handle H, const uint8_t* d_mask, int n, int* parent, int32_t* labels_out, int32_t* d_boxes,
+                      size_t boxes_stride, int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s) {
     const int w = H->cfg.width, h = H->cfg.height, npx = w * h;
     const int n_chunks = ceil_div(npx, CCL_CHUNK);
-    int* rank = H->d_scan;                                  // [n][npx]
+    int* rank = H->d_scan;                                        // [n][npx], written and read at roots only
     int* chunk_cnt = H->d_scan + (size_t)H->cfg.max_pairs * npx;  // [n][n_chunks]
-    ccl_init_kernel<<<dim3(148 * 4, n), 256, 0, s>>>(d_mask, d_labels, npx);
+    const int ngrp = npx / VEC;
+    ccl_init_kernel<VEC><<<dim3(min(ceil_div(ngrp, 256), 148 * 8), n), 256, 0, s>>>(d_mask, parent, npx);
     MAVD_LAUNCHED();
-    dim3 g(ceil_div(w, 64), ceil_div(h, 4), n);
-    ccl_merge_kernel<<<g, 256, 0, s>>>(d_mask, d_labels, w, h);
+    dim3 g(ceil_div(ngrp, 256), n);
+    ccl_merge_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, w, h);
     MAVD_LAUNCHED();
-    ccl_flatten_count_kernel<<<dim3(n_chunks, n), 256, 0, s>>>(d_labels, npx, chunk_cnt, n_chunks);
+    ccl_flatten_count_kernel<VEC><<<dim3(n_chunks, n), 256, 0, s>>>(d_mask, parent, npx, chunk_cnt, n_chunks);
     MAVD_LAUNCHED();
     ccl_scan_kernel<<<n, 1024, 0, s>>>(chunk_cnt, n_chunks, (char*)d_n_labels, nlabels_stride);
     MAVD_LAUNCHED();
-    ccl_rank_kernel<<<dim3(n_chunks, n), 256, 0, s>>>(d_labels, npx, chunk_cnt, n_chunks, rank);
+    ccl_rank_kernel<VEC><<<dim3(n_chunks, n), 256, 0, s>>>(d_mask, parent, npx, chunk_cnt, n_chunks, rank);
     MAVD_LAUNCHED();
     if (d_boxes) {
         ccl_boxes_init_kernel<<<ceil_div(n * max_boxes, 128), 128, 0, s>>>(d_boxes, boxes_stride, max_boxes, n);
         MAVD_LAUNCHED();
     }
-    ccl_relabel_kernel<<<g, 256, 0, s>>>(d_labels, rank, w, h, d_boxes, boxes_stride, max_boxes);
-    MAVD_LAUNCHED();
+    if (d_boxes || labels_out) {
+        ccl_relabel_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, rank, w, h, labels_out, d_boxes, boxes_stride, max_boxes);
+        MAVD_LAUNCHED();
+    }
     if (d_boxes) {
         ccl_boxes_final_kernel<<<ceil_div(n * max_boxes, 128), 128, 0, s>>>(d_boxes, boxes_stride, max_boxes, n);
         MAVD_LAUNCHED();
     }
     return MAVD_OK;
+}
+
+// d_labels: the caller's label image (also used as the union-find array), or NULL when only the
+// component count / boxes are wanted (the handle's scratch then holds the union-find array).
+int ccl_run(mavd_handle H, const uint8_t* d_mask, int n, int32_t* d_labels, int32_t* d_boxes, size_t boxes_stride,
+            int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s) {
+    ProfScope ps(&H->prof, MAVD_PROF_CCL, s);
+    const int w = H->cfg.width, h = H->cfg.height;
+    int* parent = d_labels ? d_labels : H->d_labels;
+    const bool vec4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_mask) & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(parent) & 15) == 0) && (((size_t)w * h) % 4 == 0);
+    if (vec4) return ccl_launch<4>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s);
+    return ccl_launch<1>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s);
 }
 
 }  // namespace mavd

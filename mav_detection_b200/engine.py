@@ -37,6 +37,10 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _hp(a: Optional[np.ndarray]) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
 class Engine:
     """One handle per (device, W, H, Farneback parameters) — SURVEY.md §8b threading/state."""
 
@@ -67,6 +71,7 @@ class Engine:
         self.levels: List[Tuple[int, int]] = [(ws[i], hs[i]) for i in range(n.value)]
         self.detect_params = DetectParams()
         self.lib.mavd_default_detect_params(C.byref(self.detect_params))
+        self._inflight: Dict[int, tuple] = {}
 
     # -- lifecycle --------------------------------------------------------------------------
     def close(self) -> None:
@@ -172,13 +177,63 @@ class Engine:
                                            self._stream()))
         return phi, total, fixed, stats
 
+    # -- reference-literal seams (FocusOfExpansion methods on a flow array of either dtype) -----
+    def _flow_kind(self, flow: torch.Tensor) -> int:
+        if flow.dtype not in (torch.float32, torch.float64) or not flow.is_cuda or not flow.is_contiguous():
+            raise ValueError('flow must be a contiguous CUDA float32/float64 tensor (n, H, W, 2)')
+        if tuple(flow.shape[1:]) != (self.height, self.width, 2):
+            raise ValueError('flow must have shape (n, %d, %d, 2), got %s' % (self.height, self.width, tuple(flow.shape)))
+        return 1 if flow.dtype == torch.float64 else 0
+
+    def foe_dense(self, flow: torch.Tensor, samples: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """FocusOfExpansion.get_FOE_dense(flow_uv) on the flow as given (no IMU) — focus_of_expansion.py:56-86."""
+        n = flow.shape[0]
+        if samples.dtype != torch.int32 or tuple(samples.shape) != (n, _lib.SAMPLES_PER_FRAME):
+            raise ValueError('samples must be int32 (n, %d): [ry(2000) | rx(2000)]' % _lib.SAMPLES_PER_FRAME)
+        foe = torch.empty((n, 2), dtype=torch.float64, device=self.device)
+        cnt = torch.empty((n,), dtype=torch.int32, device=self.device)
+        check(self.lib.mavd_foe_dense(self._h, flow.data_ptr(), self._flow_kind(flow), n, C.byref(self.detect_params),
+                                      samples.data_ptr(), foe.data_ptr(), cnt.data_ptr(), self._stream()))
+        return foe, cnt
+
+    def ransac(self, estimates: torch.Tensor, threshold: Optional[float] = None) -> torch.Tensor:
+        """FocusOfExpansion.ransac(estimates) — focus_of_expansion.py:32-54.  (K, 2) float64 -> (2,) float64."""
+        if estimates.dtype != torch.float64 or estimates.dim() != 2 or estimates.shape[1] != 2:
+            raise ValueError('estimates must be a (K, 2) float64 tensor')
+        estimates = estimates.contiguous()
+        out = torch.empty((2,), dtype=torch.float64, device=self.device)
+        thr = self.detect_params.ransac_threshold if threshold is None else float(threshold)
+        check(self.lib.mavd_ransac(self._h, estimates.data_ptr() if estimates.shape[0] else None, estimates.shape[0],
+                                   thr, out.data_ptr(), self._stream()))
+        return out
+
+    def get_phi(self, flow: torch.Tensor, foe: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """FocusOfExpansion.get_phi(flow, FoE) — focus_of_expansion.py:150-184.  Returns (phi in the flow's
+        dtype, per-frame max phi = the max_flow side effect)."""
+        n = flow.shape[0]
+        kind = self._flow_kind(flow)
+        phi = torch.empty((n, self.height, self.width), dtype=flow.dtype, device=self.device)
+        mx = torch.empty((n,), dtype=torch.float64, device=self.device)
+        foe = foe.to(device=self.device, dtype=torch.float64).contiguous()
+        if kind == 0:
+            # the C ABI lays float32 phi at the front of each frame's 8-byte-per-pixel slot
+            buf = torch.empty((n, self.height, self.width), dtype=torch.float64, device=self.device)
+            check(self.lib.mavd_get_phi(self._h, flow.data_ptr(), 0, n, foe.data_ptr(), buf.data_ptr(), mx.data_ptr(),
+                                        self._stream()))
+            npx = self.height * self.width
+            phi = buf.view(torch.float32).view(n, 2 * npx)[:, :npx].reshape(n, self.height, self.width).clone()
+        else:
+            check(self.lib.mavd_get_phi(self._h, flow.data_ptr(), 1, n, foe.data_ptr(), phi.data_ptr(), mx.data_ptr(),
+                                        self._stream()))
+        return phi, mx
+
     # -- stage 4 -----------------------------------------------------------------------------
-    def ccl(self, mask: torch.Tensor, max_boxes: int = _lib.MAX_BOXES):
+    def ccl(self, mask: torch.Tensor, max_boxes: int = _lib.MAX_BOXES, want_labels: bool = True):
         n = mask.shape[0]
-        labels = torch.empty((n, self.height, self.width), dtype=torch.int32, device=self.device)
+        labels = torch.empty((n, self.height, self.width), dtype=torch.int32, device=self.device) if want_labels else None
         boxes = torch.zeros((n, max_boxes, 5), dtype=torch.int32, device=self.device)
         cnt = torch.empty((n,), dtype=torch.int32, device=self.device)
-        check(self.lib.mavd_ccl(self._h, mask.data_ptr(), n, labels.data_ptr(), boxes.data_ptr(), max_boxes,
+        check(self.lib.mavd_ccl(self._h, mask.data_ptr(), n, _ptr(labels), boxes.data_ptr(), max_boxes,
                                 cnt.data_ptr(), self._stream()))
         return labels, boxes, cnt
 
@@ -203,11 +258,25 @@ class Engine:
                                     records.data_ptr(), self._stream()))
         return records
 
-    def process_host(self, frames: np.ndarray, imu, samples: np.ndarray, n_pairs: Optional[int] = None,
-                     pair_stride: int = 1, sky: Optional[np.ndarray] = None, seg: Optional[np.ndarray] = None,
-                     flow_out: Optional[np.ndarray] = None, fixed_out: Optional[np.ndarray] = None,
-                     records: Optional[np.ndarray] = None) -> np.ndarray:
-        """The end-to-end call: HOST buffers in, HOST records (and optional masks / flow) out."""
+    def detect(self, flow: torch.Tensor, imu, samples: torch.Tensor, sky: Optional[torch.Tensor] = None,
+               seg: Optional[torch.Tensor] = None, total_out: Optional[torch.Tensor] = None,
+               fixed_out: Optional[torch.Tensor] = None, records: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """derotate -> FoE -> phi/masks -> components from a given float32 flow (the Dataset.get_flow_uv seam)."""
+        n = flow.shape[0]
+        if flow.dtype != torch.float32 or not flow.is_cuda or not flow.is_contiguous() or \
+                tuple(flow.shape[1:]) != (self.height, self.width, 2):
+            raise ValueError('flow must be a contiguous CUDA float32 tensor (n, %d, %d, 2)' % (self.height, self.width))
+        npx = self.width * self.height
+        if records is None:
+            records = torch.empty((n, RECORD_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+        sky_stride = 0 if (sky is None or sky.dim() == 2) else npx
+        seg_stride = 0 if (seg is None or seg.dim() == 2) else npx
+        check(self.lib.mavd_detect(self._h, flow.data_ptr(), n, imu, C.byref(self.detect_params), samples.data_ptr(),
+                                   _ptr(sky), sky_stride, _ptr(seg), seg_stride, _ptr(total_out), _ptr(fixed_out),
+                                   records.data_ptr(), self._stream()))
+        return records
+
+    def _host_args(self, frames, samples, n_pairs, pair_stride, sky, seg, flow_out, fixed_out, records):
         if n_pairs is None:
             n_pairs = frames.shape[0] - 1 if pair_stride == 1 else frames.shape[0] // 2
         npx = self.width * self.height
@@ -217,18 +286,65 @@ class Engine:
                         ('flow_out', flow_out), ('fixed_out', fixed_out)):
             if a is not None and not a.flags['C_CONTIGUOUS']:
                 raise ValueError('%s must be C-contiguous' % name)
-        if frames.dtype != np.uint8 or samples.dtype != np.int32:
-            raise ValueError('frames must be uint8 and samples int32')
-
-        def hp(a):
-            return None if a is None else a.ctypes.data
+        if samples.dtype != np.int32:
+            raise ValueError('samples must be int32')
+        need = n_pairs + 1 if pair_stride == 1 else 2 * n_pairs
+        if frames is not None and (frames.dtype != np.uint8 or frames.shape[0] < need or
+                                   tuple(frames.shape[1:]) != (self.height, self.width)):
+            raise ValueError('frames must be uint8 (>=%d, %d, %d)' % (need, self.height, self.width))
         sky_stride = 0 if (sky is None or sky.ndim == 2) else npx
         seg_stride = 0 if (seg is None or seg.ndim == 2) else npx
+        return n_pairs, records, sky_stride, seg_stride
+
+    def process_host(self, frames: np.ndarray, imu, samples: np.ndarray, n_pairs: Optional[int] = None,
+                     pair_stride: int = 1, sky: Optional[np.ndarray] = None, seg: Optional[np.ndarray] = None,
+                     flow_out: Optional[np.ndarray] = None, fixed_out: Optional[np.ndarray] = None,
+                     records: Optional[np.ndarray] = None) -> np.ndarray:
+        """The end-to-end call: HOST buffers in, HOST records (and optional masks / flow) out."""
+        n_pairs, records, sky_stride, seg_stride = self._host_args(frames, samples, n_pairs, pair_stride, sky, seg,
+                                                                   flow_out, fixed_out, records)
         with torch.cuda.device(self.device):
-            check(self.lib.mavd_process_host(self._h, hp(frames), n_pairs, pair_stride, imu,
-                                             C.byref(self.detect_params), hp(samples), hp(sky), sky_stride,
-                                             hp(seg), seg_stride, hp(flow_out), hp(fixed_out),
+            check(self.lib.mavd_process_host(self._h, _hp(frames), n_pairs, pair_stride, imu,
+                                             C.byref(self.detect_params), _hp(samples), _hp(sky), sky_stride,
+                                             _hp(seg), seg_stride, _hp(flow_out), _hp(fixed_out),
                                              records.ctypes.data, self._stream()))
+        return records
+
+    def submit_host(self, slot: int, frames: np.ndarray, imu, samples: np.ndarray, n_pairs: Optional[int] = None,
+                    pair_stride: int = 1, sky: Optional[np.ndarray] = None, seg: Optional[np.ndarray] = None,
+                    flow_out: Optional[np.ndarray] = None, fixed_out: Optional[np.ndarray] = None,
+                    records: Optional[np.ndarray] = None) -> np.ndarray:
+        """Asynchronous process_host: returns at once; the outputs are valid after wait_host(slot).  Keeping
+        up to _lib.HOST_SLOTS batches in flight overlaps the host<->device copies with the compute."""
+        n_pairs, records, sky_stride, seg_stride = self._host_args(frames, samples, n_pairs, pair_stride, sky, seg,
+                                                                   flow_out, fixed_out, records)
+        with torch.cuda.device(self.device):
+            check(self.lib.mavd_submit_host(self._h, slot, _hp(frames), n_pairs, pair_stride, imu,
+                                            C.byref(self.detect_params), _hp(samples), _hp(sky), sky_stride,
+                                            _hp(seg), seg_stride, _hp(flow_out), _hp(fixed_out),
+                                            records.ctypes.data, self._stream()))
+        # keep the host buffers alive until the wait
+        self._inflight[slot] = (frames, imu, samples, sky, seg, flow_out, fixed_out, records)
+        return records
+
+    def wait_host(self, slot: int) -> None:
+        check(self.lib.mavd_wait_host(self._h, slot))
+        self._inflight.pop(slot, None)
+
+    def detect_host(self, flow: np.ndarray, imu, samples: np.ndarray, sky: Optional[np.ndarray] = None,
+                    seg: Optional[np.ndarray] = None, fixed_out: Optional[np.ndarray] = None,
+                    records: Optional[np.ndarray] = None) -> np.ndarray:
+        """Detection from a HOST float32 flow (n, H, W, 2): what Processor.run_detection does with
+        Dataset.get_flow_uv (processor.py:305-362)."""
+        if flow.dtype != np.float32 or tuple(flow.shape[1:]) != (self.height, self.width, 2) or \
+                not flow.flags['C_CONTIGUOUS']:
+            raise ValueError('flow must be C-contiguous float32 (n, %d, %d, 2)' % (self.height, self.width))
+        n, records, sky_stride, seg_stride = self._host_args(None, samples, flow.shape[0], 1, sky, seg, None, fixed_out,
+                                                             records)
+        with torch.cuda.device(self.device):
+            check(self.lib.mavd_detect_host(self._h, flow.ctypes.data, n, imu, C.byref(self.detect_params),
+                                            _hp(samples), _hp(sky), sky_stride, _hp(seg), seg_stride, _hp(fixed_out),
+                                            records.ctypes.data, self._stream()))
         return records
 
     @staticmethod
@@ -243,6 +359,10 @@ class Engine:
         """Tests only: use the non-TMA iteration kernel even where the TMA kernel applies."""
         check(self.lib.mavd_debug_force_generic_iteration(self._h, 1 if on else 0))
 
+    def force_exact_residual(self, on: bool = True) -> None:
+        """Tests only: evaluate every pixel of the residual stage in float64 (no float32 pre-decision)."""
+        check(self.lib.mavd_debug_force_exact_residual(self._h, 1 if on else 0))
+
     def profile_enable(self, on: bool = True) -> None:
         check(self.lib.mavd_profile_enable(self._h, 1 if on else 0))
 
@@ -254,3 +374,23 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.mavd_launch_count())
+
+
+_SHARED: Dict[tuple, 'Engine'] = {}
+
+
+def shared_engine(width: int, height: int, params: Optional[Dict] = None, max_pairs: int = 1,
+                  device: Optional[int] = None) -> 'Engine':
+    """One cached Engine per (device, W, H, Farneback parameters, max_pairs) for the reference-named classes
+    (Farneback, Detector, FocusOfExpansion, Processor), which all work on the same frame geometry."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    p = dict(REFERENCE_PARAMS)
+    if params:
+        p.update(params)
+    key = (device, int(width), int(height), int(max_pairs), tuple(sorted(p.items())))
+    eng = _SHARED.get(key)
+    if eng is None or not eng._h.value:
+        eng = Engine(width, height, p, max_pairs=max_pairs, device=device)
+        _SHARED[key] = eng
+    return eng

@@ -60,3 +60,59 @@ def make_sequence(width: int, height: int, n_frames: int, seq: int = 0,
 def make_pair(width: int, height: int, seq: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     s = make_sequence(width, height, 2, seq)
     return s.frames[0], s.frames[1]
+
+
+class SyntheticDataset:
+    """The subset of the reference's Dataset interface that Processor.run_detection touches
+    (/root/reference/src/datasets/dataset.py:152-175,205-230,266-350, sim_data.py:56-81), backed by a
+    SyntheticSequence held in memory.  Stands in for SimData in tests, the bench and the examples."""
+
+    def __init__(self, seq: SyntheticSequence, sequence: str = 'synthetic', flows: np.ndarray = None,
+                 results_path: str = None, bgr: bool = False) -> None:
+        self.seq = seq
+        self.sequence = sequence
+        self.N = int(seq.frames.shape[0])
+        self.capture_size = (int(seq.frames.shape[2]), int(seq.frames.shape[1]))
+        self.resolution = np.array(self.capture_size)
+        self.results_path = results_path
+        self.flows = flows            # optional precomputed (N-1, H, W, 2) float32: the get_flow_uv seam
+        self.bgr = bgr
+        self._next = 0
+
+    def get_frame(self) -> np.ndarray:
+        f = self.seq.frames[min(self._next, self.N - 1)]
+        self._next += 1
+        return np.repeat(f[..., None], 3, axis=2) if self.bgr else f
+
+    def get_flow_uv(self, i: int) -> np.ndarray:
+        if self.flows is None:
+            raise ValueError('Could not load flow field.')
+        return self.flows[i]
+
+    def get_gt_of(self, i: int):
+        return None
+
+    def get_sky_segmentation(self, i: int) -> np.ndarray:
+        return self.seq.sky_mask
+
+    def get_segmentation(self, i: int) -> np.ndarray:
+        s = self.seq.segmentation[i]
+        return np.repeat(s[..., None], 3, axis=2)
+
+    def get_depth(self, i: int):
+        return None
+
+    def get_gt_foe(self, i: int):
+        return self.seq.foe
+
+    def get_time(self, i: int) -> float:
+        return i * self.seq.dt
+
+    def get_delta_time(self, i: int) -> float:
+        return self.seq.dt
+
+    def get_angular_difference(self, first: int, second: int) -> np.ndarray:
+        return self.seq.omega[second].copy()
+
+    def release(self) -> None:
+        pass

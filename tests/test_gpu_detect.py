@@ -160,3 +160,157 @@ def test_bgr2gray_matches_opencv_fixed_point():
     except ImportError:
         pass
     eng.close()
+
+
+def _adversarial_field(h, w, foe, rng, thresholds_only=True):
+    """Flow whose angle to the FoE ray sits within 1e-9 .. 1e-1 degrees of the fixed (15 deg) or the
+    dynamic (0.75 + 8/|f|) threshold, with magnitudes hugging the 0.5 / 1.0 gates on part of the image."""
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    theta = np.arctan2(ys - foe[1], xs - foe[0])
+    mag = rng.uniform(0.3, 12.0, (h, w))
+    gate = rng.random((h, w))
+    mag = np.where(gate < 0.1, 0.5 + rng.normal(0, 1e-6, (h, w)), mag)
+    mag = np.where((gate >= 0.1) & (gate < 0.2), 1.0 + rng.normal(0, 1e-6, (h, w)), mag)
+    which = rng.random((h, w)) < 0.5
+    thr = np.where(which, 15.0, 0.75 + 8.0 / mag)
+    eps = rng.choice([-1, 1], (h, w)) * 10.0 ** rng.uniform(-9, -1, (h, w))
+    sign = rng.choice([-1, 1], (h, w))
+    ang = theta + sign * np.deg2rad(thr + eps)
+    return np.stack([mag * np.cos(ang), mag * np.sin(ang)], -1)
+
+
+@pytest.mark.parametrize('rot', [False, True])
+def test_fast_residual_path_is_bit_exact_near_thresholds(rot):
+    """phi not requested -> float32 pre-decision with guard bands; must equal the float64 evaluation
+    (and the oracle) on a field built to sit on every threshold."""
+    import torch
+    from mav_detection_b200 import engine
+    from oracle import detect_np as dn
+    h, w = 360, 512
+    rng = np.random.default_rng(17)
+    foe = (201.3, 155.8)
+    ang = np.array([0.002, -0.001, 0.0005]) if rot else np.zeros(3)
+    dt = 1 / 30
+    want = _adversarial_field(h, w, foe, rng)
+    # the kernel derotates float32 flow in float64: pre-add the rotation so the derotated field hugs the thresholds
+    flow = (want + (dn.derotation_field(w, h, ang, dt) if rot else 0.0)).astype(np.float32)
+    flow[7, 9] = (np.nan, 1.0)
+    flow[8, 9] = (np.inf, 1.0)
+    flow[20:24, 30:40] = 0.0
+    sky = np.zeros((h, w), bool)
+    sky[:30, :100] = True
+    seg = np.zeros((h, w), np.uint8)
+    seg[100:140, 200:260] = 255
+    fd = dn.derotate(3, flow, ang, dt)
+    phi_ref = dn.get_phi(fd, foe)
+    total_ref, fixed_ref = dn.masks(fd, phi_ref, sky)
+    eng = _engine(w, h)
+    imu = engine.make_imu(1, ang[None], dt, derotate=True)
+    fl = torch.from_numpy(flow[None]).cuda()
+    foe_t = torch.tensor([foe], dtype=torch.float64, device='cuda')
+    args = dict(sky=torch.from_numpy(sky).cuda(), seg=torch.from_numpy(seg).cuda())
+    _, tot_f, fix_f, st_f = eng.residual_masks(fl, imu, foe_t, want_phi=False, **args)
+    eng.force_exact_residual(True)
+    _, tot_e, fix_e, st_e = eng.residual_masks(fl, imu, foe_t, want_phi=False, **args)
+    eng.force_exact_residual(False)
+    tot_f, fix_f = tot_f[0].cpu().numpy().astype(bool), fix_f[0].cpu().numpy().astype(bool)
+    assert np.array_equal(tot_f, tot_e[0].cpu().numpy().astype(bool))
+    assert np.array_equal(fix_f, fix_e[0].cpu().numpy().astype(bool))
+    assert np.array_equal(tot_f, total_ref), int((tot_f != total_ref).sum())
+    assert np.array_equal(fix_f, fixed_ref), int((fix_f != fixed_ref).sum())
+    assert 0.1 < total_ref.mean() < 0.9 and 0.1 < fixed_ref.mean() < 0.9   # both classes well represented
+    sf, se = eng.stats_to_numpy(st_f)[0], eng.stats_to_numpy(st_e)[0]
+    for k in ('n_total', 'n_fixed', 'positives', 'negatives', 'tp_total', 'fp_total', 'tp_fixed', 'fp_fixed'):
+        assert sf[k] == se[k], k
+    assert sf['n_total'] == total_ref.sum() and sf['n_fixed'] == fixed_ref.sum()
+    assert tuple(sf['seg_bbox']) == (200, 100, 259, 139)
+    assert sf['max_phi'] == -1.0 and se['max_phi'] > 0
+    assert np.allclose(sf['seg_flow_sum'], fd[seg > 127].sum(axis=0), rtol=1e-9)
+    eng.close()
+
+
+def test_fast_residual_ragged_width_and_batch():
+    """Width not divisible by 4 (one pixel per thread) and a mixed batch (frame 0 float32, others float64)."""
+    import torch
+    from mav_detection_b200 import engine
+    from oracle import detect_np as dn
+    h, w, n = 131, 203, 3
+    rng = np.random.default_rng(23)
+    foe = np.array([[80.2, 60.1], [100.0, 50.5], [0.0, 0.0]])
+    flows = np.stack([_adversarial_field(h, w, foe[i], rng) for i in range(n)]).astype(np.float32)
+    ys, xs = np.mgrid[0:h, 0:w]
+    # frame 0 runs in float32 end to end (one float32 ulp of phi is ~1e-6 deg): use a benign noisy radial field
+    flows[0] = (np.stack([(xs - 80.2) * 0.05, (ys - 60.1) * 0.05], -1) + rng.normal(0, 0.4, (h, w, 2))).astype(np.float32)
+    ang = np.array([[0, 0, 0], [0.001, 0.002, -0.001], [0.003, 0, 0.001]], np.float64)
+    dt = 0.04
+    eng = _engine(w, h, n)
+    imu = engine.make_imu(n, ang, dt, derotate=[False, True, True])
+    _, tot, fix, st = eng.residual_masks(torch.from_numpy(flows).cuda(), imu, torch.from_numpy(foe).cuda(), want_phi=False)
+    st = eng.stats_to_numpy(st)
+    sky = np.zeros((h, w), bool)
+    for i in range(n):
+        fd = dn.derotate(i, flows[i], ang[i], dt)
+        phi = dn.get_phi(fd, tuple(foe[i]))
+        tr, fr = dn.masks(fd, phi, sky)
+        t, f = tot[i].cpu().numpy().astype(bool), fix[i].cpu().numpy().astype(bool)
+        if i == 0:
+            # float32 frame: NumPy's float32 arccos vs ours may differ in the last ulp on a handful of pixels
+            assert (t != tr).sum() <= 4 and (f != fr).sum() <= 4
+            assert abs(st[i]['max_phi'] - phi.max()) < 1e-3
+        else:
+            assert np.array_equal(t, tr) and np.array_equal(f, fr)
+            assert st[i]['max_phi'] == -1.0
+    eng.close()
+
+
+@pytest.mark.parametrize('ci', [0, 1, 2, 3])
+def test_reference_literal_seams_on_golden(golden_dir, ci):
+    """get_FOE_dense / get_phi called on the (already derotated) flow array itself, either dtype."""
+    import torch
+    g = _load(golden_dir, ci)
+    fd = g['flow_derot']                     # float64 for frame_index >= 1, float32 for frame 0
+    h, w = fd.shape[:2]
+    eng = _engine(w, h)
+    fl = torch.from_numpy(fd[None].copy()).cuda()
+    samples = torch.from_numpy(np.concatenate([g['ry'], g['rx']])[None].astype(np.int32)).cuda()
+    foe, cnt = eng.foe_dense(fl, samples)
+    assert np.array_equal(foe.cpu().numpy()[0], g['foe'])
+    phi, mx = eng.get_phi(fl, foe)
+    p = phi[0].cpu().numpy()
+    assert p.dtype == g['phi'].dtype
+    tol = 1e-9 if fd.dtype == np.float64 else 1e-4
+    assert np.abs(p - g['phi']).max() < tol
+    assert abs(float(mx[0]) - float(g['phi'].max())) < tol
+    eng.close()
+
+
+def test_ransac_matches_oracle():
+    import torch
+    from oracle import detect_np as dn
+    rng = np.random.default_rng(5)
+    eng = _engine(64, 48)
+    for k in (0, 1, 2, 37, 1000, 2500):
+        E = rng.normal(0, 40, (k, 2))
+        if k >= 37:
+            E[k // 2:k // 2 + 10] = E[3] + rng.normal(0, 1, (10, 2))     # a tight cluster, ties included
+            E[5] = E[3]
+        got = eng.ransac(torch.from_numpy(E).cuda()).cpu().numpy()
+        assert tuple(got) == dn.ransac(E), k
+    eng.close()
+
+
+def test_ccl_without_label_image():
+    import torch
+    from oracle import ccl_np
+    rng = np.random.default_rng(12)
+    masks = (rng.random((2, 120, 160)) < 0.05).astype(np.uint8)
+    masks[0, 40:60, 50:90] = 1
+    eng = _engine(160, 120, 2)
+    labels, boxes, cnt = eng.ccl(torch.from_numpy(masks).cuda(), want_labels=False)
+    assert labels is None
+    for i in range(2):
+        ref, stats = ccl_np.label(masks[i])
+        assert int(cnt[i]) == ref.max()
+        k = min(32, stats.shape[0])
+        assert np.array_equal(boxes[i, :k].cpu().numpy(), stats[:k])
+    eng.close()
