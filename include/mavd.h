@@ -181,6 +181,24 @@ int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mav
                         void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
                         void* stream);
 
+/* ---- stand-alone im_helpers seams (no handle needed) ----
+ * im_helpers.get_magnitude (src/im_helpers.py:150-159): np.linalg.norm(flow, axis=-1) in the flow's dtype. */
+int mavd_magnitude(const void* d_flow, int32_t flow_is_f64, int64_t n_pixels, void* d_out, void* stream);
+/* im_helpers.get_simple_bounding_box (src/im_helpers.py:55-84) of a uint8 (H, W, C) image: d_out5 receives
+ * {start_x, start_y, end_x, end_y, max(img)}; all four coordinates are -1 when no element exceeds 0.1*max. */
+int mavd_simple_bbox(const uint8_t* d_img, int32_t width, int32_t height, int32_t channels, int32_t* d_out5,
+                     void* stream);
+/* im_helpers.calculate_tpr_fpr (src/im_helpers.py:244-252) integer part: d_counts4 = {positives, negatives,
+ * true_positives, false_positives} for a uint8 ground truth and an int64 image (255 * mask at processor.py:350). */
+int mavd_tpr_fpr_counts(const uint8_t* d_gt, const int64_t* d_img, int64_t n, int64_t* d_counts4, void* stream);
+
+/* ---- next-row f4: the visualisation Farneback.process() returns (src/farneback.py:83-99) ----
+ * cartToPolar -> hue / value bytes (value = 2 * min-max normalised magnitude, wrapping like the NumPy uint8
+ * store) -> pixels with value 0 become (127, 255, 255) -> HSV2BGR.  d_bgr: n_pixels x 3 uint8.
+ * d_scratch3: 3 uint32 of device scratch; on return [2] = number of pixels with a non-zero value byte
+ * (0 = the reference's `invalid_frame`). */
+int mavd_flow_vis(const float* d_flow, int64_t n_pixels, uint8_t* d_bgr, uint32_t* d_scratch3, void* stream);
+
 /* ---- stage 4 (not in the reference): 8-connected components of a mask ----
  * Labels are numbered 1..n by first appearance in a raster scan (0 = background).
  * d_boxes: n x max_boxes x 5 int32 [left, top, width, height, area]; d_n_labels: n int32 (true count).

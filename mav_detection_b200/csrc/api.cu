@@ -123,8 +123,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// TMA descriptor of one M buffer: rank-3 float tensor {pitch, h, planes}, box {80, 32+2m, 5}, zero fill.
-static bool make_m_tensor_map(CUtensorMap* map, float* base, int pitch, int h, int planes, size_t plane, int m) {
+// TMA descriptor of a planar buffer: rank-3 float tensor {pitch, h, planes}, box {80, box_h, box_planes}, zero fill.
+static bool make_plane_tensor_map(CUtensorMap* map, float* base, int pitch, int h, int planes, size_t plane, int box_h,
+                                  int box_planes) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* f = nullptr;
@@ -137,7 +138,7 @@ static bool make_m_tensor_map(CUtensorMap* map, float* base, int pitch, int h, i
     }
     cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)h, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)plane * sizeof(float)};
-    cuuint32_t box[3] = {80u, (cuuint32_t)(32 + 2 * m), 5u};
+    cuuint32_t box[3] = {80u, (cuuint32_t)box_h, (cuuint32_t)box_planes};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -290,7 +291,7 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
         if (li > 0) {
             // combined blur + bilinear-resize filter per output sample: c_j = (1-a) k_j + a k_{j-1}
             const std::vector<float> kk = gaussian_kernel(L.ksz, sigma);
-            const int taps = L.ksz + 1, r = L.ksz / 2;
+            const int taps = round_up(L.ksz + 1, 4), r = L.ksz / 2;   // zero padded to whole float4 groups
             for (int axis = 0; axis < 2; ++axis) {
                 const int src = axis == 0 ? W : Hh, dst = axis == 0 ? L.w : L.h;
                 std::vector<int> i0;
@@ -301,7 +302,7 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
                 for (int d = 0; d < dst; ++d) {
                     base[d] = i0[d] - r;
                     for (int j = 0; j < taps; ++j) {
-                        const float k0 = j < L.ksz ? kk[j] : 0.f, k1 = j >= 1 ? kk[j - 1] : 0.f;
+                        const float k0 = j < L.ksz ? kk[j] : 0.f, k1 = (j >= 1 && j <= L.ksz) ? kk[j - 1] : 0.f;
                         tab[(size_t)d * taps + j] = (1.f - a[d]) * k0 + a[d] * k1;
                     }
                 }
@@ -322,8 +323,9 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
         cudaMemset(L.M[1], 0, (size_t)B * 5 * L.plane * sizeof(float));
         const int m = fp.winsize / 2;
         if (m >= 5 && m <= 8)
-            L.has_tmap = make_m_tensor_map(&L.tmapM[0], L.M[0], L.pitch, L.h, B * 5, L.plane, m) &&
-                         make_m_tensor_map(&L.tmapM[1], L.M[1], L.pitch, L.h, B * 5, L.plane, m);
+            L.has_tmap = make_plane_tensor_map(&L.tmapM[0], L.M[0], L.pitch, L.h, B * 5, L.plane, 32 + 2 * m, 5) &&
+                         make_plane_tensor_map(&L.tmapM[1], L.M[1], L.pitch, L.h, B * 5, L.plane, 32 + 2 * m, 5) &&
+                         make_plane_tensor_map(&L.tmapR, L.R, L.pitch, L.h, F * 5, L.plane, 48, 10);
     }
     for (int li = 0; li + 1 < H->n_levels; ++li) {
         Level& L = H->lv[li];
@@ -589,6 +591,29 @@ int mavd_ccl(mavd_handle h, const uint8_t* d_mask, int32_t n, int32_t* d_labels,
     MAVD_REQUIRE(max_boxes >= 0, MAVD_ERR_INVALID, "ccl: max_boxes < 0");
     return ccl_run(h, d_mask, n, d_labels, max_boxes > 0 ? d_boxes : nullptr, (size_t)max_boxes * 5, max_boxes,
                    d_n_labels, sizeof(int32_t), (cudaStream_t)stream);
+}
+
+int mavd_magnitude(const void* d_flow, int32_t flow_is_f64, int64_t n_pixels, void* d_out, void* stream) {
+    MAVD_REQUIRE(n_pixels >= 0 && (n_pixels == 0 || (d_flow && d_out)), MAVD_ERR_INVALID, "magnitude: bad arguments");
+    if (n_pixels == 0) return MAVD_OK;
+    return magnitude_run(d_flow, flow_is_f64 ? 1 : 0, n_pixels, d_out, (cudaStream_t)stream);
+}
+
+int mavd_simple_bbox(const uint8_t* d_img, int32_t width, int32_t height, int32_t channels, int32_t* d_out5,
+                     void* stream) {
+    MAVD_REQUIRE(d_img && d_out5 && width >= 1 && height >= 1 && channels >= 1, MAVD_ERR_INVALID,
+                 "simple_bbox: bad arguments");
+    return simple_bbox_run(d_img, width, height, channels, d_out5, (cudaStream_t)stream);
+}
+
+int mavd_tpr_fpr_counts(const uint8_t* d_gt, const int64_t* d_img, int64_t n, int64_t* d_counts4, void* stream) {
+    MAVD_REQUIRE(n >= 0 && d_counts4 && (n == 0 || (d_gt && d_img)), MAVD_ERR_INVALID, "tpr_fpr_counts: bad arguments");
+    return tpr_fpr_run(d_gt, d_img, n, d_counts4, (cudaStream_t)stream);
+}
+
+int mavd_flow_vis(const float* d_flow, int64_t n_pixels, uint8_t* d_bgr, uint32_t* d_scratch3, void* stream) {
+    MAVD_REQUIRE(n_pixels >= 1 && d_flow && d_bgr && d_scratch3, MAVD_ERR_INVALID, "flow_vis: bad arguments");
+    return flow_vis_run(d_flow, n_pixels, d_bgr, d_scratch3, (cudaStream_t)stream);
 }
 
 __global__ void records_fill_kernel(mavd_frame_record* rec, const double* foe, const int32_t* ninter, int n) {

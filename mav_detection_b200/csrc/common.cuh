@@ -74,6 +74,7 @@ struct Level {
     float* flow = nullptr;  // [pairs][h][pitch] float2 (unused for level 0: written to the caller's buffer)
     int last_m = 0;         // which M buffer holds the last update (for taps)
     CUtensorMap tmapM[2];   // TMA descriptors of M[0] / M[1]: dims {pitch, h, pairs*5}, box {80, 32+2m, 5}
+    CUtensorMap tmapR;      // TMA descriptor of R: dims {pitch, h, frames*5}, box {80, 48, 10} (L2 prefetch only)
     bool has_tmap = false;
 };
 
@@ -176,6 +177,10 @@ int residual_run(mavd_handle h, const void* d_flow, int flow_kind, int n, const 
                  const double* d_foe, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
                  int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
                  size_t stats_stride_bytes, int run_f64, int run_f32, cudaStream_t s);
+int magnitude_run(const void* d_flow, int is_f64, int64_t n, void* d_out, cudaStream_t s);
+int simple_bbox_run(const uint8_t* d_img, int w, int h, int c, int32_t* d_out5, cudaStream_t s);
+int tpr_fpr_run(const uint8_t* d_gt, const int64_t* d_img, int64_t n, int64_t* d_counts4, cudaStream_t s);
+int flow_vis_run(const float* d_flow, int64_t n, uint8_t* d_bgr, uint32_t* d_scratch3, cudaStream_t s);
 int ccl_run(mavd_handle h, const uint8_t* d_mask, int n, int32_t* d_labels, int32_t* d_boxes, size_t boxes_stride,
             int max_boxes, int32_t* d_n_labels, size_t nlabels_stride_bytes, cudaStream_t s);
 }  // namespace mavd

@@ -779,6 +779,193 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stand-alone im_helpers seams (im_helpers.py:150-159, 55-84, 244-252) for callers that use them outside
+// the fused residual kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) magnitude_kernel(const void* __restrict__ flow, int is_f64, int64_t n,
+                                                       void* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (is_f64) {
+        const double2 v = reinterpret_cast<const double2*>(flow)[i];
+        reinterpret_cast<double*>(out)[i] = __dsqrt_rn(__dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y)));
+    } else {
+        const float2 v = reinterpret_cast<const float2*>(flow)[i];
+        reinterpret_cast<float*>(out)[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+    }
+}
+
+int magnitude_run(const void* d_flow, int is_f64, int64_t n, void* d_out, cudaStream_t s) {
+    magnitude_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_flow, is_f64, n, d_out);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+__global__ void bbox_init_kernel(int32_t* out5) {
+    out5[0] = out5[1] = 0x7fffffff;
+    out5[2] = out5[3] = -1;
+    out5[4] = 0;
+}
+
+// out5 = {x0, y0, x1, y1, max}; element e of the (H, W, C) image belongs to column (e % (W*C)) / C
+__global__ void __launch_bounds__(256) bbox_kernel(const uint8_t* __restrict__ img, int w, int h, int c,
+                                                  int32_t* __restrict__ out5) {
+    const double thr = 0.1 * (double)out5[4];
+    const int64_t n = (int64_t)w * h * c, rowlen = (int64_t)w * c;
+    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        if ((double)img[e] > thr) {
+            const int y = (int)(e / rowlen), x = (int)((e - (int64_t)y * rowlen) / c);
+            x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y);
+        }
+    }
+    x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
+    x1 = __reduce_max_sync(0xffffffffu, x1); y1 = __reduce_max_sync(0xffffffffu, y1);
+    if ((threadIdx.x & 31) == 0 && x1 >= 0) {
+        atomicMin(out5 + 0, x0); atomicMin(out5 + 1, y0); atomicMax(out5 + 2, x1); atomicMax(out5 + 3, y1);
+    }
+}
+
+__global__ void bbox_final_kernel(int32_t* out5) {
+    if (out5[2] < 0) out5[0] = out5[1] = out5[2] = out5[3] = -1;
+}
+
+int simple_bbox_run(const uint8_t* d_img, int w, int h, int c, int32_t* d_out5, cudaStream_t s) {
+    const int64_t n = (int64_t)w * h * c;
+    bbox_init_kernel<<<1, 1, 0, s>>>(d_out5);
+    MAVD_LAUNCHED();
+    seg_max_kernel<<<dim3(148, 1), 256, 0, s>>>(d_img, 0, n, d_out5 + 4);
+    MAVD_LAUNCHED();
+    bbox_kernel<<<148 * 4, 256, 0, s>>>(d_img, w, h, c, d_out5);
+    MAVD_LAUNCHED();
+    bbox_final_kernel<<<1, 1, 0, s>>>(d_out5);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+// counts4 = {sum(gt > 127), sum(255 - gt > 127), sum(gt * img > 127), sum((255 - gt) * img > 127)}, int64 products
+__global__ void __launch_bounds__(256) tpr_fpr_kernel(const uint8_t* __restrict__ gt, const int64_t* __restrict__ img,
+                                                     int64_t n, unsigned long long* __restrict__ counts4) {
+    int pos = 0, neg = 0, tp = 0, fp = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = gt[e], v = img[e];
+        pos += g > 127;
+        neg += (255 - g) > 127;
+        tp += (g * v) > 127;
+        fp += ((255 - g) * v) > 127;
+    }
+    pos = __reduce_add_sync(0xffffffffu, pos); neg = __reduce_add_sync(0xffffffffu, neg);
+    tp = __reduce_add_sync(0xffffffffu, tp); fp = __reduce_add_sync(0xffffffffu, fp);
+    if ((threadIdx.x & 31) == 0) {
+        if (pos) atomicAdd(counts4 + 0, (unsigned long long)pos);
+        if (neg) atomicAdd(counts4 + 1, (unsigned long long)neg);
+        if (tp) atomicAdd(counts4 + 2, (unsigned long long)tp);
+        if (fp) atomicAdd(counts4 + 3, (unsigned long long)fp);
+    }
+}
+
+int tpr_fpr_run(const uint8_t* d_gt, const int64_t* d_img, int64_t n, int64_t* d_counts4, cudaStream_t s) {
+    MAVD_CUDA(cudaMemsetAsync(d_counts4, 0, 4 * sizeof(int64_t), s));
+    tpr_fpr_kernel<<<148 * 4, 256, 0, s>>>(d_gt, d_img, n, reinterpret_cast<unsigned long long*>(d_counts4));
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flow visualisation returned by Farneback.process() (farneback.py:83-99): cv2.cartToPolar -> hue/value bytes ->
+// cv2.normalize(NORM_MINMAX) * 2 -> HSV2BGR.  The arithmetic restates what cv2 4.13 computes (verified
+// bit-exact against cv2 on the CPU, see oracle/vis_np.py): magnitude sqrt(fma(x,x,y*y)); fastAtan2's degree-7
+// polynomial evaluated with FMAs; float32 min-max normalisation; float->uint8 casts that truncate and wrap
+// modulo 256 (NumPy's cast of the doubled value); 8-bit HSV2BGR with S = 255 through the float sector formula and
+// a truncating store.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cv_magnitude(float x, float y) { return __fsqrt_rn(__fmaf_rn(x, x, __fmul_rn(y, y))); }
+
+__device__ __forceinline__ float cv_fast_atan2_rad(float y, float x) {
+    const float p1 = 57.283627f, p3 = -18.667446f, p5 = 8.9140005f, p7 = -2.5397246f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+    const float c = __fdiv_rn(mn, __fadd_rn(mx, 2.220446049250313e-16f));
+    const float c2 = __fmul_rn(c, c);
+    float a = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmaf_rn(p7, c2, p5), c2, p3), c2, p1), c);
+    if (ax < ay) a = __fsub_rn(90.f, a);
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    return __fmul_rn(a, 0.017453292519943295f);
+}
+
+// scratch: [0] min(mag) bits, [1] max(mag) bits, [2] number of pixels whose value byte is non-zero
+__global__ void vis_init_kernel(unsigned* scratch) {
+    scratch[0] = 0x7f800000u;
+    scratch[1] = 0u;
+    scratch[2] = 0u;
+}
+
+__global__ void __launch_bounds__(256) vis_minmax_kernel(const float2* __restrict__ flow, int64_t n,
+                                                        unsigned* __restrict__ scratch) {
+    unsigned mn = 0x7f800000u, mx = 0u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 v = flow[i];
+        const unsigned b = __float_as_uint(cv_magnitude(v.x, v.y));   // magnitudes are >= 0: bit order == value order
+        if (b <= 0x7f800000u) { mn = min(mn, b); mx = max(mx, b); }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(scratch, mn); atomicMax(scratch + 1, mx); }
+}
+
+__device__ __forceinline__ unsigned f2u8_wrap(float v) {   // NumPy float32 -> uint8 assignment: truncate, wrap mod 256
+    return (unsigned)((int)v) & 255u;
+}
+
+__global__ void __launch_bounds__(256) vis_kernel(const float2* __restrict__ flow, int64_t n, unsigned* __restrict__ scratch,
+                                                 uint8_t* __restrict__ bgr) {
+    const float mn = __uint_as_float(scratch[0]), mx = __uint_as_float(scratch[1]);
+    // cv::normalize(NORM_MINMAX, 0..255): scale and shift in double, applied in float32
+    const double span = (double)mx - (double)mn;
+    const double dscale = 255.0 * (span > 2.220446049250313e-16 ? 1.0 / span : 0.0);
+    const float scale = (float)dscale, shift = (float)(0.0 - (double)mn * dscale);
+    int nz = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 f = flow[i];
+        const float mag = cv_magnitude(f.x, f.y), ang = cv_fast_atan2_rad(f.y, f.x);
+        unsigned h8 = f2u8_wrap(__fdiv_rn(__fdiv_rn(__fmul_rn(ang, 180.f), 3.14159274101257324f), 2.f));
+        unsigned v8 = f2u8_wrap(__fmul_rn(__fadd_rn(__fmul_rn(mag, scale), shift), 2.f));
+        nz += v8 != 0;
+        if (v8 == 0) { h8 = 127; v8 = 255; }
+        // HSV2BGR, S = 255
+        const float v = __fmul_rn((float)v8, 1.f / 255.f);
+        float h = __fmul_rn((float)h8, 6.f / 180.f);
+        while (h >= 6.f) h = __fsub_rn(h, 6.f);
+        int sec = (int)floorf(h);
+        h = __fsub_rn(h, (float)sec);
+        if ((unsigned)sec >= 6u) { sec = 0; h = 0.f; }
+        float tab[4];
+        tab[0] = v;
+        tab[1] = __fmul_rn(v, 0.f);
+        tab[2] = __fmul_rn(v, __fsub_rn(1.f, h));
+        tab[3] = __fmul_rn(v, __fsub_rn(1.f, __fsub_rn(1.f, h)));
+        const int sel = sec == 0 ? 0x130 : sec == 1 ? 0x102 : sec == 2 ? 0x301 : sec == 3 ? 0x021 : sec == 4 ? 0x013 : 0x210;
+        const float b = tab[(sel >> 8) & 3], g = tab[(sel >> 4) & 3], r = tab[sel & 3];
+        bgr[3 * i] = (uint8_t)min(255, max(0, (int)__fmul_rn(b, 255.f)));
+        bgr[3 * i + 1] = (uint8_t)min(255, max(0, (int)__fmul_rn(g, 255.f)));
+        bgr[3 * i + 2] = (uint8_t)min(255, max(0, (int)__fmul_rn(r, 255.f)));
+    }
+    nz = __reduce_add_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0 && nz) atomicAdd(scratch + 2, (unsigned)nz);
+}
+
+int flow_vis_run(const float* d_flow, int64_t n, uint8_t* d_bgr, uint32_t* d_scratch3, cudaStream_t s) {
+    vis_init_kernel<<<1, 1, 0, s>>>(d_scratch3);
+    MAVD_LAUNCHED();
+    vis_minmax_kernel<<<148 * 4, 256, 0, s>>>((const float2*)d_flow, n, d_scratch3);
+    MAVD_LAUNCHED();
+    vis_kernel<<<148 * 8, 256, 0, s>>>((const float2*)d_flow, n, d_scratch3, d_bgr);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Connected components (8-connectivity), union-find with the smaller raster index as the root, so a
 // component's root is its first pixel in raster order and ranking the roots gives canonical labels.
 //

@@ -54,10 +54,18 @@ struct PyrDesc {
     PyrLevel lv[kMaxLevels];
 };
 
+constexpr int PYR_SPLITS = 4;   // CTAs that share one 32-row block (each stages the rows, computes 1/4 of the columns)
+
+// u8 -> float without a conversion instruction: byte k of v placed in the mantissa of 2^23, then - 2^23 (exact)
+__device__ __forceinline__ float byte_to_float(uint32_t v, uint32_t selector) {
+    return __uint_as_float(__byte_perm(v, 0x4B000000u, selector)) - 8388608.f;
+}
+
 __global__ void __launch_bounds__(256) pyr_hpass_all_kernel(const uint8_t* __restrict__ frames, size_t frame_stride,
                                                            int W, int H, int rp, const __grid_constant__ PyrDesc d) {
     extern __shared__ __align__(16) uint8_t srow[];   // [32][rp]
-    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int worker = blockIdx.z * 8 + (tid >> 5);   // 8 * PYR_SPLITS warps share the output columns
     const int y0 = blockIdx.x * 32;
     const uint8_t* src = frames + (size_t)blockIdx.y * frame_stride;
     const int nrows = min(32, H - y0);
@@ -77,18 +85,31 @@ __global__ void __launch_bounds__(256) pyr_hpass_all_kernel(const uint8_t* __res
     __syncthreads();
     if (lane >= nrows) return;
     const uint8_t* row = srow + lane * rp;
+    const uint32_t* roww = reinterpret_cast<const uint32_t*>(row);
     const int y = y0 + lane;
     for (int l = 0; l < d.n; ++l) {
         const PyrLevel& L = d.lv[l];
         float* out = L.tmp + (size_t)blockIdx.y * L.tmp_stride + (size_t)y * L.pitch;
-        const int taps = L.taps;
-        for (int dx = g; dx < L.w; dx += 8) {
+        const int taps = L.taps;               // multiple of 4 (zero padded)
+        for (int dx = worker; dx < L.w; dx += 8 * PYR_SPLITS) {
             const int base = __ldg(L.xbase + dx);
             const float* tab = L.xtab + dx * taps;
             float acc = 0.f;
-            if (base >= 0 && base + taps <= W) {
-#pragma unroll 4
-                for (int j = 0; j < taps; ++j) acc += __ldg(tab + j) * (float)row[base + j];
+            if (base >= 0 && base + taps + 4 <= W) {
+                // four taps per step: one aligned word of the row per step, realigned with a funnel shift
+                const int wi = base >> 2;
+                const uint32_t sh = (uint32_t)(base & 3) * 8u;
+                uint32_t lo = roww[wi];
+                for (int k = 0; k < taps; k += 4) {
+                    const uint32_t hi = roww[wi + (k >> 2) + 1];
+                    const uint32_t v = __funnelshift_r(lo, hi, sh);
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(tab + k));
+                    acc += t.x * byte_to_float(v, 0x7540u);
+                    acc += t.y * byte_to_float(v, 0x7541u);
+                    acc += t.z * byte_to_float(v, 0x7542u);
+                    acc += t.w * byte_to_float(v, 0x7543u);
+                    lo = hi;
+                }
             } else {
                 for (int j = 0; j < taps; ++j) acc += __ldg(tab + j) * (float)row[reflect101(base + j, W)];
             }
@@ -348,9 +369,13 @@ __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, i
     Mout[4 * plane + o] = r6 * r2 + r5 * r3;
 }
 
+__device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h, int pitch, int plane, bool edge,
+                                                     float dx, float dy, const float* __restrict__ R0,
+                                                     const float* __restrict__ R1, float* __restrict__ Mout);
+
 // Level entry: flow_l = resize(flow_{l+1}) * (1/pyr_scale) (zeros on the coarsest level), then
 // UpdateMatrices.  The upsampled flow itself is never stored: BlurBox rebuilds the flow from M alone.
-__global__ void __launch_bounds__(256) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
+__global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
                                                            int pitch, int pair_stride,
                                                            const float2* __restrict__ cflow, int cw, int ch,
                                                            int cpitch, size_t cflow_stride,
@@ -379,7 +404,7 @@ __global__ void __launch_bounds__(256) matrices_init_kernel(const float* __restr
     }
     if (flow_dbg) flow_dbg[(size_t)p * flow_dbg_stride + (size_t)y * flow_dbg_pitch + x] = make_float2(dx, dy);
     const float* R0 = R + (size_t)(p * pair_stride) * 5 * plane;
-    update_matrices_px(x, y, w, h, pitch, plane, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
+    update_matrices_fast(x, y, w, h, pitch, (int)plane, true, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -610,13 +635,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
+// L2 prefetch of a tensor box (no shared memory, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // UpdateMatrices with 32-bit index arithmetic; `edge` is tile-uniform (tile within 5 px of a border).
 __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h, int pitch, int plane, bool edge,
                                                      float dx, float dy, const float* __restrict__ R0,
                                                      const float* __restrict__ R1, float* __restrict__ Mout) {
+    // every address is base + one 32-bit element index: one IMAD.WIDE per address instead of 64-bit add chains
     const int o = y * pitch + x;
-    const float r0y = __ldg(R0 + o), r0x = __ldg(R0 + plane + o), r0yy = __ldg(R0 + 2 * plane + o),
-                r0xx = __ldg(R0 + 3 * plane + o), r0xy = __ldg(R0 + 4 * plane + o);
+    const float r0y = __ldg(R0 + o), r0x = __ldg(R0 + (o + plane)), r0yy = __ldg(R0 + (o + 2 * plane)),
+                r0xx = __ldg(R0 + (o + 3 * plane)), r0xy = __ldg(R0 + (o + 4 * plane));
     float fx = (float)x + dx, fy = (float)y + dy;
     const float flx = floorf(fx), fly = floorf(fy);
     const int x1 = (int)fminf(fmaxf(flx, -2.f), 1.0e6f), y1 = (int)fminf(fmaxf(fly, -2.f), 1.0e6f);
@@ -626,17 +658,16 @@ __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h,
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
         const float gx = 1.f - fx, gy = 1.f - fy;
         const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
-        const float* p0 = R1 + (y1 * pitch + x1);
-        const float* p1 = p0 + pitch;
-        r2 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
-        p0 += plane; p1 += plane;
-        r3 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
-        p0 += plane; p1 += plane;
-        r4 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
-        p0 += plane; p1 += plane;
-        r5 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
-        p0 += plane; p1 += plane;
-        r6 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        const int q0 = y1 * pitch + x1, q1 = q0 + pitch;
+        r2 = a00 * __ldg(R1 + q0) + a01 * __ldg(R1 + q0 + 1) + a10 * __ldg(R1 + q1) + a11 * __ldg(R1 + q1 + 1);
+        r3 = a00 * __ldg(R1 + (q0 + plane)) + a01 * __ldg(R1 + (q0 + plane) + 1) + a10 * __ldg(R1 + (q1 + plane)) +
+             a11 * __ldg(R1 + (q1 + plane) + 1);
+        r4 = a00 * __ldg(R1 + (q0 + 2 * plane)) + a01 * __ldg(R1 + (q0 + 2 * plane) + 1) +
+             a10 * __ldg(R1 + (q1 + 2 * plane)) + a11 * __ldg(R1 + (q1 + 2 * plane) + 1);
+        r5 = a00 * __ldg(R1 + (q0 + 3 * plane)) + a01 * __ldg(R1 + (q0 + 3 * plane) + 1) +
+             a10 * __ldg(R1 + (q1 + 3 * plane)) + a11 * __ldg(R1 + (q1 + 3 * plane) + 1);
+        r6 = a00 * __ldg(R1 + (q0 + 4 * plane)) + a01 * __ldg(R1 + (q0 + 4 * plane) + 1) +
+             a10 * __ldg(R1 + (q1 + 4 * plane)) + a11 * __ldg(R1 + (q1 + 4 * plane) + 1);
         r4 = (r0yy + r4) * 0.5f;
         r5 = (r0xx + r5) * 0.5f;
         r6 = (r0xy + r6) * 0.25f;
@@ -656,14 +687,15 @@ __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h,
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
     Mout[o] = r4 * r4 + r6 * r6;
-    Mout[plane + o] = (r4 + r5) * r6;
-    Mout[2 * plane + o] = r5 * r5 + r6 * r6;
-    Mout[3 * plane + o] = r4 * r2 + r6 * r3;
-    Mout[4 * plane + o] = r6 * r2 + r5 * r3;
+    Mout[o + plane] = (r4 + r5) * r6;
+    Mout[o + 2 * plane] = r5 * r5 + r6 * r6;
+    Mout[o + 3 * plane] = r4 * r2 + r6 * r3;
+    Mout[o + 4 * plane] = r6 * r2 + r5 * r3;
 }
 
 template <int M_, bool LAST>
-__global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap, IterArgs a) {
+__global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                              const __grid_constant__ CUtensorMap tmapR, IterArgs a) {
     constexpr int RW = IT_TX + 16;          // 80 staged columns (halo 8 each side, 16-byte aligned)
     constexpr int RH = IT_TY + 2 * M_;      // staged rows
     constexpr int CH = RH * RW;             // floats per plane box
@@ -681,6 +713,9 @@ __global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_const
     if (tid == 0) {
         mbar_expect_tx(&bar, 5 * CH * (uint32_t)sizeof(float));
         tma_load_3d(box, &tmap, x0 - 8, y0 - M_, p * 5, &bar);
+        // R0 (this tile) and R1 (this tile displaced by the flow) are read ~10 us from now by the per-pixel
+        // phase: start their HBM -> L2 transfer now (10 consecutive planes = both frames' expansions)
+        if (!LAST) tma_prefetch_3d(&tmapR, x0 - 8, y0 - 8, p * a.pair_stride * 5);
     }
     const bool interior = (x0 - 8 >= 0) && (x0 + IT_TX + 8 <= w) && (y0 - M_ >= 0) && (y0 + IT_TY + M_ <= h);
     mbar_wait(&bar, 0);
@@ -758,7 +793,7 @@ __global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_const
         const float* sp = box + r * RW + 8 + cx;
         const float g11 = sp[0] * scale, g12 = sp[CH] * scale, g22 = sp[2 * CH] * scale, h1 = sp[3 * CH] * scale,
                     h2 = sp[4 * CH] * scale;
-        const float idet = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
+        const float idet = __frcp_rn(g11 * g22 - g12 * g12 + 1e-3f);   // MUFU.RCP + one Newton step, no slow-path call
         const float fx = (g11 * h2 - g12 * h1) * idet;
         const float fy = (g22 * h1 - g12 * h2) * idet;
         if (fl) fl[y * a.flow_pitch + x] = make_float2(fx, fy);
@@ -798,7 +833,7 @@ static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s
 }
 
 template <int M_, bool LAST>
-static int launch_iter_tma(const CUtensorMap& map, const IterArgs& a, dim3 grid, cudaStream_t s) {
+static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const IterArgs& a, dim3 grid, cudaStream_t s) {
     constexpr size_t smem = sizeof(float) * 5 * (IT_TY + 2 * M_) * (IT_TX + 16);
     static bool configured = false;
     if (!configured) {
@@ -806,18 +841,19 @@ static int launch_iter_tma(const CUtensorMap& map, const IterArgs& a, dim3 grid,
                                        (int)smem));
         configured = true;
     }
-    iter_box_tma_kernel<M_, LAST><<<grid, 256, smem, s>>>(map, a);
+    iter_box_tma_kernel<M_, LAST><<<grid, 256, smem, s>>>(map, mapR, a);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
 
 template <bool LAST>
-static int launch_iter_tma_m(int m, const CUtensorMap& map, const IterArgs& a, dim3 grid, cudaStream_t s) {
+static int launch_iter_tma_m(int m, const CUtensorMap& map, const CUtensorMap& mapR, const IterArgs& a, dim3 grid,
+                             cudaStream_t s) {
     switch (m) {
-        case 5: return launch_iter_tma<5, LAST>(map, a, grid, s);
-        case 6: return launch_iter_tma<6, LAST>(map, a, grid, s);
-        case 7: return launch_iter_tma<7, LAST>(map, a, grid, s);
-        default: return launch_iter_tma<8, LAST>(map, a, grid, s);
+        case 5: return launch_iter_tma<5, LAST>(map, mapR, a, grid, s);
+        case 6: return launch_iter_tma<6, LAST>(map, mapR, a, grid, s);
+        case 7: return launch_iter_tma<7, LAST>(map, mapR, a, grid, s);
+        default: return launch_iter_tma<8, LAST>(map, mapR, a, grid, s);
     }
 }
 
@@ -845,13 +881,13 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         for (int li = 1; li < H->n_levels; ++li) {
             const Level& L = H->lv[li];
             PyrLevel& P = d.lv[li - 1];
-            P.w = L.w; P.h = L.h; P.pitch = L.pitch; P.taps = L.ksz + 1;
+            P.w = L.w; P.h = L.h; P.pitch = L.pitch; P.taps = round_up(L.ksz + 1, 4);
             P.xbase = L.xbase; P.xtab = L.xtab; P.ybase = L.ybase; P.ytab = L.ytab;
             P.tmp = L.tmp; P.img = L.img; P.tmp_stride = (size_t)Hh * L.pitch; P.img_stride = L.plane;
             P.vblk0 = vb; P.vtiles_x = ceil_div(L.w, 64);
             vb += P.vtiles_x * ceil_div(L.h, 4);
         }
-        pyr_hpass_all_kernel<<<dim3(ceil_div(Hh, 32), n_frames), 256, 32 * H->pyr_row_pitch, s>>>(
+        pyr_hpass_all_kernel<<<dim3(ceil_div(Hh, 32), n_frames, PYR_SPLITS), 256, 32 * H->pyr_row_pitch, s>>>(
             d_frames, frame_bytes, W, Hh, H->pyr_row_pitch, d);
         MAVD_LAUNCHED();
         pyr_vpass_all_kernel<<<dim3(vb, n_frames), 256, 0, s>>>(Hh, d);
@@ -912,7 +948,8 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), s);
             int rc;
             if (!gauss && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter)
-                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], a, g, s) : launch_iter_tma_m<false>(m, L.tmapM[cur], a, g, s);
+                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], L.tmapR, a, g, s)
+                          : launch_iter_tma_m<false>(m, L.tmapM[cur], L.tmapR, a, g, s);
             else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, s) : launch_iter<true, false>(a, g, smem, s);
             else       rc = last ? launch_iter<false, true>(a, g, smem, s) : launch_iter<false, false>(a, g, smem, s);
             if (rc != MAVD_OK) return rc;
