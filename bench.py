@@ -375,6 +375,7 @@ def run_b200(args):
             'gpu_launches': int(launches),
             'roofline': roof,
             'kernel_time_shares': shares,
+            'kernel_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1] > 0},
             'cpu_baseline': cpu,
         }
         print(json.dumps(line))

@@ -12,6 +12,7 @@
 //   matrices_init_kernel   flow upsample (x 1/pyr_scale) fused with UpdateMatrices   (8P' +) 40P -> 20P
 //   iter_kernel            box/Gaussian blur of M + 2x2 solve + UpdateMatrices   88P (28P for the last)
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -54,30 +55,46 @@ struct PyrDesc {
     PyrLevel lv[kMaxLevels];
 };
 
-constexpr int PYR_SPLITS = 4;   // CTAs that share one 32-row block (each stages the rows, computes 1/4 of the columns)
+constexpr int PYR_SPLITS = 2;   // CTAs that share one 32-row block (each stages the rows, computes half of the columns)
+constexpr int PYR_NT = 512;     // 16 warps: 3 CTAs of 61 KB smem per SM -> 48 resident warps
 
 // u8 -> float without a conversion instruction: byte k of v placed in the mantissa of 2^23, then - 2^23 (exact)
 __device__ __forceinline__ float byte_to_float(uint32_t v, uint32_t selector) {
     return __uint_as_float(__byte_perm(v, 0x4B000000u, selector)) - 8388608.f;
 }
 
-__global__ void __launch_bounds__(256) pyr_hpass_all_kernel(const uint8_t* __restrict__ frames, size_t frame_stride,
-                                                           int W, int H, int rp, const __grid_constant__ PyrDesc d) {
+__device__ __forceinline__ float dot4_bytes(float acc, const float4 t, uint32_t v) {
+    acc += t.x * byte_to_float(v, 0x7540u);
+    acc += t.y * byte_to_float(v, 0x7541u);
+    acc += t.z * byte_to_float(v, 0x7542u);
+    acc += t.w * byte_to_float(v, 0x7543u);
+    return acc;
+}
+
+__device__ __forceinline__ float hpass_slow(const uint8_t* row, const float* __restrict__ tab, int base, int taps, int W) {
+    float acc = 0.f;
+    for (int j = 0; j < taps; ++j) acc += __ldg(tab + j) * (float)row[reflect101(base + j, W)];
+    return acc;
+}
+
+__global__ void __launch_bounds__(PYR_NT, 3) pyr_hpass_all_kernel(const uint8_t* __restrict__ frames, size_t frame_stride,
+                                                                  int W, int H, int rp, const __grid_constant__ PyrDesc d) {
     extern __shared__ __align__(16) uint8_t srow[];   // [32][rp]
     const int tid = threadIdx.x, lane = tid & 31;
-    const int worker = blockIdx.z * 8 + (tid >> 5);   // 8 * PYR_SPLITS warps share the output columns
+    constexpr int NWORK = (PYR_NT / 32) * PYR_SPLITS;             // warps that share the output columns
+    const int worker = blockIdx.z * (PYR_NT / 32) + (tid >> 5);
     const int y0 = blockIdx.x * 32;
     const uint8_t* src = frames + (size_t)blockIdx.y * frame_stride;
     const int nrows = min(32, H - y0);
     if (((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
         const int w4 = W >> 2;
-        for (int idx = tid; idx < nrows * w4; idx += 256) {
+        for (int idx = tid; idx < nrows * w4; idx += PYR_NT) {
             const int rr = idx / w4, q = idx - rr * w4;
             reinterpret_cast<uint32_t*>(srow + rr * rp)[q] =
                 __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(y0 + rr) * W) + q);
         }
     } else {
-        for (int idx = tid; idx < nrows * W; idx += 256) {
+        for (int idx = tid; idx < nrows * W; idx += PYR_NT) {
             const int rr = idx / W, q = idx - rr * W;
             srow[rr * rp + q] = src[(size_t)(y0 + rr) * W + q];
         }
@@ -91,29 +108,36 @@ __global__ void __launch_bounds__(256) pyr_hpass_all_kernel(const uint8_t* __res
         const PyrLevel& L = d.lv[l];
         float* out = L.tmp + (size_t)blockIdx.y * L.tmp_stride + (size_t)y * L.pitch;
         const int taps = L.taps;               // multiple of 4 (zero padded)
-        for (int dx = worker; dx < L.w; dx += 8 * PYR_SPLITS) {
-            const int base = __ldg(L.xbase + dx);
-            const float* tab = L.xtab + dx * taps;
-            float acc = 0.f;
-            if (base >= 0 && base + taps + 4 <= W) {
+        // two output columns per step (independent accumulation chains)
+        for (int dx = worker; dx < L.w; dx += 2 * NWORK) {
+            const int dx2 = dx + NWORK;
+            const bool have2 = dx2 < L.w;
+            const int base0 = __ldg(L.xbase + dx), base1 = have2 ? __ldg(L.xbase + dx2) : base0;
+            const float* tab0 = L.xtab + dx * taps;
+            const float* tab1 = L.xtab + (have2 ? dx2 : dx) * taps;
+            const bool fast0 = base0 >= 0 && base0 + taps + 4 <= W, fast1 = base1 >= 0 && base1 + taps + 4 <= W;
+            float acc0 = 0.f, acc1 = 0.f;
+            if (fast0 && fast1) {
                 // four taps per step: one aligned word of the row per step, realigned with a funnel shift
-                const int wi = base >> 2;
-                const uint32_t sh = (uint32_t)(base & 3) * 8u;
-                uint32_t lo = roww[wi];
+                const int wi0 = base0 >> 2, wi1 = base1 >> 2;
+                const uint32_t sh0 = (uint32_t)(base0 & 3) * 8u, sh1 = (uint32_t)(base1 & 3) * 8u;
+                uint32_t lo0 = roww[wi0], lo1 = roww[wi1];
+#pragma unroll 2
                 for (int k = 0; k < taps; k += 4) {
-                    const uint32_t hi = roww[wi + (k >> 2) + 1];
-                    const uint32_t v = __funnelshift_r(lo, hi, sh);
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(tab + k));
-                    acc += t.x * byte_to_float(v, 0x7540u);
-                    acc += t.y * byte_to_float(v, 0x7541u);
-                    acc += t.z * byte_to_float(v, 0x7542u);
-                    acc += t.w * byte_to_float(v, 0x7543u);
-                    lo = hi;
+                    const uint32_t hi0 = roww[wi0 + (k >> 2) + 1], hi1 = roww[wi1 + (k >> 2) + 1];
+                    const float4 t0 = __ldg(reinterpret_cast<const float4*>(tab0 + k));
+                    const float4 t1 = __ldg(reinterpret_cast<const float4*>(tab1 + k));
+                    acc0 = dot4_bytes(acc0, t0, __funnelshift_r(lo0, hi0, sh0));
+                    acc1 = dot4_bytes(acc1, t1, __funnelshift_r(lo1, hi1, sh1));
+                    lo0 = hi0;
+                    lo1 = hi1;
                 }
             } else {
-                for (int j = 0; j < taps; ++j) acc += __ldg(tab + j) * (float)row[reflect101(base + j, W)];
+                acc0 = hpass_slow(row, tab0, base0, taps, W);
+                if (have2) acc1 = hpass_slow(row, tab1, base1, taps, W);
             }
-            out[dx] = acc;
+            out[dx] = acc0;
+            if (have2) out[dx2] = acc1;
         }
     }
 }
@@ -375,7 +399,8 @@ __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h,
 
 // Level entry: flow_l = resize(flow_{l+1}) * (1/pyr_scale) (zeros on the coarsest level), then
 // UpdateMatrices.  The upsampled flow itself is never stored: BlurBox rebuilds the flow from M alone.
-__global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
+template <int VARIANT>
+__global__ void __launch_bounds__(256, VARIANT == 2 ? 6 : 8) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
                                                            int pitch, int pair_stride,
                                                            const float2* __restrict__ cflow, int cw, int ch,
                                                            int cpitch, size_t cflow_stride,
@@ -404,7 +429,8 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
     }
     if (flow_dbg) flow_dbg[(size_t)p * flow_dbg_stride + (size_t)y * flow_dbg_pitch + x] = make_float2(dx, dy);
     const float* R0 = R + (size_t)(p * pair_stride) * 5 * plane;
-    update_matrices_fast(x, y, w, h, pitch, (int)plane, true, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
+    if (VARIANT == 0) update_matrices_px(x, y, w, h, pitch, plane, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
+    else update_matrices_fast(x, y, w, h, pitch, (int)plane, true, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -693,13 +719,15 @@ __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h,
     Mout[o + 4 * plane] = r6 * r2 + r5 * r3;
 }
 
-template <int M_, bool LAST>
-__global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                              const __grid_constant__ CUtensorMap tmapR, IterArgs a) {
+template <int M_, bool LAST, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                             const __grid_constant__ CUtensorMap tmapR,
+                                                                             IterArgs a) {
     constexpr int RW = IT_TX + 16;          // 80 staged columns (halo 8 each side, 16-byte aligned)
     constexpr int RH = IT_TY + 2 * M_;      // staged rows
     constexpr int CH = RH * RW;             // floats per plane box
     constexpr int NC = IT_TX + 2 * M_;      // columns the vertical pass must produce
+    constexpr int NW = NT / 32;             // warps
     extern __shared__ __align__(128) float box[];   // [5][RH][RW]
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -722,7 +750,7 @@ __global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_const
 
     if (!interior) {
         // replicate borders: every out-of-image cell takes the value of the clamped (in-image) cell
-        for (int idx = tid; idx < 5 * CH; idx += 256) {
+        for (int idx = tid; idx < 5 * CH; idx += NT) {
             const int c = idx / CH, rem = idx - c * CH;
             const int rr = rem / RW, cc = rem - rr * RW;
             const int y = y0 - M_ + rr, x = x0 - 8 + cc;
@@ -732,8 +760,8 @@ __global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_const
         __syncthreads();
     }
 
-    // ---- vertical running sums, in place: 15 warp-tasks (plane, 32-column block) over 8 warps ----
-    for (int t = warp; t < 15; t += 8) {
+    // ---- vertical running sums, in place: 15 warp-tasks (plane, 32-column block) ----
+    for (int t = warp; t < 15; t += NW) {
         const int c = t / 3, col = (t - 3 * c) * 32 + lane;
         if (col < NC) {
             float* q = box + c * CH + (8 - M_) + col;
@@ -759,9 +787,11 @@ __global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_const
     // ---- horizontal sums, in place: half-warp = one row, thread = 4 outputs ----
     {
         const int q4 = tid & 15, rsub = tid >> 4;
+        constexpr int ROWS_PER_IT = NT / 16;
 #pragma unroll 2
-        for (int it = 0; it < 10; ++it) {
-            const int c = it >> 1, r = (it & 1) * 16 + rsub;
+        for (int it = 0; it < (5 * IT_TY) / ROWS_PER_IT; ++it) {
+            const int task = it * ROWS_PER_IT + rsub;
+            const int c = task / IT_TY, r = task - c * IT_TY;
             float* row = box + c * CH + r * RW + 4 * q4;
             float u[20];
 #pragma unroll
@@ -785,8 +815,8 @@ __global__ void __launch_bounds__(256, 3) iter_box_tma_kernel(const __grid_const
     const bool edge = (x0 < 5) || (y0 < 5) || (x0 + IT_TX > w - 5) || (y0 + IT_TY > h - 5);
     const float scale = a.scale;
 #pragma unroll 2
-    for (int j = 0; j < (IT_TX * IT_TY) / 256; ++j) {
-        const int idx = j * 256 + tid;
+    for (int j = 0; j < (IT_TX * IT_TY) / NT; ++j) {
+        const int idx = j * NT + tid;
         const int cx = idx & 63, r = idx >> 6;
         const int x = x0 + cx, y = y0 + r;
         if (x >= w || y >= h) continue;
@@ -832,16 +862,16 @@ static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s
     return MAVD_OK;
 }
 
-template <int M_, bool LAST>
+template <int M_, bool LAST, int NT>
 static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const IterArgs& a, dim3 grid, cudaStream_t s) {
     constexpr size_t smem = sizeof(float) * 5 * (IT_TY + 2 * M_) * (IT_TX + 16);
     static bool configured = false;
     if (!configured) {
-        MAVD_CUDA(cudaFuncSetAttribute(iter_box_tma_kernel<M_, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MAVD_CUDA(cudaFuncSetAttribute(iter_box_tma_kernel<M_, LAST, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         configured = true;
     }
-    iter_box_tma_kernel<M_, LAST><<<grid, 256, smem, s>>>(map, mapR, a);
+    iter_box_tma_kernel<M_, LAST, NT><<<grid, NT, smem, s>>>(map, mapR, a);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
@@ -849,11 +879,20 @@ static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, cons
 template <bool LAST>
 static int launch_iter_tma_m(int m, const CUtensorMap& map, const CUtensorMap& mapR, const IterArgs& a, dim3 grid,
                              cudaStream_t s) {
+    static const int nt = getenv("MAVD_ITER_NT") ? atoi(getenv("MAVD_ITER_NT")) : 256;
+    if (nt == 512) {
+        switch (m) {
+            case 5: return launch_iter_tma<5, LAST, 512>(map, mapR, a, grid, s);
+            case 6: return launch_iter_tma<6, LAST, 512>(map, mapR, a, grid, s);
+            case 7: return launch_iter_tma<7, LAST, 512>(map, mapR, a, grid, s);
+            default: return launch_iter_tma<8, LAST, 512>(map, mapR, a, grid, s);
+        }
+    }
     switch (m) {
-        case 5: return launch_iter_tma<5, LAST>(map, mapR, a, grid, s);
-        case 6: return launch_iter_tma<6, LAST>(map, mapR, a, grid, s);
-        case 7: return launch_iter_tma<7, LAST>(map, mapR, a, grid, s);
-        default: return launch_iter_tma<8, LAST>(map, mapR, a, grid, s);
+        case 5: return launch_iter_tma<5, LAST, 256>(map, mapR, a, grid, s);
+        case 6: return launch_iter_tma<6, LAST, 256>(map, mapR, a, grid, s);
+        case 7: return launch_iter_tma<7, LAST, 256>(map, mapR, a, grid, s);
+        default: return launch_iter_tma<8, LAST, 256>(map, mapR, a, grid, s);
     }
 }
 
@@ -887,7 +926,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             P.vblk0 = vb; P.vtiles_x = ceil_div(L.w, 64);
             vb += P.vtiles_x * ceil_div(L.h, 4);
         }
-        pyr_hpass_all_kernel<<<dim3(ceil_div(Hh, 32), n_frames, PYR_SPLITS), 256, 32 * H->pyr_row_pitch, s>>>(
+        pyr_hpass_all_kernel<<<dim3(ceil_div(Hh, 32), n_frames, PYR_SPLITS), PYR_NT, 32 * H->pyr_row_pitch, s>>>(
             d_frames, frame_bytes, W, Hh, H->pyr_row_pitch, d);
         MAVD_LAUNCHED();
         pyr_vpass_all_kernel<<<dim3(vb, n_frames), 256, 0, s>>>(Hh, d);
@@ -914,10 +953,14 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             dim3 g(ceil_div(L.w, 64), ceil_div(L.h, 4), n_pairs);
             const bool top = (li == H->n_levels - 1);
             const Level* C = top ? nullptr : &H->lv[li + 1];
-            matrices_init_kernel<<<g, 256, 0, s>>>(
-                L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,
-                top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,
-                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0);
+            static const int variant = getenv("MAVD_MI_VARIANT") ? atoi(getenv("MAVD_MI_VARIANT")) : 0;
+#define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,                  \
+                top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,        \
+                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0
+            if (variant == 1) matrices_init_kernel<1><<<g, 256, 0, s>>>(MI_ARGS);
+            else if (variant == 2) matrices_init_kernel<2><<<g, 256, 0, s>>>(MI_ARGS);
+            else matrices_init_kernel<0><<<g, 256, 0, s>>>(MI_ARGS);
+#undef MI_ARGS
             MAVD_LAUNCHED();
         }
         // iterations
