@@ -3,6 +3,7 @@
 // thread-local message.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -386,6 +387,18 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
         C_TRY(A.upload(&H->d_xn, xn));
         C_TRY(A.upload(&H->d_yn, yn));
     }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&H->s_aux, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&H->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            H->s_aux = nullptr;   // the path still works, just without the overlap
+        }
+        const char* env = getenv("MAVD_NO_OVERLAP");
+        H->no_overlap = env && env[0] == '1';
+    }
     H->bytes = A.bytes;
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -408,6 +421,9 @@ int mavd_destroy(mavd_handle h) {
         if (S.ev_done) cudaEventDestroy(S.ev_done);
         if (S.ev_out) cudaEventDestroy(S.ev_out);
     }
+    if (H->s_aux) cudaStreamDestroy(H->s_aux);
+    if (H->ev_fork) cudaEventDestroy(H->ev_fork);
+    if (H->ev_join) cudaEventDestroy(H->ev_join);
     if (H->s_in) cudaStreamDestroy(H->s_in);
     if (H->s_out) cudaStreamDestroy(H->s_out);
     for (auto& r : H->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -199,7 +199,9 @@ __device__ __forceinline__ void blur3_row4(const uint8_t* __restrict__ p, float 
     hv[3] = 0.25f * v6 + 0.5f * v7 + 0.25f * v8;
 }
 
-template <bool U8>
+// N_ > 0: poly_n known at compile time (5, 7 and 8 are instantiated: OpenCV's sample value, its other GPU value
+// and the reference's) so the tap loops carry no predicates; N_ == 0: any poly_n <= 8 at run time.
+template <bool U8, int N_>
 __global__ void __launch_bounds__(256) polyexp_kernel(const void* __restrict__ src_base, size_t src_stride, int w,
                                                      int h, int pitch, int u8_aligned, PolyConst pc,
                                                      float* __restrict__ R, size_t plane) {
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const void* __restrict__ s
     __shared__ __align__(16) float t[3][PE_TY * PE_RW];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * PE_TX, y0 = blockIdx.y * PE_TY;
-    const int n = pc.n;
+    const int n = N_ > 0 ? N_ : pc.n;
 
     // stage rows y0-n .. y0+TY+n-1 (replicate), columns x0-8 .. x0+TX+8-1 (replicate)
     const int rows = PE_TY + 2 * n;
@@ -393,14 +395,9 @@ __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, i
     Mout[4 * plane + o] = r6 * r2 + r5 * r3;
 }
 
-__device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h, int pitch, int plane, bool edge,
-                                                     float dx, float dy, const float* __restrict__ R0,
-                                                     const float* __restrict__ R1, float* __restrict__ Mout);
-
 // Level entry: flow_l = resize(flow_{l+1}) * (1/pyr_scale) (zeros on the coarsest level), then
 // UpdateMatrices.  The upsampled flow itself is never stored: BlurBox rebuilds the flow from M alone.
-template <int VARIANT>
-__global__ void __launch_bounds__(256, VARIANT == 2 ? 6 : 8) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
+__global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
                                                            int pitch, int pair_stride,
                                                            const float2* __restrict__ cflow, int cw, int ch,
                                                            int cpitch, size_t cflow_stride,
@@ -429,8 +426,9 @@ __global__ void __launch_bounds__(256, VARIANT == 2 ? 6 : 8) matrices_init_kerne
     }
     if (flow_dbg) flow_dbg[(size_t)p * flow_dbg_stride + (size_t)y * flow_dbg_pitch + x] = make_float2(dx, dy);
     const float* R0 = R + (size_t)(p * pair_stride) * 5 * plane;
-    if (VARIANT == 0) update_matrices_px(x, y, w, h, pitch, plane, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
-    else update_matrices_fast(x, y, w, h, pitch, (int)plane, true, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
+    // (the 32-bit-offset variant used by the fused iteration needs > 32 registers here and loses more to occupancy
+    // than it gains in instructions: 0.87 vs 0.675 ms per 16-pair step, profiles/README.md)
+    update_matrices_px(x, y, w, h, pitch, plane, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -879,15 +877,6 @@ static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, cons
 template <bool LAST>
 static int launch_iter_tma_m(int m, const CUtensorMap& map, const CUtensorMap& mapR, const IterArgs& a, dim3 grid,
                              cudaStream_t s) {
-    static const int nt = getenv("MAVD_ITER_NT") ? atoi(getenv("MAVD_ITER_NT")) : 256;
-    if (nt == 512) {
-        switch (m) {
-            case 5: return launch_iter_tma<5, LAST, 512>(map, mapR, a, grid, s);
-            case 6: return launch_iter_tma<6, LAST, 512>(map, mapR, a, grid, s);
-            case 7: return launch_iter_tma<7, LAST, 512>(map, mapR, a, grid, s);
-            default: return launch_iter_tma<8, LAST, 512>(map, mapR, a, grid, s);
-        }
-    }
     switch (m) {
         case 5: return launch_iter_tma<5, LAST, 256>(map, mapR, a, grid, s);
         case 6: return launch_iter_tma<6, LAST, 256>(map, mapR, a, grid, s);
@@ -932,38 +921,43 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         pyr_vpass_all_kernel<<<dim3(vb, n_frames), 256, 0, s>>>(Hh, d);
         MAVD_LAUNCHED();
     }
-    for (int li = H->n_levels - 1; li >= 0; --li) {
+    // polynomial expansion of one level for all frames (level 0 reads the u8 frames and blurs on the fly)
+    auto expand_level = [&](int li, cudaStream_t st) -> int {
         Level& L = H->lv[li];
-        // polynomial expansion for all frames (level 0 reads the u8 frames and blurs on the fly)
-        {
-            ProfScope ps(&H->prof, MAVD_PROF_POLYEXP, s);
-            dim3 g(ceil_div(L.w, PE_TX), ceil_div(L.h, PE_TY), n_frames);
-            if (li == 0) {
-                const int aligned = ((reinterpret_cast<uintptr_t>(d_frames) & 3) == 0 && (W & 3) == 0) ? 1 : 0;
-                polyexp_kernel<true><<<g, 256, 0, s>>>(d_frames, frame_bytes, L.w, L.h, L.pitch, aligned, H->poly, L.R,
-                                                       L.plane);
-            } else {
-                polyexp_kernel<false><<<g, 256, 0, s>>>(L.img, L.plane, L.w, L.h, L.pitch, 0, H->poly, L.R, L.plane);
-            }
-            MAVD_LAUNCHED();
+        ProfScope ps(&H->prof, MAVD_PROF_POLYEXP, st);
+        dim3 g(ceil_div(L.w, PE_TX), ceil_div(L.h, PE_TY), n_frames);
+        const int aligned = ((reinterpret_cast<uintptr_t>(d_frames) & 3) == 0 && (W & 3) == 0) ? 1 : 0;
+#define PE_LAUNCH(N)                                                                                                   \
+        do {                                                                                                           \
+            if (li == 0) polyexp_kernel<true, N><<<g, 256, 0, st>>>(d_frames, frame_bytes, L.w, L.h, L.pitch, aligned,  \
+                                                                    H->poly, L.R, L.plane);                            \
+            else polyexp_kernel<false, N><<<g, 256, 0, st>>>(L.img, L.plane, L.w, L.h, L.pitch, 0, H->poly, L.R,       \
+                                                             L.plane);                                                 \
+        } while (0)
+        switch (H->poly.n) {
+            case 5: PE_LAUNCH(5); break;
+            case 7: PE_LAUNCH(7); break;
+            case 8: PE_LAUNCH(8); break;
+            default: PE_LAUNCH(0); break;
         }
-        // matrices from the upsampled coarser flow
+#undef PE_LAUNCH
+        MAVD_LAUNCHED();
+        return MAVD_OK;
+    };
+    // matrices from the upsampled coarser flow, then the iterations of one level
+    auto solve_level = [&](int li, cudaStream_t st) -> int {
+        Level& L = H->lv[li];
         {
-            ProfScope ps(&H->prof, MAVD_PROF_MATRICES, s);
+            ProfScope ps(&H->prof, MAVD_PROF_MATRICES, st);
             dim3 g(ceil_div(L.w, 64), ceil_div(L.h, 4), n_pairs);
             const bool top = (li == H->n_levels - 1);
             const Level* C = top ? nullptr : &H->lv[li + 1];
-            static const int variant = getenv("MAVD_MI_VARIANT") ? atoi(getenv("MAVD_MI_VARIANT")) : 0;
-#define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,                  \
-                top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,        \
-                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0
-            if (variant == 1) matrices_init_kernel<1><<<g, 256, 0, s>>>(MI_ARGS);
-            else if (variant == 2) matrices_init_kernel<2><<<g, 256, 0, s>>>(MI_ARGS);
-            else matrices_init_kernel<0><<<g, 256, 0, s>>>(MI_ARGS);
-#undef MI_ARGS
+            matrices_init_kernel<<<g, 256, 0, st>>>(
+                L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,
+                top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,
+                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0);
             MAVD_LAUNCHED();
         }
-        // iterations
         int cur = 0;
         for (int it = 0; it < fp.iterations; ++it) {
             const bool last = (it == fp.iterations - 1);
@@ -988,17 +982,43 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             dim3 g(ceil_div(L.w, IT_TX), ceil_div(L.h, IT_TY), n_pairs);
             const int RW = IT_TX + 2 * hx, RH = IT_TY + 2 * m;
             const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
-            ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), s);
+            ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), st);
             int rc;
             if (!gauss && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter)
-                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], L.tmapR, a, g, s)
-                          : launch_iter_tma_m<false>(m, L.tmapM[cur], L.tmapR, a, g, s);
-            else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, s) : launch_iter<true, false>(a, g, smem, s);
-            else       rc = last ? launch_iter<false, true>(a, g, smem, s) : launch_iter<false, false>(a, g, smem, s);
+                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], L.tmapR, a, g, st)
+                          : launch_iter_tma_m<false>(m, L.tmapM[cur], L.tmapR, a, g, st);
+            else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, st) : launch_iter<true, false>(a, g, smem, st);
+            else       rc = last ? launch_iter<false, true>(a, g, smem, st) : launch_iter<false, false>(a, g, smem, st);
             if (rc != MAVD_OK) return rc;
             if (!last) cur ^= 1;
         }
         L.last_m = cur;
+        return MAVD_OK;
+    };
+
+    // The coarse levels (>= 2) are chains of small, latency-bound launches (a 60x34 level is 2 tiles per pair); the
+    // expansions of levels 1 and 0 are large and depend only on the frames / pyramid.  Run the coarse chain on a
+    // high-priority side stream while the caller's stream does the two big expansions, and join before level 1's
+    // matrices need the level-2 flow.  Stream order as seen by the caller is unchanged.
+    const bool fork = H->n_levels >= 3 && H->s_aux != nullptr && !H->no_overlap;
+    if (fork) {
+        MAVD_CUDA(cudaEventRecord(H->ev_fork, s));
+        MAVD_CUDA(cudaStreamWaitEvent(H->s_aux, H->ev_fork, 0));
+        for (int li = H->n_levels - 1; li >= 2; --li) {
+            TRY_RC(expand_level(li, H->s_aux));
+            TRY_RC(solve_level(li, H->s_aux));
+        }
+        MAVD_CUDA(cudaEventRecord(H->ev_join, H->s_aux));
+        TRY_RC(expand_level(1, s));
+        TRY_RC(expand_level(0, s));
+        MAVD_CUDA(cudaStreamWaitEvent(s, H->ev_join, 0));
+        TRY_RC(solve_level(1, s));
+        TRY_RC(solve_level(0, s));
+    } else {
+        for (int li = H->n_levels - 1; li >= 0; --li) {
+            TRY_RC(expand_level(li, s));
+            TRY_RC(solve_level(li, s));
+        }
     }
     H->last_pairs = n_pairs;
     H->last_stride = pair_stride;

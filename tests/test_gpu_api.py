@@ -201,8 +201,21 @@ def test_farneback_class_process():
         # crosses a truncation boundary
         ref_img, _ = vis_np.process_visualisation_cv2(ref_flow, (H, W, 3))
         assert (out == ref_img).all(-1).mean() > 0.99
-    # a frame identical to its predecessor: zero flow -> the reference's invalid_frame branch returns the previous result
-    fb2 = Farneback(FakeCapture([bgr[0], bgr[1], bgr[1]]), None)
-    first = fb2.process()
-    again = fb2.process()
-    assert np.array_equal(again, first)
+    # invalid_frame branch (farneback.py:97-98): an all-zero value channel returns the previous result.  It needs an
+    # exactly uniform flow magnitude, which Farneback never produces (even identical frames give non-zero flow at
+    # the right/bottom border, in cv2 as well), so the kernel's counter is checked directly on synthetic fields.
+    import torch
+    from mav_detection_b200 import _lib
+    lib = _lib.load()
+    for name, field, expect_invalid in (('zero', np.zeros((H, W, 2), np.float32), True),
+                                        ('const', np.full((H, W, 2), 1.5, np.float32), True),
+                                        ('ramp', flow, False)):
+        d = torch.from_numpy(np.ascontiguousarray(field)).cuda()
+        out_d = torch.empty((H, W, 3), dtype=torch.uint8, device='cuda')
+        scratch = torch.zeros((3,), dtype=torch.int32, device='cuda')
+        _lib.check(lib.mavd_flow_vis(d.data_ptr(), H * W, out_d.data_ptr(), scratch.data_ptr(), None))
+        torch.cuda.synchronize()
+        ref_img, ref_invalid = vis_np.process_visualisation(field)
+        assert ref_invalid == expect_invalid, name
+        assert (int(scratch[2].item()) == 0) == expect_invalid, name
+        assert np.array_equal(out_d.cpu().numpy(), ref_img), name
