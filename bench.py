@@ -27,15 +27,15 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (W, H, farneback params, pairs per step, label)
-    'c2': (1920, 1080, dict(pyr_scale=0.5, levels=5, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0), 16,
+    'c2': (1920, 1080, dict(pyr_scale=0.5, levels=5, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0), 64,
            'C2: synthetic AirSim-like 1920x1080 sequence, Farneback (0.5,5,15,3,5,1.2,0) 6 pyramid images'),
-    'c2ref': (1920, 1080, dict(pyr_scale=0.4, levels=1, winsize=12, iterations=10, poly_n=8, poly_sigma=1.2, flags=0), 16,
+    'c2ref': (1920, 1080, dict(pyr_scale=0.4, levels=1, winsize=12, iterations=10, poly_n=8, poly_sigma=1.2, flags=0), 32,
               "C2': 1920x1080 with the reference's own parameters (0.4,1,12,10,8,1.2,0)"),
     'c1': (640, 480, dict(pyr_scale=0.4, levels=1, winsize=12, iterations=10, poly_n=8, poly_sigma=1.2, flags=0), 1,
            'C1: one 640x480 pair, reference parameters'),
     'c3': (640, 480, dict(pyr_scale=0.5, levels=5, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0), 64,
            'C3: 640x480, 64 pairs per launch'),
-    'c4': (3840, 2160, dict(pyr_scale=0.5, levels=7, winsize=15, iterations=10, poly_n=5, poly_sigma=1.2, flags=0), 4,
+    'c4': (3840, 2160, dict(pyr_scale=0.5, levels=7, winsize=15, iterations=10, poly_n=5, poly_sigma=1.2, flags=0), 8,
            'C4: 3840x2160, 7 pyramid images, winsize 15, 10 iterations'),
 }
 N_BATCHES = 4          # distinct resident batches cycled through (working set per step >> L2 anyway)
@@ -101,9 +101,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
-def build_workload(name: str, rank: int = 0):
+def build_workload(name: str, rank: int = 0, pairs: int = 0):
     from mav_detection_b200 import synth
     W, H, params, B, label = WORKLOADS[name]
+    B = pairs or B
     n_frames = N_BATCHES * B + 1
     seq = synth.make_sequence(W, H, n_frames, seq=rank, with_rotation=False)
     rs = np.random.RandomState(1000 + rank)   # legacy generator = the stream np.random.randint draws from
@@ -178,7 +179,7 @@ def run_reference(args):
     if rank != 0:
         return
     import cv2
-    wl = build_workload(args.workload)
+    wl = build_workload(args.workload, 0, args.pairs)
     workers = cpu_workers()
     per_step = workers
     ref = CpuReference(wl, workers)
@@ -218,7 +219,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    wl = build_workload(args.workload, rank)
+    wl = build_workload(args.workload, rank, args.pairs)
     W, H, B, params = wl['W'], wl['H'], wl['B'], wl['params']
     seq = wl['seq']
     eng = engine.Engine(W, H, params, max_pairs=B, device=local)
@@ -392,6 +393,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--pairs', type=int, default=0, help='frame pairs per step (default: the workload\'s)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

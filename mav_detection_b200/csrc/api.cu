@@ -392,12 +392,13 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&H->s_aux, cudaStreamNonBlocking, hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&H->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&H->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&H->ev_pyr, cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
             H->s_aux = nullptr;   // the path still works, just without the overlap
         }
-        const char* env = getenv("MAVD_NO_OVERLAP");
-        H->no_overlap = env && env[0] == '1';
+        const char* env = getenv("MAVD_OVERLAP");
+        if (env && env[0] >= '0' && env[0] <= '2') H->overlap_mode = env[0] - '0';
     }
     H->bytes = A.bytes;
     cudaError_t e = cudaDeviceSynchronize();
@@ -424,6 +425,7 @@ int mavd_destroy(mavd_handle h) {
     if (H->s_aux) cudaStreamDestroy(H->s_aux);
     if (H->ev_fork) cudaEventDestroy(H->ev_fork);
     if (H->ev_join) cudaEventDestroy(H->ev_join);
+    if (H->ev_pyr) cudaEventDestroy(H->ev_pyr);
     if (H->s_in) cudaStreamDestroy(H->s_in);
     if (H->s_out) cudaStreamDestroy(H->s_out);
     for (auto& r : H->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -154,8 +154,9 @@ struct mavd_handle_s {
     } slot[MAVD_HOST_SLOTS];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaStream_t s_aux = nullptr;     // high-priority side stream for the coarse pyramid levels (farneback_run)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool no_overlap = false;          // MAVD_NO_OVERLAP=1: keep every launch on the caller's stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pyr = nullptr;
+    int overlap_mode = 2;             // MAVD_OVERLAP: 0 = every launch on the caller's stream, 1 = coarse levels on the
+                                      // side stream, 2 = pyramid + coarse levels on the side stream
     mavd::Profiler prof;
     bool force_generic_iter = false;  // tests: run the non-TMA iteration kernel
     // last call bookkeeping for taps

@@ -406,11 +406,13 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
                                                            const int* __restrict__ fyi0,
                                                            const float* __restrict__ fya, float up_scale,
                                                            float* __restrict__ M, float2* __restrict__ flow_dbg,
-                                                           int flow_dbg_pitch, size_t flow_dbg_stride) {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+                                                           int flow_dbg_pitch, size_t flow_dbg_stride, int n_pairs,
+                                                           int tiles_x) {
+    // 1-D grid, pair index fastest (same L2 sharing of R between consecutive pairs as in iter_box_tma_kernel)
+    const int p = blockIdx.x % n_pairs, tile = blockIdx.x / n_pairs;
+    const int x = (tile % tiles_x) * 64 + (threadIdx.x & 63);
+    const int y = (tile / tiles_x) * 4 + (threadIdx.x >> 6);
     if (x >= w || y >= h) return;
-    const int p = blockIdx.z;
     float dx = 0.f, dy = 0.f;
     if (cflow) {
         const float2* cf = cflow + (size_t)p * cflow_stride;
@@ -453,6 +455,7 @@ struct IterArgs {
     float scale;            // 1 / winsize^2 (box) or 1 (Gaussian: kernel already normalised)
     int pair_stride;
     const float* gk;        // Gaussian half kernel [m+1] (device) or nullptr
+    int n_pairs, tiles_x;   // TMA kernel: 1-D grid (see iter_box_tma_kernel)
 };
 
 template <int M_>
@@ -729,8 +732,14 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
     extern __shared__ __align__(128) float box[];   // [5][RH][RW]
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * IT_TX, y0 = blockIdx.y * IT_TY;
-    const int p = blockIdx.z;
+    // 1-D grid with the pair index fastest: CTAs that run at the same time work on the SAME tile of consecutive
+    // pairs, and R1 of pair p is R0 of pair p+1 (sequence mode), so every R plane is fetched from HBM once and
+    // served to its second reader from L2
+    // (the last iteration reads no R: it keeps tile-fastest order, which is better for the M halo reuse)
+    const int n_tiles = gridDim.x / a.n_pairs;
+    const int p = LAST ? blockIdx.x / n_tiles : blockIdx.x % a.n_pairs;
+    const int tile = LAST ? blockIdx.x % n_tiles : blockIdx.x / a.n_pairs;
+    const int x0 = (tile % a.tiles_x) * IT_TX, y0 = (tile / a.tiles_x) * IT_TY;
     const int w = a.w, h = a.h, pitch = a.pitch;
     const int plane = (int)a.plane;
 
@@ -896,8 +905,9 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
     const size_t frame_bytes = (size_t)W * Hh;
 
     // pyramid images of every coarser level for all frames: two launches
-    if (H->n_levels > 1) {
-        ProfScope ps(&H->prof, MAVD_PROF_PYRAMID, s);
+    auto build_pyramid = [&](cudaStream_t st) -> int {
+        if (H->n_levels <= 1) return MAVD_OK;
+        ProfScope ps(&H->prof, MAVD_PROF_PYRAMID, st);
         static bool configured = false;
         if (!configured) {
             MAVD_CUDA(cudaFuncSetAttribute(pyr_hpass_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -915,12 +925,13 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             P.vblk0 = vb; P.vtiles_x = ceil_div(L.w, 64);
             vb += P.vtiles_x * ceil_div(L.h, 4);
         }
-        pyr_hpass_all_kernel<<<dim3(ceil_div(Hh, 32), n_frames, PYR_SPLITS), PYR_NT, 32 * H->pyr_row_pitch, s>>>(
+        pyr_hpass_all_kernel<<<dim3(ceil_div(Hh, 32), n_frames, PYR_SPLITS), PYR_NT, 32 * H->pyr_row_pitch, st>>>(
             d_frames, frame_bytes, W, Hh, H->pyr_row_pitch, d);
         MAVD_LAUNCHED();
-        pyr_vpass_all_kernel<<<dim3(vb, n_frames), 256, 0, s>>>(Hh, d);
+        pyr_vpass_all_kernel<<<dim3(vb, n_frames), 256, 0, st>>>(Hh, d);
         MAVD_LAUNCHED();
-    }
+        return MAVD_OK;
+    };
     // polynomial expansion of one level for all frames (level 0 reads the u8 frames and blurs on the fly)
     auto expand_level = [&](int li, cudaStream_t st) -> int {
         Level& L = H->lv[li];
@@ -952,10 +963,10 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             dim3 g(ceil_div(L.w, 64), ceil_div(L.h, 4), n_pairs);
             const bool top = (li == H->n_levels - 1);
             const Level* C = top ? nullptr : &H->lv[li + 1];
-            matrices_init_kernel<<<g, 256, 0, st>>>(
+            matrices_init_kernel<<<dim3(g.x * g.y * g.z), 256, 0, st>>>(
                 L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,
                 top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,
-                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0);
+                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0, n_pairs, (int)g.x);
             MAVD_LAUNCHED();
         }
         int cur = 0;
@@ -980,13 +991,16 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
                 a.flow = nullptr; a.flow_pitch = 0; a.flow_stride = 0;
             }
             dim3 g(ceil_div(L.w, IT_TX), ceil_div(L.h, IT_TY), n_pairs);
+            a.n_pairs = n_pairs;
+            a.tiles_x = g.x;
+            const dim3 g1(g.x * g.y * g.z);
             const int RW = IT_TX + 2 * hx, RH = IT_TY + 2 * m;
             const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
             ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), st);
             int rc;
             if (!gauss && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter)
-                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], L.tmapR, a, g, st)
-                          : launch_iter_tma_m<false>(m, L.tmapM[cur], L.tmapR, a, g, st);
+                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], L.tmapR, a, g1, st)
+                          : launch_iter_tma_m<false>(m, L.tmapM[cur], L.tmapR, a, g1, st);
             else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, st) : launch_iter<true, false>(a, g, smem, st);
             else       rc = last ? launch_iter<false, true>(a, g, smem, st) : launch_iter<false, false>(a, g, smem, st);
             if (rc != MAVD_OK) return rc;
@@ -1000,8 +1014,26 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
     // expansions of levels 1 and 0 are large and depend only on the frames / pyramid.  Run the coarse chain on a
     // high-priority side stream while the caller's stream does the two big expansions, and join before level 1's
     // matrices need the level-2 flow.  Stream order as seen by the caller is unchanged.
-    const bool fork = H->n_levels >= 3 && H->s_aux != nullptr && !H->no_overlap;
-    if (fork) {
+    const bool fork = H->n_levels >= 3 && H->s_aux != nullptr && H->overlap_mode != 0;
+    if (fork && H->overlap_mode == 2) {
+        // the pyramid too goes to the side stream: level 0's expansion reads only the u8 frames
+        MAVD_CUDA(cudaEventRecord(H->ev_fork, s));
+        MAVD_CUDA(cudaStreamWaitEvent(H->s_aux, H->ev_fork, 0));
+        TRY_RC(build_pyramid(H->s_aux));
+        MAVD_CUDA(cudaEventRecord(H->ev_pyr, H->s_aux));
+        for (int li = H->n_levels - 1; li >= 2; --li) {
+            TRY_RC(expand_level(li, H->s_aux));
+            TRY_RC(solve_level(li, H->s_aux));
+        }
+        MAVD_CUDA(cudaEventRecord(H->ev_join, H->s_aux));
+        TRY_RC(expand_level(0, s));
+        MAVD_CUDA(cudaStreamWaitEvent(s, H->ev_pyr, 0));
+        TRY_RC(expand_level(1, s));
+        MAVD_CUDA(cudaStreamWaitEvent(s, H->ev_join, 0));
+        TRY_RC(solve_level(1, s));
+        TRY_RC(solve_level(0, s));
+    } else if (fork) {
+        TRY_RC(build_pyramid(s));
         MAVD_CUDA(cudaEventRecord(H->ev_fork, s));
         MAVD_CUDA(cudaStreamWaitEvent(H->s_aux, H->ev_fork, 0));
         for (int li = H->n_levels - 1; li >= 2; --li) {
@@ -1015,6 +1047,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         TRY_RC(solve_level(1, s));
         TRY_RC(solve_level(0, s));
     } else {
+        TRY_RC(build_pyramid(s));
         for (int li = H->n_levels - 1; li >= 0; --li) {
             TRY_RC(expand_level(li, s));
             TRY_RC(solve_level(li, s));
