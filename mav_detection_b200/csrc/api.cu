@@ -310,7 +310,7 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
                 if (axis == 0) { C_TRY(A.upload(&L.xbase, base)); C_TRY(A.upload(&L.xtab, tab)); }
                 else           { C_TRY(A.upload(&L.ybase, base)); C_TRY(A.upload(&L.ytab, tab)); }
             }
-            C_TRY(A.alloc(&L.tmp, (size_t)F * Hh * L.pitch));
+            C_TRY(A.alloc(&L.tmp, (size_t)F * L.h * round_up(W, 4)));   // vertical-pass output [F][h_l][Wp]
         }
         C_TRY(A.alloc(&L.img, (size_t)F * L.plane));
         C_TRY(A.alloc(&L.R, (size_t)F * 5 * L.plane));
@@ -339,15 +339,6 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
         resize_tables(C.h, L.h, i0, a);
         C_TRY(A.upload(&L.fyi0, i0));
         C_TRY(A.upload(&L.fya, a));
-    }
-    {
-        int rp = round_up(W, 4);
-        if (((rp / 4) & 1) == 0) rp += 4;   // odd word pitch: lane = row reads hit 32 distinct banks
-        H->pyr_row_pitch = rp;
-        if (H->n_levels > 1 && 32 * rp > 220 * 1024) {
-            set_error("width %d too large for the pyramid row staging (max ~7000)", W);
-            return fail(MAVD_ERR_UNSUPPORTED);
-        }
     }
     C_TRY(poly_setup(fp.poly_n, fp.poly_sigma, H->poly));
     {

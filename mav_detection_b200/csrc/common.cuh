@@ -63,7 +63,7 @@ struct Level {
     // pyramid tables (full-res -> this level): combined blur+resize filter of ksz+1 taps per output sample
     int* xbase = nullptr;  float* xtab = nullptr;   // [w], [w][ksz+1]
     int* ybase = nullptr;  float* ytab = nullptr;   // [h], [h][ksz+1]
-    float* tmp = nullptr;                           // [frames][H][pitch] horizontal pass output (levels >= 1)
+    float* tmp = nullptr;                           // [frames][h][Wp] vertical pass output (levels >= 1)
     // flow upsample tables (next-coarser level -> this level)
     int* fxi0 = nullptr; float* fxa = nullptr;  // [w]
     int* fyi0 = nullptr; float* fya = nullptr;  // [h]
@@ -122,7 +122,6 @@ struct mavd_handle_s {
     mavd::Level lv[mavd::kMaxLevels];  // lv[0] = finest (k = 0)
     mavd::PolyConst poly;
     float* gauss_win = nullptr;     // [m+1] device, FarnebackUpdateFlow_GaussianBlur half kernel
-    int pyr_row_pitch = 0;          // bytes per staged u8 row in pyr_hpass_all (word pitch odd)
     int max_frames = 0;
     size_t bytes = 0;
     // detection workspace

@@ -455,9 +455,8 @@ struct FastPrm {
     float dyn_offset, dyn_base, dyn_gain, dyn_min_mag, fixed_min_mag, fixed_angle;
 };
 
-__device__ __forceinline__ bool pixel_fast(double fdx, double fdy, int x, int y, double foex, double foey,
-                                           const FastPrm& p, bool& m_total, bool& m_fixed) {
-    const float fx = (float)fdx, fy = (float)fdy;
+__device__ __forceinline__ bool pixel_fast(float fx, float fy, float dx, float dy, const FastPrm& p, bool& m_total,
+                                           bool& m_fixed) {
     const float a2 = fx * fx + fy * fy;
     if (!(a2 < 1e30f)) return false;                       // NaN / inf / huge: exact path
     const float a = sqrtf(a2);
@@ -466,7 +465,6 @@ __device__ __forceinline__ bool pixel_fast(double fdx, double fdy, int x, int y,
     const bool gt_dyn = a > p.dyn_min_mag, gt_fix = a > p.fixed_min_mag;
     m_total = m_fixed = false;
     if (!gt_dyn && !gt_fix) return true;
-    const float dx = (float)((double)x - foex), dy = (float)((double)y - foey);
     const float b2 = dx * dx + dy * dy;
     if (!(b2 < 1e30f) || a2 * b2 < 1e-8f) return false;    // |f||d| near the 1e-6 clamp of the norm: exact path
     const float dot = fx * dx + fy * dy;
@@ -477,7 +475,7 @@ __device__ __forceinline__ bool pixel_fast(double fdx, double fdy, int x, int y,
         m_fixed = phi > p.fixed_angle;
     }
     if (gt_dyn) {
-        const float thr = p.dyn_offset + (p.dyn_base + p.dyn_gain / a);
+        const float thr = p.dyn_offset + (p.dyn_base + __fdividef(p.dyn_gain, a));   // 2 ulp: far inside the guard band
         if (fabsf(phi - thr) <= 2e-3f + 1e-5f * thr) return false;
         m_total = phi > thr;      // amin is impossible: the host enables FAST only when offset - base < 0
     }
@@ -515,7 +513,12 @@ __global__ void __launch_bounds__(256) residual_kernel(const ResidualArgs A, con
     const uint8_t* sky = A.sky ? A.sky + (size_t)f * A.sky_stride : nullptr;
     const uint8_t* seg = A.seg ? A.seg + (size_t)f * A.seg_stride : nullptr;
     const bool want_stats = A.stats_base != nullptr;
-    const double seg_thr = seg && want_stats ? 0.1 * (double)A.seg_max[f] : 0.0;
+    // g > 0.1 * max  <=>  g >= seg_min (g integer): the largest integer not above the float64 threshold, plus one
+    int seg_min = 0;
+    if (seg && want_stats) {
+        const double thr = 0.1 * (double)A.seg_max[f];
+        seg_min = (int)floor(thr) + 1;
+    }
 
     int c_tot = 0, c_fix = 0, c_pos = 0, c_neg = 0, c_tpt = 0, c_fpt = 0, c_tpf = 0, c_fpf = 0;
     int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;
@@ -553,6 +556,7 @@ __global__ void __launch_bounds__(256) residual_kernel(const ResidualArgs A, con
         }
         double yn = 0.0;
         if (MODE == 0 && dr.on) yn = __ldg(A.yn + y);
+        const float dyf = (float)((double)y - foey);     // FAST: FoE ray components in float32
         unsigned totw = 0, fixw = 0;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
@@ -581,7 +585,12 @@ __global__ void __launch_bounds__(256) residual_kernel(const ResidualArgs A, con
                 bool decided = false;
                 if (FAST) {
                     if (!not_sky) decided = true;          // both masks are multiplied by ~sky
-                    else decided = pixel_fast(fdx, fdy, x, y, foex, foey, fp, mt, mf);
+                    else {
+                        // without derotation the float64 flow IS the float32 input: skip the round trip
+                        const float ffx = (MODE == 0 && !dr.on) ? vfx[k] : (float)fdx;
+                        const float ffy = (MODE == 0 && !dr.on) ? vfy[k] : (float)fdy;
+                        decided = pixel_fast(ffx, ffy, (float)((double)x - foex), dyf, fp, mt, mf);
+                    }
                 }
                 if (!decided) {
                     double phi;
@@ -604,7 +613,7 @@ __global__ void __launch_bounds__(256) residual_kernel(const ResidualArgs A, con
                     c_fpt += mt && g <= 254;
                     c_tpf += mf && g >= 1;
                     c_fpf += mf && g <= 254;
-                    if ((double)g > seg_thr) { bx0 = min(bx0, x); bx1 = max(bx1, x); by0 = min(by0, y); by1 = max(by1, y); }
+                    if (g >= seg_min) { bx0 = min(bx0, x); bx1 = max(bx1, x); by0 = min(by0, y); by1 = max(by1, y); }
                     if (g > 127) { sfx += fdx; sfy += fdy; }
                 }
             }
