@@ -446,40 +446,45 @@ __device__ __forceinline__ void pixel_exact_f32(float fx, float fy, int x, int y
     m_fixed = (((a > (float)prm.fixed_min_mag) && not_sky) ? phi : 0.f) > (float)prm.fixed_angle;
 }
 
-// float32 pre-decision.  Returns false when the pixel must take the exact path.
-// Error budget of the estimate: the inputs are float64 values rounded once to float32 (direction error
-// < 3e-7 rad per vector), cross/dot carry < 2 ulp of |f||d|, atan2f < 4 ulp: together < 3e-4 degrees
-// for every angle in [0, 180]; the guard band is 2e-3 degrees plus 1e-5 relative on the dynamic
-// threshold, and 1e-5 relative on the magnitude gates (sqrtf error 2e-7 relative).
+// float32 pre-decision, branch-free and without an inverse trigonometric function.  Returns false when the pixel
+// must take the exact path.
+//   phi > T  <=>  sin(phi - T) > 0  <=>  crs * cos T - dot * sin T > 0      (phi, T in [0, 180) degrees)
+// with dot = f . d and crs = |f x d| (so that |f||d| sin(phi - T) is the tested quantity).  Error budget, relative
+// to |f||d|: inputs rounded once to float32 (6e-8 each), dot / crs with FMAs (< 4e-7), __sincosf (< 5e-7), the
+// dynamic threshold through rsqrtf (2 ulp) -> under 3e-6 in total.  A pixel is decided here only when
+// |sin(phi - T)| > 3.6e-5 (2e-3 degrees, plus 1e-5 relative on the dynamic threshold) and the squared magnitude is
+// further than 1e-5 relative from both magnitude gates; everything else, and any non-finite, huge or degenerate
+// input, takes the float64 path.  The reference's own evaluation (float64 arccos) is within 1e-12 of the exact angle
+// at every threshold in range, so both sides agree on all pixels decided here.
 struct FastPrm {
-    float dyn_offset, dyn_base, dyn_gain, dyn_min_mag, fixed_min_mag, fixed_angle;
+    float dyn_c0;                     // dyn_offset + dyn_base, degrees
+    float dyn_gain;                   // degrees x pixels
+    float dyn_mm2, fix_mm2;           // squared magnitude gates
+    float dyn_mm2_guard, fix_mm2_guard;
+    float fix_cos, fix_sin;           // of the fixed angle threshold
 };
 
 __device__ __forceinline__ bool pixel_fast(float fx, float fy, float dx, float dy, const FastPrm& p, bool& m_total,
                                            bool& m_fixed) {
-    const float a2 = fx * fx + fy * fy;
-    if (!(a2 < 1e30f)) return false;                       // NaN / inf / huge: exact path
-    const float a = sqrtf(a2);
-    const float gd = fabsf(a - p.dyn_min_mag), gf = fabsf(a - p.fixed_min_mag);
-    if (gd <= 1e-5f * fmaxf(1.f, p.dyn_min_mag) || gf <= 1e-5f * fmaxf(1.f, p.fixed_min_mag)) return false;
-    const bool gt_dyn = a > p.dyn_min_mag, gt_fix = a > p.fixed_min_mag;
-    m_total = m_fixed = false;
-    if (!gt_dyn && !gt_fix) return true;
-    const float b2 = dx * dx + dy * dy;
-    if (!(b2 < 1e30f) || a2 * b2 < 1e-8f) return false;    // |f||d| near the 1e-6 clamp of the norm: exact path
-    const float dot = fx * dx + fy * dy;
-    const float crs = fabsf(fx * dy - fy * dx);
-    const float phi = atan2f(crs, dot) * 57.29577951308232f;
-    if (gt_fix) {
-        if (fabsf(phi - p.fixed_angle) <= 2e-3f) return false;
-        m_fixed = phi > p.fixed_angle;
-    }
-    if (gt_dyn) {
-        const float thr = p.dyn_offset + (p.dyn_base + __fdividef(p.dyn_gain, a));   // 2 ulp: far inside the guard band
-        if (fabsf(phi - thr) <= 2e-3f + 1e-5f * thr) return false;
-        m_total = phi > thr;      // amin is impossible: the host enables FAST only when offset - base < 0
-    }
-    return true;
+    const float a2 = fmaf(fx, fx, fy * fy), b2 = fmaf(dx, dx, dy * dy);
+    const float ab2 = a2 * b2;
+    const bool gt_dyn = a2 > p.dyn_mm2, gt_fix = a2 > p.fix_mm2;
+    bool undecided = !(a2 < 1e15f) | !(b2 < 1e15f);                         // NaN / inf / huge
+    undecided |= (fabsf(a2 - p.dyn_mm2) <= p.dyn_mm2_guard) | (fabsf(a2 - p.fix_mm2) <= p.fix_mm2_guard);
+    const float dot = fmaf(fx, dx, fy * dy), crs = fabsf(fmaf(fx, dy, -(fy * dx)));
+    const float sf = crs * p.fix_cos - dot * p.fix_sin;
+    const float thr = fmaf(p.dyn_gain, rsqrtf(a2), p.dyn_c0);               // degrees; inf when a2 == 0 (then !gt_dyn)
+    const float tr = thr * 0.017453292519943295f;
+    float sn, cs;
+    __sincosf(tr, &sn, &cs);
+    const float sd = crs * cs - dot * sn;
+    const float mf = 3.6e-5f, md = 3.6e-5f + 1e-5f * tr;
+    undecided |= (gt_dyn | gt_fix) & (ab2 < 1e-8f);                         // |f||d| near the 1e-6 clamp of the norm
+    undecided |= gt_fix & (sf * sf <= (mf * mf) * ab2);
+    undecided |= gt_dyn & ((sd * sd <= (md * md) * ab2) | !(thr < 170.f));
+    m_fixed = gt_fix & (sf > 0.f);
+    m_total = gt_dyn & (sd > 0.f);      // amin is impossible: the host enables FAST only when offset - base < 0
+    return !undecided;
 }
 
 constexpr int RES_ITEMS = 4;     // pixel groups per thread
@@ -747,8 +752,8 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
     // FAST needs: phi not requested, and the parameter ranges its guard bands were derived for
     const bool fast = !H->force_exact_residual && d_phi == nullptr && p.fixed_angle >= 0.0 && p.dyn_gain >= 0.0 &&
                       p.dyn_offset - p.dyn_base < -1e-2 && p.dyn_min_mag >= 0.0 && p.fixed_min_mag >= 0.0 &&
-                      p.fixed_angle < 1e3 && p.dyn_offset + p.dyn_base < 1e3 && p.dyn_gain < 1e6 &&
-                      p.dyn_min_mag < 1e6 && p.fixed_min_mag < 1e6;
+                      p.fixed_angle <= 170.0 && p.dyn_offset + p.dyn_base < 160.0 && p.dyn_gain < 1e6 &&
+                      p.dyn_min_mag < 1e3 && p.fixed_min_mag < 1e3;
     if (d_stats) {
         stats_init_kernel<<<ceil_div(n, 128), 128, 0, s>>>((char*)d_stats, stats_stride, n, d_seg ? seg_max : nullptr);
         MAVD_LAUNCHED();
@@ -764,8 +769,11 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
     A.sky = d_sky; A.sky_stride = sky_stride; A.seg = d_seg; A.seg_stride = seg_stride; A.seg_max = seg_max;
     A.phi_out = d_phi; A.total_out = d_total; A.fixed_out = d_fixed;
     A.stats_base = (char*)d_stats; A.stats_stride = stats_stride;
-    const FastPrm fp{(float)p.dyn_offset, (float)p.dyn_base, (float)p.dyn_gain, (float)p.dyn_min_mag,
-                     (float)p.fixed_min_mag, (float)p.fixed_angle};
+    auto gate_guard = [](double t) { const double g = 1e-5 * (t > 1.0 ? t : 1.0); return (float)(2.0 * t * g + g * g); };
+    const double fixed_rad = p.fixed_angle * (3.14159265358979323846 / 180.0);
+    const FastPrm fp{(float)(p.dyn_offset + p.dyn_base), (float)p.dyn_gain,
+                     (float)(p.dyn_min_mag * p.dyn_min_mag), (float)(p.fixed_min_mag * p.fixed_min_mag),
+                     gate_guard(p.dyn_min_mag), gate_guard(p.fixed_min_mag), (float)cos(fixed_rad), (float)sin(fixed_rad)};
     auto al = [](const void* q, uintptr_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
     const bool vec4 = (w % 4 == 0) && al(d_flow, 16) && al(d_sky, 4) && al(d_seg, 4) && al(d_total, 4) && al(d_fixed, 4) &&
                       (sky_stride % 4 == 0) && (seg_stride % 4 == 0);

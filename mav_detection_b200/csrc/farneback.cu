@@ -375,16 +375,13 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
                                                            const float* __restrict__ fya, float up_scale,
                                                            float* __restrict__ M, float2* __restrict__ flow_dbg,
                                                            int flow_dbg_pitch, size_t flow_dbg_stride, int n_pairs,
-                                                           int tiles_x, int group) {
-    // 1-D grid, pairs interleaved in groups (same L2 sharing of R between consecutive pairs as in iter_box_tma_kernel)
-    const int n_tiles = gridDim.x / n_pairs;
-    const int per_group = group * n_tiles;
-    const int gidx = blockIdx.x / per_group, rem = blockIdx.x - gidx * per_group;
-    const int gsize = min(group, n_pairs - gidx * group);
-    const int tile = rem / gsize;
-    const int p = gidx * group + (rem - tile * gsize);
-    const int x = (tile % tiles_x) * 64 + (threadIdx.x & 63);
-    const int y = (tile / tiles_x) * 4 + (threadIdx.x >> 6);
+                                                           int tiles_x) {
+    // 1-D grid, pair index fastest (same L2 sharing of R between consecutive pairs as in iter_box_tma_kernel; one
+    // pixel per thread, so the index arithmetic is kept to two divisions: grouping the pairs costs more than it saves)
+    const int p = blockIdx.x % n_pairs, tile = blockIdx.x / n_pairs;
+    const int ty = tile / tiles_x;
+    const int x = (tile - ty * tiles_x) * 64 + (threadIdx.x & 63);
+    const int y = ty * 4 + (threadIdx.x >> 6);
     if (x >= w || y >= h) return;
     float dx = 0.f, dy = 0.f;
     if (cflow) {
@@ -954,7 +951,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             matrices_init_kernel<<<dim3(g.x * g.y * g.z), 256, 0, st>>>(
                 L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,
                 top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,
-                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0, n_pairs, (int)g.x, pair_group);
+                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0, n_pairs, (int)g.x);
             MAVD_LAUNCHED();
         }
         int cur = 0;
