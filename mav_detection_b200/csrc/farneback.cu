@@ -155,12 +155,13 @@ __global__ void pyr0_kernel(const uint8_t* __restrict__ frame, int W, int H, flo
 constexpr int PE_TX = 64, PE_TY = 32, PE_H = 8, PE_RW = PE_TX + 2 * PE_H;  // 80
 
 __device__ __forceinline__ void blur3_row4(const uint8_t* __restrict__ p, float (&hv)[4]) {
-    // p is 4-byte aligned and points 4 bytes left of the first of four output cells
+    // p is 4-byte aligned and points 4 bytes left of the first of four output cells.  Bytes -> floats with the
+    // mantissa trick (byte_to_float: permute + exact subtract, full-rate pipes) instead of I2F on the XU pipe.
     const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(p));
     const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(p) + 1);
     const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(p) + 2);
-    const float v3 = (float)(a >> 24), v4 = (float)(b & 255u), v5 = (float)((b >> 8) & 255u),
-                v6 = (float)((b >> 16) & 255u), v7 = (float)(b >> 24), v8 = (float)(c & 255u);
+    const float v3 = byte_to_float(a, 0x7543u), v4 = byte_to_float(b, 0x7540u), v5 = byte_to_float(b, 0x7541u),
+                v6 = byte_to_float(b, 0x7542u), v7 = byte_to_float(b, 0x7543u), v8 = byte_to_float(c, 0x7540u);
     hv[0] = 0.25f * v3 + 0.5f * v4 + 0.25f * v5;
     hv[1] = 0.25f * v4 + 0.5f * v5 + 0.25f * v6;
     hv[2] = 0.25f * v5 + 0.5f * v6 + 0.25f * v7;
@@ -365,6 +366,18 @@ __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, i
 
 // Level entry: flow_l = resize(flow_{l+1}) * (1/pyr_scale) (zeros on the coarsest level), then
 // UpdateMatrices.  The upsampled flow itself is never stored: BlurBox rebuilds the flow from M alone.
+// cv::resize(INTER_LINEAR) source index / weight of destination index d (api.cu: resize_tables), evaluated with the
+// same double operations, one rounding each, so the values equal the host-built tables bit for bit
+__device__ __forceinline__ void resize_coord(int d, double scale, int src, int& i0, float& a) {
+    const float f = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+    int s = (int)floorf(f);
+    a = f - (float)s;
+    if (s < 0) { s = 0; a = 0.f; }
+    if (s >= src - 1) { s = src - 1; a = 0.f; }
+    i0 = s;
+}
+
+template <bool TABLES>
 __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
                                                            int pitch, int pair_stride,
                                                            const float2* __restrict__ cflow, int cw, int ch,
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
                                                            const float* __restrict__ fya, float up_scale,
                                                            float* __restrict__ M, float2* __restrict__ flow_dbg,
                                                            int flow_dbg_pitch, size_t flow_dbg_stride, int n_pairs,
-                                                           int tiles_x) {
+                                                           int tiles_x, double xscale, double yscale) {
     // 1-D grid, pair index fastest (same L2 sharing of R between consecutive pairs as in iter_box_tma_kernel; one
     // pixel per thread, so the index arithmetic is kept to two divisions: grouping the pairs costs more than it saves)
     const int p = blockIdx.x % n_pairs, tile = blockIdx.x / n_pairs;
@@ -386,9 +399,16 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
     float dx = 0.f, dy = 0.f;
     if (cflow) {
         const float2* cf = cflow + (size_t)p * cflow_stride;
-        const int xa0 = fxi0[x], ya0 = fyi0[y];
+        int xa0, ya0;
+        float ax, ay;
+        if (TABLES) {
+            xa0 = fxi0[x]; ya0 = fyi0[y]; ax = fxa[x]; ay = fya[y];
+        } else {
+            // one dependent memory round trip less than reading the tables
+            resize_coord(x, xscale, cw, xa0, ax);
+            resize_coord(y, yscale, ch, ya0, ay);
+        }
         const int xa1 = min(xa0 + 1, cw - 1), ya1 = min(ya0 + 1, ch - 1);
-        const float ax = fxa[x], ay = fya[y];
         const float2 f00 = cf[(size_t)ya0 * cpitch + xa0], f01 = cf[(size_t)ya0 * cpitch + xa1];
         const float2 f10 = cf[(size_t)ya1 * cpitch + xa0], f11 = cf[(size_t)ya1 * cpitch + xa1];
         const float tx0 = f00.x * (1.f - ax) + f01.x * ax, tx1 = f10.x * (1.f - ax) + f11.x * ax;
@@ -398,8 +418,10 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
     }
     if (flow_dbg) flow_dbg[(size_t)p * flow_dbg_stride + (size_t)y * flow_dbg_pitch + x] = make_float2(dx, dy);
     const float* R0 = R + (size_t)(p * pair_stride) * 5 * plane;
-    // (the 32-bit-offset variant used by the fused iteration needs > 32 registers here and loses more to occupancy
-    // than it gains in instructions: 0.87 vs 0.675 ms per 16-pair step, profiles/README.md)
+    // One pixel per thread at 32 registers (full occupancy) is the fastest form measured: the 32-bit-offset
+    // UpdateMatrices of the fused iteration (> 32 registers: 0.87 vs 0.675 ms per 16-pair step) and variants with
+    // 8 pixels per thread that halve the instruction count (2.45-2.67 vs 2.22 ms per 64-pair step) all lose more to
+    // occupancy than they save: the kernel is bound by the latency of its three dependent memory round trips.
     update_matrices_px(x, y, w, h, pitch, plane, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
 }
 
@@ -948,10 +970,14 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             dim3 g(ceil_div(L.w, 64), ceil_div(L.h, 4), n_pairs);
             const bool top = (li == H->n_levels - 1);
             const Level* C = top ? nullptr : &H->lv[li + 1];
-            matrices_init_kernel<<<dim3(g.x * g.y * g.z), 256, 0, st>>>(
-                L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,
-                top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,
-                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0, n_pairs, (int)g.x);
+            static const bool tables = getenv("MAVD_MAT_TABLES") && getenv("MAVD_MAT_TABLES")[0] == '1';
+            const double xscale = top ? 1.0 : 1.0 / ((double)L.w / C->w), yscale = top ? 1.0 : 1.0 / ((double)L.h / C->h);
+#define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,                    \
+                top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,          \
+                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0, n_pairs, (int)g.x, xscale, yscale
+            if (tables) matrices_init_kernel<true><<<dim3(g.x * g.y * g.z), 256, 0, st>>>(MI_ARGS);
+            else matrices_init_kernel<false><<<dim3(g.x * g.y * g.z), 256, 0, st>>>(MI_ARGS);
+#undef MI_ARGS
             MAVD_LAUNCHED();
         }
         int cur = 0;

@@ -32,7 +32,7 @@ echo "ncu all rc=$?"
 ncu -i $OUT/prof_all_$TAG.ncu-rep --page raw --csv > $OUT/prof_all_$TAG.csv 2>/dev/null
 rm -f $OUT/prof_all_$TAG.ncu-rep
 # source-level capture of the heaviest kernels (one launch each, after the warm-up steps): <name regex>:<launches to skip>
-for KS in ${PROFILE_KERNELS:-iter_box_tma_kernel.*7,.*0:70 matrices_init:23 pyr_hpass:3 polyexp:23 residual_kernel:4}; do
+for KS in ${PROFILE_KERNELS:-iter_box_tma:69 matrices_init:23 pyr_vfirst:3 polyexp:22 residual_kernel:4}; do
   K=${KS%%:*}; S=${KS##*:}
   N=$(echo $K | tr -cd 'a-z_')
   ncu --set full --clock-control none --import-source on -k "regex:$K" -s $S -c 1 -o $OUT/prof_${N}_$TAG -f $BENCH > $OUT/ncu_${N}_$TAG.log 2>&1
