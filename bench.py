@@ -339,7 +339,8 @@ def run_b200(args):
             traffic = None
             try:
                 with open(os.path.join(ROOT, 'profiles', 'iter_kernel_traffic.json')) as f:
-                    traffic = json.load(f).get(args.workload)
+                    per_pair = json.load(f).get(args.workload + '_per_pair')
+                traffic = per_pair * B if per_pair else None      # bytes per launch, like `achieved`
             except Exception:
                 pass
             roof = {'bound': 'hbm', 'kernel': 'iter_kernel<box,not-last> finest level', 'achieved': achieved,

@@ -79,11 +79,28 @@ __global__ void __launch_bounds__(256) pyr_vfirst_kernel(const uint8_t* __restri
     const int taps = L.taps;
     const bool inside = base >= 0 && base + taps <= H;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (word_ok && x + 4 <= W) {
-#pragma unroll 4
+    if (word_ok && x + 4 <= W && inside) {
+        // interior: walk down the rows with a pointer, four taps (one float4 of weights) per step
+        const uint8_t* q = src + (size_t)base * W;
+        for (int j = 0; j < taps; j += 4) {          // taps is a multiple of 4 (zero padded)
+            const float4 t = __ldg(reinterpret_cast<const float4*>(tab + j));
+            const uint32_t v0 = __ldg(reinterpret_cast<const uint32_t*>(q));
+            const uint32_t v1 = __ldg(reinterpret_cast<const uint32_t*>(q + W));
+            const uint32_t v2 = __ldg(reinterpret_cast<const uint32_t*>(q + 2 * (size_t)W));
+            const uint32_t v3 = __ldg(reinterpret_cast<const uint32_t*>(q + 3 * (size_t)W));
+            q += 4 * (size_t)W;
+            a0 += t.x * byte_to_float(v0, 0x7540u); a1 += t.x * byte_to_float(v0, 0x7541u);
+            a2 += t.x * byte_to_float(v0, 0x7542u); a3 += t.x * byte_to_float(v0, 0x7543u);
+            a0 += t.y * byte_to_float(v1, 0x7540u); a1 += t.y * byte_to_float(v1, 0x7541u);
+            a2 += t.y * byte_to_float(v1, 0x7542u); a3 += t.y * byte_to_float(v1, 0x7543u);
+            a0 += t.z * byte_to_float(v2, 0x7540u); a1 += t.z * byte_to_float(v2, 0x7541u);
+            a2 += t.z * byte_to_float(v2, 0x7542u); a3 += t.z * byte_to_float(v2, 0x7543u);
+            a0 += t.w * byte_to_float(v3, 0x7540u); a1 += t.w * byte_to_float(v3, 0x7541u);
+            a2 += t.w * byte_to_float(v3, 0x7542u); a3 += t.w * byte_to_float(v3, 0x7543u);
+        }
+    } else if (word_ok && x + 4 <= W) {
         for (int j = 0; j < taps; ++j) {
-            const int row = inside ? base + j : reflect101(base + j, H);
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)row * W));
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)reflect101(base + j, H) * W));
             const float t = __ldg(tab + j);
             a0 += t * byte_to_float(v, 0x7540u);
             a1 += t * byte_to_float(v, 0x7541u);
