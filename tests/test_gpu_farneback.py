@@ -153,6 +153,43 @@ def test_1080p_properties():
     eng.close()
 
 
+def test_4k_seven_level_config_matches_cv2():
+    """BASELINE config 4 shape: 3840x2160, levels=7 (7 pyramid images), winsize 15, 10 iterations — one pair against
+    cv2 on the host (about 8 s of CPU)."""
+    cv2 = pytest.importorskip('cv2')
+    import torch
+    from mav_detection_b200 import engine, synth
+    p = dict(pyr_scale=0.5, levels=7, winsize=15, iterations=10, poly_n=5, poly_sigma=1.2, flags=0)
+    s = synth.make_sequence(3840, 2160, 2, seq=1)
+    eng = engine.Engine(3840, 2160, p, max_pairs=1)
+    assert len(eng.levels) == 7 and eng.levels[-1] == (60, 34)
+    flow = eng.farneback(torch.from_numpy(s.frames).cuda()).cpu().numpy()[0]
+    ref = cv2.calcOpticalFlowFarneback(s.frames[0], s.frames[1], None, 0.5, 7, 15, 10, 5, 1.2, 0)
+    epe = np.linalg.norm(flow - ref, axis=-1)
+    assert np.isfinite(flow).all() and epe.mean() < EPE_MEAN_TOL, (epe.mean(), epe.max())
+    eng.close()
+
+
+def test_64_pairs_per_launch_640x480():
+    """BASELINE config 3 shape: 64 MIDGARD-sized pairs in ONE call; every pair equals the same pair run alone
+    (bit for bit) and three of them are checked against cv2."""
+    cv2 = pytest.importorskip('cv2')
+    import torch
+    from mav_detection_b200 import engine, synth
+    s = synth.make_sequence(640, 480, 65, seq=7)
+    eng = engine.Engine(640, 480, engine.SAMPLE_PARAMS, max_pairs=64)
+    assert len(eng.levels) == 4                                   # levels=5 is capped at 3 by the 32-pixel rule
+    frames = torch.from_numpy(s.frames).cuda()
+    flow = eng.farneback(frames).cpu().numpy()
+    assert flow.shape == (64, 480, 640, 2) and np.isfinite(flow).all()
+    for i in (0, 31, 63):
+        alone = eng.farneback(frames[i:i + 2].contiguous()).cpu().numpy()[0]
+        assert np.array_equal(alone, flow[i]), i
+        ref = cv2.calcOpticalFlowFarneback(s.frames[i], s.frames[i + 1], None, 0.5, 5, 15, 3, 5, 1.2, 0)
+        assert np.linalg.norm(flow[i] - ref, axis=-1).mean() < EPE_MEAN_TOL
+    eng.close()
+
+
 def test_errors_map_to_python_exceptions():
     import torch
     from mav_detection_b200 import engine
