@@ -242,6 +242,13 @@ int mavd_submit_host(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32
                      const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
                      float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream);
 int mavd_wait_host(mavd_handle h, int32_t slot);
+/* The same with (H, W, 3) uint8 BGR frames as cv2.VideoCapture.read() / Dataset.get_frame() deliver them
+ * (src/farneback.py:73, src/datasets/dataset.py:223-230): the frames are copied as they are and converted to gray on
+ * the device on the copy-in stream (mavd_bgr2gray == cv2.cvtColor(COLOR_BGR2GRAY), src/farneback.py:74). */
+int mavd_submit_host_bgr(mavd_handle h, int32_t slot, const uint8_t* h_bgr_frames, int32_t n_pairs, int32_t pair_stride,
+                         const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
+                         const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
+                         float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream);
 
 /* Detection from a HOST flow field (n x H x W x 2 float32), the Dataset.get_flow_uv seam end to end. */
 int mavd_detect_host(mavd_handle h, const float* h_flow, int32_t n, const mavd_imu* h_imu,

@@ -88,6 +88,8 @@ SIGNATURES = {
                               _P, _P, _P, _P]),
     'mavd_submit_host': (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
                                    _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
+    'mavd_submit_host_bgr': (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
+                                       _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P]),
     'mavd_wait_host': (C.c_int, [_P, C.c_int32]),
     'mavd_detect_host': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P, _P, C.c_int64, _P,
                                    C.c_int64, _P, _P, _P]),

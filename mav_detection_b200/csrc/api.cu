@@ -699,10 +699,11 @@ static int ensure_slot(mavd_handle h, int slot, bool want_flow_out, bool want_fl
     return MAVD_OK;
 }
 
-int mavd_submit_host(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32_t n_pairs, int32_t pair_stride,
-                     const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
-                     const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
-                     float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+static int submit_host_impl(mavd_handle h, int32_t slot, const uint8_t* h_frames, int bgr, int32_t n_pairs,
+                            int32_t pair_stride, const mavd_imu* h_imu, const mavd_detect_params* prm,
+                            const int32_t* h_samples, const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg,
+                            int64_t seg_stride, float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records,
+                            void* stream) {
     TRY(check_batch(h, n_pairs, "submit_host"));
     MAVD_REQUIRE(slot >= 0 && slot < MAVD_HOST_SLOTS, MAVD_ERR_INVALID, "slot %d out of range", slot);
     MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
@@ -716,8 +717,18 @@ int mavd_submit_host(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32
     MAVD_REQUIRE(!S.busy, MAVD_ERR_INVALID, "slot %d is still in flight: call mavd_wait_host first", slot);
     cudaStream_t s = (cudaStream_t)stream;
     const int n_frames = pair_stride == 1 ? n_pairs + 1 : 2 * n_pairs;
-    // copy-in stream
-    MAVD_CUDA(cudaMemcpyAsync(S.d_frames, h_frames, npx * n_frames, cudaMemcpyHostToDevice, h->s_in));
+    if (bgr && !S.d_bgr) {
+        mavd_handle_full* H = static_cast<mavd_handle_full*>(h);
+        TRY(H->arena.alloc(&S.d_bgr, (size_t)h->max_frames * npx * 3));
+        H->bytes = H->arena.bytes;
+    }
+    // copy-in stream (BGR frames are converted to gray there too, so the compute stream sees gray frames only)
+    if (bgr) {
+        MAVD_CUDA(cudaMemcpyAsync(S.d_bgr, h_frames, 3 * npx * n_frames, cudaMemcpyHostToDevice, h->s_in));
+        TRY(bgr2gray_run(S.d_bgr, S.d_frames, (int64_t)npx * n_frames, h->s_in));
+    } else {
+        MAVD_CUDA(cudaMemcpyAsync(S.d_frames, h_frames, npx * n_frames, cudaMemcpyHostToDevice, h->s_in));
+    }
     MAVD_CUDA(cudaMemcpyAsync(S.d_samples, h_samples, sizeof(int32_t) * MAVD_SAMPLES_PER_FRAME * n_pairs,
                               cudaMemcpyHostToDevice, h->s_in));
     if (h_sky) MAVD_CUDA(cudaMemcpyAsync(S.d_sky, h_sky, sky_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, h->s_in));
@@ -739,6 +750,22 @@ int mavd_submit_host(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32
     // the next batch's copy-in must not overwrite staging a kernel still reads: ordered by slot reuse rule
     S.busy = true;
     return MAVD_OK;
+}
+
+int mavd_submit_host(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32_t n_pairs, int32_t pair_stride,
+                     const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
+                     const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
+                     float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+    return submit_host_impl(h, slot, h_frames, 0, n_pairs, pair_stride, h_imu, prm, h_samples, h_sky, sky_stride, h_seg,
+                            seg_stride, h_flow_out, h_fixed_out, h_records, stream);
+}
+
+int mavd_submit_host_bgr(mavd_handle h, int32_t slot, const uint8_t* h_bgr_frames, int32_t n_pairs, int32_t pair_stride,
+                         const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
+                         const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
+                         float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+    return submit_host_impl(h, slot, h_bgr_frames, 1, n_pairs, pair_stride, h_imu, prm, h_samples, h_sky, sky_stride,
+                            h_seg, seg_stride, h_flow_out, h_fixed_out, h_records, stream);
 }
 
 int mavd_wait_host(mavd_handle h, int32_t slot) {

@@ -290,8 +290,10 @@ class Engine:
             raise ValueError('samples must be int32')
         need = n_pairs + 1 if pair_stride == 1 else 2 * n_pairs
         if frames is not None and (frames.dtype != np.uint8 or frames.shape[0] < need or
-                                   tuple(frames.shape[1:]) != (self.height, self.width)):
-            raise ValueError('frames must be uint8 (>=%d, %d, %d)' % (need, self.height, self.width))
+                                   tuple(frames.shape[1:]) not in ((self.height, self.width),
+                                                                   (self.height, self.width, 3))):
+            raise ValueError('frames must be uint8 (>=%d, %d, %d) gray or (>=%d, %d, %d, 3) BGR'
+                             % (need, self.height, self.width, need, self.height, self.width))
         sky_stride = 0 if (sky is None or sky.ndim == 2) else npx
         seg_stride = 0 if (seg is None or seg.ndim == 2) else npx
         return n_pairs, records, sky_stride, seg_stride
@@ -300,7 +302,14 @@ class Engine:
                      pair_stride: int = 1, sky: Optional[np.ndarray] = None, seg: Optional[np.ndarray] = None,
                      flow_out: Optional[np.ndarray] = None, fixed_out: Optional[np.ndarray] = None,
                      records: Optional[np.ndarray] = None) -> np.ndarray:
-        """The end-to-end call: HOST buffers in, HOST records (and optional masks / flow) out."""
+        """The end-to-end call: HOST buffers in, HOST records (and optional masks / flow) out.  Frames may be gray
+        (F, H, W) or BGR (F, H, W, 3)."""
+        if frames.ndim == 4:
+            self.wait_host(0)
+            records = self.submit_host(0, frames, imu, samples, n_pairs, pair_stride, sky, seg, flow_out, fixed_out,
+                                       records)
+            self.wait_host(0)
+            return records
         n_pairs, records, sky_stride, seg_stride = self._host_args(frames, samples, n_pairs, pair_stride, sky, seg,
                                                                    flow_out, fixed_out, records)
         with torch.cuda.device(self.device):
@@ -318,11 +327,12 @@ class Engine:
         up to _lib.HOST_SLOTS batches in flight overlaps the host<->device copies with the compute."""
         n_pairs, records, sky_stride, seg_stride = self._host_args(frames, samples, n_pairs, pair_stride, sky, seg,
                                                                    flow_out, fixed_out, records)
+        submit = self.lib.mavd_submit_host_bgr if frames.ndim == 4 else self.lib.mavd_submit_host
         with torch.cuda.device(self.device):
-            check(self.lib.mavd_submit_host(self._h, slot, _hp(frames), n_pairs, pair_stride, imu,
-                                            C.byref(self.detect_params), _hp(samples), _hp(sky), sky_stride,
-                                            _hp(seg), seg_stride, _hp(flow_out), _hp(fixed_out),
-                                            records.ctypes.data, self._stream()))
+            check(submit(self._h, slot, _hp(frames), n_pairs, pair_stride, imu,
+                         C.byref(self.detect_params), _hp(samples), _hp(sky), sky_stride,
+                         _hp(seg), seg_stride, _hp(flow_out), _hp(fixed_out),
+                         records.ctypes.data, self._stream()))
         # keep the host buffers alive until the wait
         self._inflight[slot] = (frames, imu, samples, sky, seg, flow_out, fixed_out, records)
         return records

@@ -34,8 +34,8 @@ def _ratio(a: int, b: int) -> float:
 
 
 def to_gray(frame: np.ndarray) -> np.ndarray:
-    """(H, W, 3) BGR or (H, W) gray uint8 -> gray uint8 on the host side of the boundary is NOT done here:
-    BGR frames are converted on the device (mavd_bgr2gray); this only validates the shape."""
+    """Validates a frame: (H, W) gray or (H, W, 3) BGR uint8.  No conversion happens on the host: BGR frames are
+    converted on the device (mavd_bgr2gray)."""
     if frame.ndim == 2 or (frame.ndim == 3 and frame.shape[2] == 3):
         return frame
     raise ValueError('frames must be (H, W) gray or (H, W, 3) BGR uint8')
@@ -86,18 +86,13 @@ class Processor:
             f.write(json.dumps(utils.get_json(self.config.results[frame_index]), indent=4, sort_keys=True))
 
     # ------------------------------------------------------------------------------------------------
-    def _gray_frame(self, frame: np.ndarray) -> np.ndarray:
-        frame = to_gray(np.ascontiguousarray(frame))
-        if frame.ndim == 2:
-            return frame
-        import torch
-        return self.engine.bgr2gray(torch.from_numpy(frame).to(self.engine.device)).cpu().numpy()
-
     def _next_frame(self) -> np.ndarray:
+        """The next frame as the dataset delivers it: (H, W) gray or (H, W, 3) BGR.  BGR frames travel to the device
+        unchanged and are converted there (mavd_submit_host_bgr), as cv2.cvtColor does at farneback.py:74."""
         frame = self.dataset.get_frame()
         if frame is None:
             raise ValueError('Could not load frame.')
-        return self._gray_frame(frame)
+        return to_gray(np.ascontiguousarray(frame))
 
     def _host_inputs(self, indices: List[int]):
         """Per-frame host inputs in frame order: IMU, FoE sample indices, sky and segmentation masks."""
@@ -203,8 +198,9 @@ class Processor:
                 finish((-1, indices, records, sky))
             else:
                 # flow(i) = Farneback(frame i, frame i+1); consecutive batches share one frame
-                frames = np.empty((len(indices) + 1, height, width), np.uint8)
-                frames[0] = self._pending_frame if self._pending_frame is not None else self._next_frame()
+                first_frame = self._pending_frame if self._pending_frame is not None else self._next_frame()
+                frames = np.empty((len(indices) + 1,) + first_frame.shape, np.uint8)     # gray or BGR, as delivered
+                frames[0] = first_frame
                 for k in range(len(indices)):
                     frames[k + 1] = self._next_frame()
                 self._pending_frame = frames[-1].copy()

@@ -94,7 +94,7 @@ def test_ransac_method_edge_cases():
     assert foe_obj.ransac(E) == dn.ransac(E)
 
 
-@pytest.mark.parametrize('flow_source', ['dataset', 'farneback'])
+@pytest.mark.parametrize('flow_source', ['dataset', 'farneback', 'farneback-bgr'])
 def test_processor_run_detection_matches_oracle_chain(tmp_path, flow_source):
     """Processor.run_detection over a synthetic sequence: FrameResult per frame == the oracle chained over the same
     frames with the same global random stream; JSON files carry the keys Validator.load_results reads."""
@@ -112,7 +112,9 @@ def test_processor_run_detection_matches_oracle_chain(tmp_path, flow_source):
     cvflow = np.stack([cv2.calcOpticalFlowFarneback(seq.frames[i], seq.frames[i + 1], None, p['pyr_scale'], p['levels'],
                                                     p['winsize'], p['iterations'], p['poly_n'], p['poly_sigma'], p['flags'])
                        for i in range(F - 1)])
-    ds = synth.SyntheticDataset(seq, flows=cvflow, results_path=str(tmp_path / 'results'))
+    bgr = flow_source.endswith('-bgr')       # frames delivered as (H, W, 3) BGR, converted to gray on the device
+    flow_source = flow_source.split('-')[0]
+    ds = synth.SyntheticDataset(seq, flows=cvflow, results_path=str(tmp_path / 'results'), bgr=bgr)
     RunConfig.register_dataset(RunConfig.DatasetType.SIMULATION, lambda logger, sequence: ds)
     cfg = RunConfig(logging.getLogger('test'), 'simulation', 'synthetic', False, False, False, True, False, False,
                     'FLOW_FOE_CLUSTERING')
