@@ -326,7 +326,8 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
         if (m >= 5 && m <= 8)
             L.has_tmap = make_plane_tensor_map(&L.tmapM[0], L.M[0], L.pitch, L.h, B * 5, L.plane, 32 + 2 * m, 5) &&
                          make_plane_tensor_map(&L.tmapM[1], L.M[1], L.pitch, L.h, B * 5, L.plane, 32 + 2 * m, 5) &&
-                         make_plane_tensor_map(&L.tmapR, L.R, L.pitch, L.h, F * 5, L.plane, 48, 10);
+                         make_plane_tensor_map(&L.tmapR, L.R, L.pitch, L.h, F * 5, L.plane, 48, 10) &&
+                         make_plane_tensor_map(&L.tmapRbox, L.R, L.pitch, L.h, F * 5, L.plane, 32 + 2 * m, 5);
     }
     for (int li = 0; li + 1 < H->n_levels; ++li) {
         Level& L = H->lv[li];

@@ -75,6 +75,7 @@ struct Level {
     int last_m = 0;         // which M buffer holds the last update (for taps)
     CUtensorMap tmapM[2];   // TMA descriptors of M[0] / M[1]: dims {pitch, h, pairs*5}, box {80, 32+2m, 5}
     CUtensorMap tmapR;      // TMA descriptor of R: dims {pitch, h, frames*5}, box {80, 48, 10} (L2 prefetch only)
+    CUtensorMap tmapRbox;   // TMA descriptor of R with the M box geometry {80, 32+2m, 5}: R1 staged in shared memory
     bool has_tmap = false;
 };
 

@@ -730,9 +730,10 @@ __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h,
     Mout[o + 4 * plane] = r6 * r2 + r5 * r3;
 }
 
-template <int M_, bool LAST, int NT>
+template <int M_, bool LAST, int NT, bool R1S>
 __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                              const __grid_constant__ CUtensorMap tmapR,
+                                                                             const __grid_constant__ CUtensorMap tmapRbox,
                                                                              IterArgs a) {
     constexpr int RW = IT_TX + 16;          // 80 staged columns (halo 8 each side, 16-byte aligned)
     constexpr int RH = IT_TY + 2 * M_;      // staged rows
@@ -841,6 +842,106 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
     float2* fl = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
     const bool edge = (x0 < 5) || (y0 < 5) || (x0 + IT_TX > w - 5) || (y0 + IT_TY > h - 5);
     const float scale = a.scale;
+    if (R1S && !LAST) {
+        // ---- R1 through shared memory ----
+        // (a) every thread turns the sums of its pixels into flow vectors (registers) and the box is free again;
+        // (b) ONE TMA load brings the 5 planes of R1 around the tile, displaced by the flow of the tile centre,
+        //     into the box; (c) the bilinear gather reads shared memory with immediate offsets (one base address per
+        //     pixel, ~30-cycle latency) instead of 20 global loads.  Pixels whose footprint leaves the box (flow
+        //     differs from the centre's by more than ~5 px) take the global path; values are identical either way.
+        constexpr int PPT = (IT_TX * IT_TY) / NT;
+        __shared__ int s_org[2];
+        float ffx[PPT], ffy[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const int idx = j * NT + tid;
+            const int cx = idx & 63, r = idx >> 6;
+            const float* sp = box + r * RW + 8 + cx;
+            const float g11 = sp[0] * scale, g12 = sp[CH] * scale, g22 = sp[2 * CH] * scale, h1 = sp[3 * CH] * scale,
+                        h2 = sp[4 * CH] * scale;
+            const float idet = __frcp_rn(g11 * g22 - g12 * g12 + 1e-3f);
+            ffx[j] = (g11 * h2 - g12 * h1) * idet;
+            ffy[j] = (g22 * h1 - g12 * h2) * idet;
+            if (cx == IT_TX / 2 && r == IT_TY / 2) {
+                // box origin: tile origin displaced by the centre pixel's flow, x a multiple of 4
+                const float cfx = fminf(fmaxf(ffx[j], -1.0e5f), 1.0e5f), cfy = fminf(fmaxf(ffy[j], -1.0e5f), 1.0e5f);
+                s_org[0] = ((x0 + (int)floorf(cfx == cfx ? cfx : 0.f)) & ~3) - 8;
+                s_org[1] = y0 + (int)floorf(cfy == cfy ? cfy : 0.f) - M_;
+            }
+        }
+        __syncthreads();                       // all sums consumed, origin published
+        const int bx = s_org[0], by = s_org[1];
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async write
+            mbar_expect_tx(&bar, 5 * CH * (uint32_t)sizeof(float));
+            tma_load_3d(box, &tmapRbox, bx, by, (p * a.pair_stride + 1) * 5, &bar);
+        }
+        mbar_wait(&bar, 1);
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {     // fully unrolled: ffx / ffy stay in registers
+            const int idx = j * NT + tid;
+            const int cx = idx & 63, r = idx >> 6;
+            const int x = x0 + cx, y = y0 + r;
+            if (x >= w || y >= h) continue;
+            const float dx = ffx[j], dy = ffy[j];
+            const int o = y * pitch + x;
+            const float r0y = __ldg(R0 + o), r0x = __ldg(R0 + (o + plane)), r0yy = __ldg(R0 + (o + 2 * plane)),
+                        r0xx = __ldg(R0 + (o + 3 * plane)), r0xy = __ldg(R0 + (o + 4 * plane));
+            float fx = (float)x + dx, fy = (float)y + dy;
+            const float flx = floorf(fx), fly = floorf(fy);
+            const int x1 = (int)fminf(fmaxf(flx, -2.f), 1.0e6f), y1 = (int)fminf(fmaxf(fly, -2.f), 1.0e6f);
+            fx -= flx;
+            fy -= fly;
+            float r2, r3, r4, r5, r6;
+            if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+                const float gx = 1.f - fx, gy = 1.f - fy;
+                const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
+                const int lx = x1 - bx, ly = y1 - by;
+                if ((unsigned)lx < (unsigned)(RW - 1) && (unsigned)ly < (unsigned)(RH - 1)) {
+                    const float* q = box + ly * RW + lx;
+                    r2 = a00 * q[0] + a01 * q[1] + a10 * q[RW] + a11 * q[RW + 1];
+                    r3 = a00 * q[CH] + a01 * q[CH + 1] + a10 * q[CH + RW] + a11 * q[CH + RW + 1];
+                    r4 = a00 * q[2 * CH] + a01 * q[2 * CH + 1] + a10 * q[2 * CH + RW] + a11 * q[2 * CH + RW + 1];
+                    r5 = a00 * q[3 * CH] + a01 * q[3 * CH + 1] + a10 * q[3 * CH + RW] + a11 * q[3 * CH + RW + 1];
+                    r6 = a00 * q[4 * CH] + a01 * q[4 * CH + 1] + a10 * q[4 * CH + RW] + a11 * q[4 * CH + RW + 1];
+                } else {
+                    const int q0 = y1 * pitch + x1, q1 = q0 + pitch;
+                    r2 = a00 * __ldg(R1 + q0) + a01 * __ldg(R1 + q0 + 1) + a10 * __ldg(R1 + q1) + a11 * __ldg(R1 + q1 + 1);
+                    r3 = a00 * __ldg(R1 + (q0 + plane)) + a01 * __ldg(R1 + (q0 + plane) + 1) +
+                         a10 * __ldg(R1 + (q1 + plane)) + a11 * __ldg(R1 + (q1 + plane) + 1);
+                    r4 = a00 * __ldg(R1 + (q0 + 2 * plane)) + a01 * __ldg(R1 + (q0 + 2 * plane) + 1) +
+                         a10 * __ldg(R1 + (q1 + 2 * plane)) + a11 * __ldg(R1 + (q1 + 2 * plane) + 1);
+                    r5 = a00 * __ldg(R1 + (q0 + 3 * plane)) + a01 * __ldg(R1 + (q0 + 3 * plane) + 1) +
+                         a10 * __ldg(R1 + (q1 + 3 * plane)) + a11 * __ldg(R1 + (q1 + 3 * plane) + 1);
+                    r6 = a00 * __ldg(R1 + (q0 + 4 * plane)) + a01 * __ldg(R1 + (q0 + 4 * plane) + 1) +
+                         a10 * __ldg(R1 + (q1 + 4 * plane)) + a11 * __ldg(R1 + (q1 + 4 * plane) + 1);
+                }
+                r4 = (r0yy + r4) * 0.5f;
+                r5 = (r0xx + r5) * 0.5f;
+                r6 = (r0xy + r6) * 0.25f;
+            } else {
+                r2 = r3 = 0.f;
+                r4 = r0yy;
+                r5 = r0xx;
+                r6 = r0xy * 0.5f;
+            }
+            r2 = (r0y - r2) * 0.5f;
+            r3 = (r0x - r3) * 0.5f;
+            r2 += r4 * dy + r6 * dx;
+            r3 += r6 * dy + r5 * dx;
+            if (edge && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
+                const float sc = (x < 5 ? border_factor(x) : 1.f) * (x >= w - 5 ? border_factor(w - x - 1) : 1.f) *
+                                 (y < 5 ? border_factor(y) : 1.f) * (y >= h - 5 ? border_factor(h - y - 1) : 1.f);
+                r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+            }
+            Mout[o] = r4 * r4 + r6 * r6;
+            Mout[o + plane] = (r4 + r5) * r6;
+            Mout[o + 2 * plane] = r5 * r5 + r6 * r6;
+            Mout[o + 3 * plane] = r4 * r2 + r6 * r3;
+            Mout[o + 4 * plane] = r6 * r2 + r5 * r3;
+        }
+        return;
+    }
 #pragma unroll 2
     for (int j = 0; j < (IT_TX * IT_TY) / NT; ++j) {
         const int idx = j * NT + tid;
@@ -889,28 +990,39 @@ static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s
     return MAVD_OK;
 }
 
-template <int M_, bool LAST, int NT>
-static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const IterArgs& a, dim3 grid, cudaStream_t s) {
+template <int M_, bool LAST, int NT, bool R1S>
+static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const CUtensorMap& mapRbox, const IterArgs& a,
+                           dim3 grid, cudaStream_t s) {
     constexpr size_t smem = sizeof(float) * 5 * (IT_TY + 2 * M_) * (IT_TX + 16);
     static bool configured = false;
     if (!configured) {
-        MAVD_CUDA(cudaFuncSetAttribute(iter_box_tma_kernel<M_, LAST, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MAVD_CUDA(cudaFuncSetAttribute(iter_box_tma_kernel<M_, LAST, NT, R1S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         configured = true;
     }
-    iter_box_tma_kernel<M_, LAST, NT><<<grid, NT, smem, s>>>(map, mapR, a);
+    iter_box_tma_kernel<M_, LAST, NT, R1S><<<grid, NT, smem, s>>>(map, mapR, mapRbox, a);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
 
 template <bool LAST>
-static int launch_iter_tma_m(int m, const CUtensorMap& map, const CUtensorMap& mapR, const IterArgs& a, dim3 grid,
-                             cudaStream_t s) {
+static int launch_iter_tma_m(int m, const CUtensorMap& map, const CUtensorMap& mapR, const CUtensorMap& mapRbox,
+                             const IterArgs& a, dim3 grid, cudaStream_t s) {
+    // R1 staged in shared memory by a second TMA load: 4.36 vs 4.56 ms per 64-pair step (MAVD_R1S=0 switches it off)
+    static const bool r1s = !(getenv("MAVD_R1S") && getenv("MAVD_R1S")[0] == '0');
+    if (r1s && !LAST) {
+        switch (m) {
+            case 5: return launch_iter_tma<5, LAST, 256, true>(map, mapR, mapRbox, a, grid, s);
+            case 6: return launch_iter_tma<6, LAST, 256, true>(map, mapR, mapRbox, a, grid, s);
+            case 7: return launch_iter_tma<7, LAST, 256, true>(map, mapR, mapRbox, a, grid, s);
+            default: return launch_iter_tma<8, LAST, 256, true>(map, mapR, mapRbox, a, grid, s);
+        }
+    }
     switch (m) {
-        case 5: return launch_iter_tma<5, LAST, 256>(map, mapR, a, grid, s);
-        case 6: return launch_iter_tma<6, LAST, 256>(map, mapR, a, grid, s);
-        case 7: return launch_iter_tma<7, LAST, 256>(map, mapR, a, grid, s);
-        default: return launch_iter_tma<8, LAST, 256>(map, mapR, a, grid, s);
+        case 5: return launch_iter_tma<5, LAST, 256, false>(map, mapR, mapRbox, a, grid, s);
+        case 6: return launch_iter_tma<6, LAST, 256, false>(map, mapR, mapRbox, a, grid, s);
+        case 7: return launch_iter_tma<7, LAST, 256, false>(map, mapR, mapRbox, a, grid, s);
+        default: return launch_iter_tma<8, LAST, 256, false>(map, mapR, mapRbox, a, grid, s);
     }
 }
 
@@ -1028,8 +1140,8 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), st);
             int rc;
             if (!gauss && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter)
-                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], L.tmapR, a, g1, st)
-                          : launch_iter_tma_m<false>(m, L.tmapM[cur], L.tmapR, a, g1, st);
+                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], L.tmapR, L.tmapRbox, a, g1, st)
+                          : launch_iter_tma_m<false>(m, L.tmapM[cur], L.tmapR, L.tmapRbox, a, g1, st);
             else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, st) : launch_iter<true, false>(a, g, smem, st);
             else       rc = last ? launch_iter<false, true>(a, g, smem, st) : launch_iter<false, false>(a, g, smem, st);
             if (rc != MAVD_OK) return rc;
