@@ -437,8 +437,9 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
     const float* R0 = R + (size_t)(p * pair_stride) * 5 * plane;
     // One pixel per thread at 32 registers (full occupancy) is the fastest form measured: the 32-bit-offset
     // UpdateMatrices of the fused iteration (> 32 registers: 0.87 vs 0.675 ms per 16-pair step) and variants with
-    // 8 pixels per thread that halve the instruction count (2.45-2.67 vs 2.22 ms per 64-pair step) all lose more to
-    // occupancy than they save: the kernel is bound by the latency of its three dependent memory round trips.
+    // 8 pixels per thread that halve the instruction count (2.45-2.67 vs 2.22 ms per 64-pair step), and a tiled
+    // variant with the R1 footprint staged by TMA like the fused iteration's (2.57 ms), all lose more to occupancy
+    // than they save: the kernel is bound by the latency of its dependent memory round trips.
     update_matrices_px(x, y, w, h, pitch, plane, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
 }
 
@@ -730,6 +731,71 @@ __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h,
     Mout[o + 4 * plane] = r6 * r2 + r5 * r3;
 }
 
+// UpdateMatrices with the R1 footprint read from a shared-memory box [5][RH][RW] whose cell (0, 0) is image pixel
+// (bx, by); footprints that leave the box fall back to global loads.  Same operations, same order as
+// update_matrices_fast: identical results.
+template <int RW, int RH>
+__device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, int pitch, int plane, bool edge, float dx,
+                                                    float dy, const float* __restrict__ R0, const float* __restrict__ R1,
+                                                    float* __restrict__ Mout, const float* box, int bx, int by) {
+    constexpr int CH = RH * RW;
+    const int o = y * pitch + x;
+    const float r0y = __ldg(R0 + o), r0x = __ldg(R0 + (o + plane)), r0yy = __ldg(R0 + (o + 2 * plane)),
+                r0xx = __ldg(R0 + (o + 3 * plane)), r0xy = __ldg(R0 + (o + 4 * plane));
+    float fx = (float)x + dx, fy = (float)y + dy;
+    const float flx = floorf(fx), fly = floorf(fy);
+    const int x1 = (int)fminf(fmaxf(flx, -2.f), 1.0e6f), y1 = (int)fminf(fmaxf(fly, -2.f), 1.0e6f);
+    fx -= flx;
+    fy -= fly;
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float gx = 1.f - fx, gy = 1.f - fy;
+        const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
+        const int lx = x1 - bx, ly = y1 - by;
+        if ((unsigned)lx < (unsigned)(RW - 1) && (unsigned)ly < (unsigned)(RH - 1)) {
+            const float* q = box + ly * RW + lx;
+            r2 = a00 * q[0] + a01 * q[1] + a10 * q[RW] + a11 * q[RW + 1];
+            r3 = a00 * q[CH] + a01 * q[CH + 1] + a10 * q[CH + RW] + a11 * q[CH + RW + 1];
+            r4 = a00 * q[2 * CH] + a01 * q[2 * CH + 1] + a10 * q[2 * CH + RW] + a11 * q[2 * CH + RW + 1];
+            r5 = a00 * q[3 * CH] + a01 * q[3 * CH + 1] + a10 * q[3 * CH + RW] + a11 * q[3 * CH + RW + 1];
+            r6 = a00 * q[4 * CH] + a01 * q[4 * CH + 1] + a10 * q[4 * CH + RW] + a11 * q[4 * CH + RW + 1];
+        } else {
+            const int q0 = y1 * pitch + x1, q1 = q0 + pitch;
+            r2 = a00 * __ldg(R1 + q0) + a01 * __ldg(R1 + q0 + 1) + a10 * __ldg(R1 + q1) + a11 * __ldg(R1 + q1 + 1);
+            r3 = a00 * __ldg(R1 + (q0 + plane)) + a01 * __ldg(R1 + (q0 + plane) + 1) +
+                 a10 * __ldg(R1 + (q1 + plane)) + a11 * __ldg(R1 + (q1 + plane) + 1);
+            r4 = a00 * __ldg(R1 + (q0 + 2 * plane)) + a01 * __ldg(R1 + (q0 + 2 * plane) + 1) +
+                 a10 * __ldg(R1 + (q1 + 2 * plane)) + a11 * __ldg(R1 + (q1 + 2 * plane) + 1);
+            r5 = a00 * __ldg(R1 + (q0 + 3 * plane)) + a01 * __ldg(R1 + (q0 + 3 * plane) + 1) +
+                 a10 * __ldg(R1 + (q1 + 3 * plane)) + a11 * __ldg(R1 + (q1 + 3 * plane) + 1);
+            r6 = a00 * __ldg(R1 + (q0 + 4 * plane)) + a01 * __ldg(R1 + (q0 + 4 * plane) + 1) +
+                 a10 * __ldg(R1 + (q1 + 4 * plane)) + a11 * __ldg(R1 + (q1 + 4 * plane) + 1);
+        }
+        r4 = (r0yy + r4) * 0.5f;
+        r5 = (r0xx + r5) * 0.5f;
+        r6 = (r0xy + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = r0yy;
+        r5 = r0xx;
+        r6 = r0xy * 0.5f;
+    }
+    r2 = (r0y - r2) * 0.5f;
+    r3 = (r0x - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if (edge && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
+        const float sc = (x < 5 ? border_factor(x) : 1.f) * (x >= w - 5 ? border_factor(w - x - 1) : 1.f) *
+                         (y < 5 ? border_factor(y) : 1.f) * (y >= h - 5 ? border_factor(h - y - 1) : 1.f);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    Mout[o] = r4 * r4 + r6 * r6;
+    Mout[o + plane] = (r4 + r5) * r6;
+    Mout[o + 2 * plane] = r5 * r5 + r6 * r6;
+    Mout[o + 3 * plane] = r4 * r2 + r6 * r3;
+    Mout[o + 4 * plane] = r6 * r2 + r5 * r3;
+}
+
 template <int M_, bool LAST, int NT, bool R1S>
 __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                              const __grid_constant__ CUtensorMap tmapR,
@@ -883,62 +949,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
             const int cx = idx & 63, r = idx >> 6;
             const int x = x0 + cx, y = y0 + r;
             if (x >= w || y >= h) continue;
-            const float dx = ffx[j], dy = ffy[j];
-            const int o = y * pitch + x;
-            const float r0y = __ldg(R0 + o), r0x = __ldg(R0 + (o + plane)), r0yy = __ldg(R0 + (o + 2 * plane)),
-                        r0xx = __ldg(R0 + (o + 3 * plane)), r0xy = __ldg(R0 + (o + 4 * plane));
-            float fx = (float)x + dx, fy = (float)y + dy;
-            const float flx = floorf(fx), fly = floorf(fy);
-            const int x1 = (int)fminf(fmaxf(flx, -2.f), 1.0e6f), y1 = (int)fminf(fmaxf(fly, -2.f), 1.0e6f);
-            fx -= flx;
-            fy -= fly;
-            float r2, r3, r4, r5, r6;
-            if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-                const float gx = 1.f - fx, gy = 1.f - fy;
-                const float a00 = gx * gy, a01 = fx * gy, a10 = gx * fy, a11 = fx * fy;
-                const int lx = x1 - bx, ly = y1 - by;
-                if ((unsigned)lx < (unsigned)(RW - 1) && (unsigned)ly < (unsigned)(RH - 1)) {
-                    const float* q = box + ly * RW + lx;
-                    r2 = a00 * q[0] + a01 * q[1] + a10 * q[RW] + a11 * q[RW + 1];
-                    r3 = a00 * q[CH] + a01 * q[CH + 1] + a10 * q[CH + RW] + a11 * q[CH + RW + 1];
-                    r4 = a00 * q[2 * CH] + a01 * q[2 * CH + 1] + a10 * q[2 * CH + RW] + a11 * q[2 * CH + RW + 1];
-                    r5 = a00 * q[3 * CH] + a01 * q[3 * CH + 1] + a10 * q[3 * CH + RW] + a11 * q[3 * CH + RW + 1];
-                    r6 = a00 * q[4 * CH] + a01 * q[4 * CH + 1] + a10 * q[4 * CH + RW] + a11 * q[4 * CH + RW + 1];
-                } else {
-                    const int q0 = y1 * pitch + x1, q1 = q0 + pitch;
-                    r2 = a00 * __ldg(R1 + q0) + a01 * __ldg(R1 + q0 + 1) + a10 * __ldg(R1 + q1) + a11 * __ldg(R1 + q1 + 1);
-                    r3 = a00 * __ldg(R1 + (q0 + plane)) + a01 * __ldg(R1 + (q0 + plane) + 1) +
-                         a10 * __ldg(R1 + (q1 + plane)) + a11 * __ldg(R1 + (q1 + plane) + 1);
-                    r4 = a00 * __ldg(R1 + (q0 + 2 * plane)) + a01 * __ldg(R1 + (q0 + 2 * plane) + 1) +
-                         a10 * __ldg(R1 + (q1 + 2 * plane)) + a11 * __ldg(R1 + (q1 + 2 * plane) + 1);
-                    r5 = a00 * __ldg(R1 + (q0 + 3 * plane)) + a01 * __ldg(R1 + (q0 + 3 * plane) + 1) +
-                         a10 * __ldg(R1 + (q1 + 3 * plane)) + a11 * __ldg(R1 + (q1 + 3 * plane) + 1);
-                    r6 = a00 * __ldg(R1 + (q0 + 4 * plane)) + a01 * __ldg(R1 + (q0 + 4 * plane) + 1) +
-                         a10 * __ldg(R1 + (q1 + 4 * plane)) + a11 * __ldg(R1 + (q1 + 4 * plane) + 1);
-                }
-                r4 = (r0yy + r4) * 0.5f;
-                r5 = (r0xx + r5) * 0.5f;
-                r6 = (r0xy + r6) * 0.25f;
-            } else {
-                r2 = r3 = 0.f;
-                r4 = r0yy;
-                r5 = r0xx;
-                r6 = r0xy * 0.5f;
-            }
-            r2 = (r0y - r2) * 0.5f;
-            r3 = (r0x - r3) * 0.5f;
-            r2 += r4 * dy + r6 * dx;
-            r3 += r6 * dy + r5 * dx;
-            if (edge && ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10))) {
-                const float sc = (x < 5 ? border_factor(x) : 1.f) * (x >= w - 5 ? border_factor(w - x - 1) : 1.f) *
-                                 (y < 5 ? border_factor(y) : 1.f) * (y >= h - 5 ? border_factor(h - y - 1) : 1.f);
-                r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
-            }
-            Mout[o] = r4 * r4 + r6 * r6;
-            Mout[o + plane] = (r4 + r5) * r6;
-            Mout[o + 2 * plane] = r5 * r5 + r6 * r6;
-            Mout[o + 3 * plane] = r4 * r2 + r6 * r3;
-            Mout[o + 4 * plane] = r6 * r2 + r5 * r3;
+            update_matrices_box<RW, RH>(x, y, w, h, pitch, plane, edge, ffx[j], ffy[j], R0, R1, Mout, box, bx, by);
         }
         return;
     }
