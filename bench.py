@@ -343,7 +343,7 @@ def run_b200(args):
                 traffic = per_pair * B if per_pair else None      # bytes per launch, like `achieved`
             except Exception:
                 pass
-            roof = {'bound': 'hbm', 'kernel': 'iter_kernel<box,not-last> finest level', 'achieved': achieved,
+            roof = {'bound': 'hbm', 'kernel': 'iter_box_tma_kernel<m, not-last> (fused Farneback iteration), finest level', 'achieved': achieved,
                     'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak,
                     'traffic': traffic, 'us_per_launch': dur_s * 1e6, 'us_per_pair': dur_s * 1e6 / B,
                     'algorithmic_bytes_per_launch': algorithmic_bytes_iter(W, H, B), 'launches_timed': it_n}
