@@ -490,7 +490,7 @@ __device__ __forceinline__ bool pixel_fast(float fx, float fy, float dx, float d
 constexpr int RES_ITEMS = 4;     // pixel groups per thread
 
 template <int MODE, bool FAST, int VEC>
-__global__ void __launch_bounds__(256) residual_kernel(const ResidualArgs A, const FastPrm fp) {
+__global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, const FastPrm fp) {
     const int f = blockIdx.y;
     DerotRow dr;
     dr.on = 0;
@@ -561,40 +561,43 @@ __global__ void __launch_bounds__(256) residual_kernel(const ResidualArgs A, con
         }
         double yn = 0.0;
         if (MODE == 0 && dr.on) yn = __ldg(A.yn + y);
-        const float dyf = (float)((double)y - foey);     // FAST: FoE ray components in float32
+        // FAST: FoE ray components in float32 (x0 + k in float adds one rounding, 6e-8 relative: inside the budget)
+        const float dyf = (float)((double)y - foey), dxf0 = (float)((double)x0 - foex);
         unsigned totw = 0, fixw = 0;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
             const int x = x0 + k;
             const bool not_sky = ((skyw >> (8 * k)) & 255u) == 0;
             bool mt = false, mf = false;
-            double fdx = 0.0, fdy = 0.0;
             if (MODE == 1) {
                 float phi;
                 pixel_exact_f32(vfx[k], vfy[k], x, y, foex, foey, A.prm, not_sky, mt, mf, phi);
-                fdx = vfx[k]; fdy = vfy[k];
                 maxphi = fmax(maxphi, (double)phi);
                 if (A.phi_out) reinterpret_cast<float*>(reinterpret_cast<double*>(A.phi_out) + fbase)[i0 + k] = phi;
             } else {
-                if (MODE == 0) {
-                    fdx = vfx[k]; fdy = vfy[k];
-                    if (dr.on) {
-                        double r0, r1;
-                        derot_tab(dr, __ldg(A.xn + x), yn, r0, r1);
-                        fdx = __dsub_rn(fdx, r0);
-                        fdy = __dsub_rn(fdy, r1);
-                    }
-                } else {
-                    fdx = vx[k]; fdy = vy[k];
-                }
+                double fdx = 0.0, fdy = 0.0;
                 bool decided = false;
-                if (FAST) {
-                    if (!not_sky) decided = true;          // both masks are multiplied by ~sky
-                    else {
-                        // without derotation the float64 flow IS the float32 input: skip the round trip
-                        const float ffx = (MODE == 0 && !dr.on) ? vfx[k] : (float)fdx;
-                        const float ffy = (MODE == 0 && !dr.on) ? vfy[k] : (float)fdy;
-                        decided = pixel_fast(ffx, ffy, (float)((double)x - foex), dyf, fp, mt, mf);
+                if (FAST && MODE == 0 && !dr.on) {
+                    // no derotation: the float64 flow IS the float32 input, doubles are needed on the exact path only
+                    decided = !not_sky;                // both masks are multiplied by ~sky
+                    if (!decided) decided = pixel_fast(vfx[k], vfy[k], dxf0 + (float)k, dyf, fp, mt, mf);
+                    if (!decided) { fdx = (double)vfx[k]; fdy = (double)vfy[k]; }
+                } else {
+                    if (MODE == 0) {
+                        fdx = vfx[k]; fdy = vfy[k];
+                        if (dr.on) {
+                            double r0, r1;
+                            derot_tab(dr, __ldg(A.xn + x), yn, r0, r1);
+                            fdx = __dsub_rn(fdx, r0);
+                            fdy = __dsub_rn(fdy, r1);
+                        }
+                    } else {
+                        fdx = vx[k]; fdy = vy[k];
+                    }
+                    vx[k] = fdx; vy[k] = fdy;          // kept for the flow sum over the segmentation below
+                    if (FAST) {
+                        if (!not_sky) decided = true;
+                        else decided = pixel_fast((float)fdx, (float)fdy, dxf0 + (float)k, dyf, fp, mt, mf);
                     }
                 }
                 if (!decided) {
@@ -608,18 +611,32 @@ __global__ void __launch_bounds__(256) residual_kernel(const ResidualArgs A, con
             }
             totw |= (mt ? 1u : 0u) << (8 * k);
             fixw |= (mf ? 1u : 0u) << (8 * k);
-            if (want_stats) {
-                c_tot += mt; c_fix += mf;
-                if (seg) {
-                    const int g = (segw >> (8 * k)) & 255u;
-                    c_pos += g > 127;
-                    c_neg += (255 - g) > 127;
-                    c_tpt += mt && g >= 1;
-                    c_fpt += mt && g <= 254;
-                    c_tpf += mf && g >= 1;
-                    c_fpf += mf && g <= 254;
-                    if (g >= seg_min) { bx0 = min(bx0, x); bx1 = max(bx1, x); by0 = min(by0, y); by1 = max(by1, y); }
-                    if (g > 127) { sfx += fdx; sfy += fdy; }
+        }
+        if (want_stats) {
+            // counts on whole words: mask bytes are 0/1, segmentation bytes are tested with per-byte compares
+            c_tot += __popc(totw); c_fix += __popc(fixw);
+            if (seg) {
+                const unsigned live = VEC == 4 ? 0xffffffffu : 0xffu;
+                const unsigned hi = segw & 0x80808080u & live;                        // g > 127
+                const unsigned nz = __vcmpne4(segw, 0u) & 0x01010101u & live;          // g >= 1
+                const unsigned n255 = __vcmpne4(segw, 0xffffffffu) & 0x01010101u & live;   // g <= 254
+                c_pos += __popc(hi);
+                c_neg += VEC - __popc(hi);
+                c_tpt += __popc(totw & nz); c_fpt += __popc(totw & n255);
+                c_tpf += __popc(fixw & nz); c_fpf += __popc(fixw & n255);
+                const unsigned smin = (unsigned)min(seg_min, 256);
+                const unsigned ge = smin > 255u ? 0u : (__vcmpgeu4(segw, smin * 0x01010101u) & live);
+                if (ge) {
+                    bx0 = min(bx0, x0 + ((__ffs(ge) - 1) >> 3)); bx1 = max(bx1, x0 + ((31 - __clz(ge)) >> 3));
+                    by0 = min(by0, y); by1 = max(by1, y);
+                }
+                if (hi) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k)
+                        if ((hi >> (8 * k)) & 0x80u) {
+                            if (MODE == 1 || (FAST && MODE == 0 && !dr.on)) { sfx += (double)vfx[k]; sfy += (double)vfy[k]; }
+                            else { sfx += vx[k]; sfy += vy[k]; }
+                        }
                 }
             }
         }
