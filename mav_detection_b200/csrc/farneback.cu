@@ -830,9 +830,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
     const int w = a.w, h = a.h, pitch = a.pitch;
     const int plane = (int)a.plane;
 
-    if (tid == 0) mbar_init(&bar, 1);
-    __syncthreads();
     if (tid == 0) {
+        // the issuing thread initialises the barrier and starts the load before the block-wide sync that publishes
+        // the barrier to the waiters, so the transfer is already in flight while the other warps arrive
+        mbar_init(&bar, 1);
         mbar_expect_tx(&bar, 5 * CH * (uint32_t)sizeof(float));
         tma_load_3d(box, &tmap, x0 - 8, y0 - M_, p * 5, &bar);
         // R0 (this tile) and R1 (this tile displaced by the flow) are read ~10 us from now by the per-pixel
@@ -840,6 +841,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         if (!LAST) tma_prefetch_3d(&tmapR, x0 - 8, y0 - 8, p * a.pair_stride * 5);
     }
     const bool interior = (x0 - 8 >= 0) && (x0 + IT_TX + 8 <= w) && (y0 - M_ >= 0) && (y0 + IT_TY + M_ <= h);
+    __syncthreads();
     mbar_wait(&bar, 0);
 
     if (!interior) {
