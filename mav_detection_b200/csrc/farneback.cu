@@ -171,12 +171,10 @@ __global__ void pyr0_kernel(const uint8_t* __restrict__ frame, int W, int H, flo
 // ------------------------------------------------------------------------------------------------
 constexpr int PE_TX = 64, PE_TY = 32, PE_H = 8, PE_RW = PE_TX + 2 * PE_H;  // 80
 
-__device__ __forceinline__ void blur3_row4(const uint8_t* __restrict__ p, float (&hv)[4]) {
-    // p is 4-byte aligned and points 4 bytes left of the first of four output cells.  Bytes -> floats with the
-    // mantissa trick (byte_to_float: permute + exact subtract, full-rate pipes) instead of I2F on the XU pipe.
-    const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(p));
-    const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(p) + 1);
-    const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(p) + 2);
+// horizontal [1/4 1/2 1/4] blur of four cells from the three aligned words around them (a holds the byte left of the
+// first cell in its top byte, c the byte right of the last cell in its bottom byte).  Bytes -> floats with the
+// mantissa trick (byte_to_float: permute + exact subtract, full-rate pipes) instead of I2F on the XU pipe.
+__device__ __forceinline__ void blur3_words(uint32_t a, uint32_t b, uint32_t c, float (&hv)[4]) {
     const float v3 = byte_to_float(a, 0x7543u), v4 = byte_to_float(b, 0x7540u), v5 = byte_to_float(b, 0x7541u),
                 v6 = byte_to_float(b, 0x7542u), v7 = byte_to_float(b, 0x7543u), v8 = byte_to_float(c, 0x7540u);
     hv[0] = 0.25f * v3 + 0.5f * v4 + 0.25f * v5;
@@ -212,25 +210,40 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const void* __restrict__ s
         const bool fast = u8_aligned && (x0 - PE_H - 4 >= 0) && (x0 + PE_TX + PE_H + 4 <= w) && (y0 - n - 1 >= 0) &&
                           (y0 + PE_TY + n + 1 <= h);
         if (fast) {
-            // 20 groups of 4 cells x 12 row segments; each thread marches down its rows with a 3-row window
+            // 20 groups of 4 cells x 12 row segments.  Each thread first issues ALL its loads (three words per row,
+            // rows r0-1 .. r1), then blurs: the global-load latency is paid once per thread, not once per row.
+            constexpr int RPS_MAX = N_ > 0 ? (PE_TY + 2 * N_ + 11) / 12 : (PE_TY + 2 * kMaxPolyN + 11) / 12;
             const int g = tid % 20, seg = tid / 20;
             const int rps = (rows + 11) / 12;
             const int r0 = seg * rps, r1 = min(rows, r0 + rps);
             if (seg < 12 && r0 < r1) {
                 const uint8_t* p = src + (size_t)(y0 - n + r0 - 1) * w + (x0 - PE_H + 4 * g - 4);
-                float hp[4], hc[4], hn[4];
-                blur3_row4(p, hp);
-                blur3_row4(p + w, hc);
-                for (int rr = r0; rr < r1; ++rr) {
-                    blur3_row4(p + (size_t)(rr - r0 + 2) * w, hn);
-                    float4 v;
-                    v.x = 0.25f * hp[0] + 0.5f * hc[0] + 0.25f * hn[0];
-                    v.y = 0.25f * hp[1] + 0.5f * hc[1] + 0.25f * hn[1];
-                    v.z = 0.25f * hp[2] + 0.5f * hc[2] + 0.25f * hn[2];
-                    v.w = 0.25f * hp[3] + 0.5f * hc[3] + 0.25f * hn[3];
-                    *reinterpret_cast<float4*>(&raw[(rr + PE_H - n) * PE_RW + 4 * g]) = v;
+                uint32_t wa[RPS_MAX + 2], wb[RPS_MAX + 2], wc[RPS_MAX + 2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { hp[i] = hc[i]; hc[i] = hn[i]; }
+                for (int i = 0; i < RPS_MAX + 2; ++i) {
+                    if (i < r1 - r0 + 2) {
+                        const uint32_t* q = reinterpret_cast<const uint32_t*>(p + (size_t)i * w);
+                        wa[i] = __ldg(q); wb[i] = __ldg(q + 1); wc[i] = __ldg(q + 2);
+                    } else {
+                        wa[i] = wb[i] = wc[i] = 0u;
+                    }
+                }
+                float hp[4], hc[4], hn[4];
+                blur3_words(wa[0], wb[0], wc[0], hp);
+                blur3_words(wa[1], wb[1], wc[1], hc);
+#pragma unroll
+                for (int i = 0; i < RPS_MAX; ++i) {
+                    if (i < r1 - r0) {
+                        blur3_words(wa[i + 2], wb[i + 2], wc[i + 2], hn);
+                        float4 v;
+                        v.x = 0.25f * hp[0] + 0.5f * hc[0] + 0.25f * hn[0];
+                        v.y = 0.25f * hp[1] + 0.5f * hc[1] + 0.25f * hn[1];
+                        v.z = 0.25f * hp[2] + 0.5f * hc[2] + 0.25f * hn[2];
+                        v.w = 0.25f * hp[3] + 0.5f * hc[3] + 0.25f * hn[3];
+                        *reinterpret_cast<float4*>(&raw[(r0 + i + PE_H - n) * PE_RW + 4 * g]) = v;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { hp[k] = hc[k]; hc[k] = hn[k]; }
+                    }
                 }
             }
         } else {
