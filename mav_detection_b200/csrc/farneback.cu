@@ -881,12 +881,20 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                 in[j] = q[j * RW];
                 s += in[j];
             }
+            // running sums, re-seeded from the window every 8 rows (bounds the float32 drift; the same association
+            // as iter_kernel's 8-row segments, so both kernels produce bit-identical sums)
 #pragma unroll
             for (int y = 0; y < IT_TY; ++y) {
                 q[y * RW] = s;
                 if (y < IT_TY - 1) {
                     in[y + 2 * M_ + 1] = q[(y + 2 * M_ + 1) * RW];
-                    s += in[y + 2 * M_ + 1] - in[y];
+                    if (((y + 1) & 7) == 0) {
+                        s = 0.f;
+#pragma unroll
+                        for (int j = 0; j <= 2 * M_; ++j) s += in[y + 1 + j];
+                    } else {
+                        s += in[y + 2 * M_ + 1] - in[y];
+                    }
                 }
             }
         }

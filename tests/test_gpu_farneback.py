@@ -97,7 +97,8 @@ def test_ragged_sizes_and_windows_vs_cv2(size, winsize, poly_n, flags):
 
 @pytest.mark.parametrize('winsize', [11, 12, 15, 17])
 def test_tma_and_generic_iteration_kernels_agree(winsize):
-    """winsize/2 in 5..8 runs the TMA-staged kernel; the generic kernel must give (nearly) the same flow."""
+    """winsize/2 in 5..8 runs the TMA-staged kernel; the generic kernel associates its sums identically, so the
+    flows are bit-equal."""
     import torch
     from mav_detection_b200 import engine, synth
     s = synth.make_sequence(700, 500, 3, seq=5)
@@ -108,7 +109,40 @@ def test_tma_and_generic_iteration_kernels_agree(winsize):
     eng.force_generic_iteration(True)
     b = eng.farneback(frames).cpu().numpy()
     eng.force_generic_iteration(False)
-    epe = np.linalg.norm(a - b, axis=-1)
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
+    eng.close()
+
+
+def test_discontinuous_flow_exercises_the_gather_fallback():
+    """The fused iteration stages R1 around each tile at an origin displaced by the tile centre's flow; footprints
+    that leave that box fall back to global loads.  Two image halves moving 9 px in opposite directions put both
+    kinds of pixel into the tiles on the seam; the result must equal the generic (non-TMA) kernel and cv2."""
+    cv2 = pytest.importorskip('cv2')
+    import torch
+    from mav_detection_b200 import engine
+    rng = np.random.default_rng(3)
+    lo = rng.random((70, 110), dtype=np.float32)
+    tex = cv2.resize(lo, None, fx=8, fy=8, interpolation=cv2.INTER_CUBIC)
+    H, W = 384, 704
+    a = tex[40:40 + H, 60:60 + W]
+    b = a.copy()
+    b[:, :W // 2] = tex[40:40 + H, 60 - 9:60 - 9 + W // 2]          # left half moves right by 9 px
+    b[:, W // 2:] = tex[40 + 7:40 + 7 + H, 60 + W // 2:60 + W]      # right half moves up by 7 px
+    f0 = np.clip(a * 255, 0, 255).astype(np.uint8)
+    f1 = np.clip(b * 255, 0, 255).astype(np.uint8)
+    p = dict(pyr_scale=0.5, levels=4, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+    eng = engine.Engine(W, H, p, max_pairs=1)
+    frames = torch.from_numpy(np.stack([f0, f1])).cuda()
+    flow = eng.farneback(frames).cpu().numpy()[0]
+    assert np.abs(flow[100:300, 100:250, 0]).mean() > 5 and np.abs(flow[100:300, 450:600, 1]).mean() > 4
+    eng.force_generic_iteration(True)
+    gen = eng.farneback(frames).cpu().numpy()[0]
+    eng.force_generic_iteration(False)
+    # the two kernels associate their float32 sums identically: bit-equal flow, also across the branch
+    # discontinuities of UpdateMatrices (bottom row with dy ~ 0) where any rounding difference would be amplified
+    assert np.array_equal(flow, gen), float(np.abs(flow - gen).max())
+    ref = cv2.calcOpticalFlowFarneback(f0, f1, None, 0.5, 4, 15, 3, 5, 1.2, 0)
+    epe = np.linalg.norm(flow - ref, axis=-1)
     assert epe.mean() < EPE_MEAN_TIGHT and epe.max() < EPE_MAX_TOL, (epe.mean(), epe.max())
     eng.close()
 
