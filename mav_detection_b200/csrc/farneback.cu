@@ -4,13 +4,15 @@
 // HBM layout: every per-level field is PLANAR with a row pitch that is a multiple of 64 floats
 // (256 B): image [frame][h][pitch]; R [frame][5][h][pitch]; M [pair][5][h][pitch] (ping-pong);
 // flow [pair][h][pitch] float2.  64-wide tiles therefore never cross a row end and every tile row is
-// 16-byte aligned (float4 / cp.async / TMA friendly).  Batch elements sit in grid.z.
+// 16-byte aligned (float4 / cp.async / TMA friendly).  Batch elements sit in grid.z, or are interleaved into
+// a 1-D grid where the CTA order matters for L2 (consecutive pairs share an R plane).
 //
 // Kernels (algorithmic bytes per level pixel P):
-//   pyr_vfirst / pyr_hsecond       blur+resize from full-res u8 for all coarse levels, two launches
-//   polyexp_kernel         separable polynomial expansion, smem tile            4P -> 20P (level 0: 1P -> 20P)
-//   matrices_init_kernel   flow upsample (x 1/pyr_scale) fused with UpdateMatrices   (8P' +) 40P -> 20P
-//   iter_kernel            box/Gaussian blur of M + 2x2 solve + UpdateMatrices   88P (28P for the last)
+//   pyr_vfirst / pyr_hsecond  blur+resize from full-res u8 for all coarse levels, two launches
+//   polyexp_kernel            separable polynomial expansion, smem tile          4P -> 20P (level 0: 1P -> 20P)
+//   matrices_init_kernel      flow upsample (x 1/pyr_scale) fused with UpdateMatrices   (8P' +) 40P -> 20P
+//   iter_box_tma_kernel       box blur of M + 2x2 solve + UpdateMatrices, TMA-staged     88P (28P for the last)
+//   iter_kernel               the same for Gaussian windows and window sizes outside 11..17 (generic staging)
 #include <math.h>
 #include <stdlib.h>
 
@@ -655,10 +657,12 @@ __global__ void __launch_bounds__(256, 3) iter_kernel(IterArgs a) {
 //              registers, the sum for row y overwrites row y after its input has been consumed
 //   horizontal half-warp = one row: 4 outputs per thread from 5 float4 reads, written back over
 //              columns 8..71 after a __syncwarp (rows are private to a half-warp)
-//   pixel      x-fastest mapping: 2x2 solve, then UpdateMatrices with coalesced R0 loads, R1 gather
-//              through the read-only path and coalesced M' stores
+//   pixel      x-fastest mapping: 2x2 solve into registers; then a SECOND TMA load puts the five R1 planes
+//              around the tile (displaced by the tile centre's flow) into the same box, and UpdateMatrices
+//              gathers from shared memory (global fallback for footprints outside the box), with
+//              coalesced R0 loads and M' stores
 // Out-of-image box cells arrive as zeros (TMA fill) and are overwritten with the replicated edge
-// values for border tiles only.  Three __syncthreads per tile instead of eleven.
+// values for border tiles only.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
