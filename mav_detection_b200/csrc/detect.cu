@@ -1037,6 +1037,9 @@ __device__ __forceinline__ unsigned load_mask_word(const uint8_t* __restrict__ m
     return m[i0];
 }
 
+// init: every foreground pixel points at the first pixel of its run INSIDE its 4-pixel word, so the links between
+// horizontally adjacent pixels of a word never touch memory again (the run start has the smallest raster index of
+// the run, consistent with "smaller index = root")
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int npx) {
     const size_t base = (size_t)blockIdx.y * npx;
@@ -1045,12 +1048,20 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict
         const int i0 = q * VEC;
         const unsigned wv = load_mask_word<VEC>(mask + base, i0);
         if (wv == 0) continue;
+        int start = 0;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k)
-            if ((wv >> (8 * k)) & 255u) parent[base + i0 + k] = i0 + k;
+        for (int k = 0; k < VEC; ++k) {
+            const bool fg = ((wv >> (8 * k)) & 255u) != 0;
+            if (!fg) { start = k + 1; continue; }
+            parent[base + i0 + k] = i0 + start;
+        }
     }
 }
 
+// merge: one union per (run, neighbouring run) adjacency instead of two per pixel.  For a run [s, e] of a word:
+//   left   the run starts the word and the pixel left of the word is set
+//   up     every upper-row run that touches columns s-1 .. e+1 (8-connectivity) is joined once, at its first
+//          pixel inside that column range
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w, int h) {
     const int npx = w * h;
@@ -1063,19 +1074,33 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restric
     if (wv == 0) return;
     int* par = parent + base;
     const int y = i0 / w, x0 = i0 - y * w;
+    // bit k + 1 of `cur`: pixel k of this word is set; `up`: pixel k of the row above (bit 0 = the pixel up-left of
+    // the word, bit VEC + 1 = the pixel up-right of it)
+    unsigned cur = 0, up = 0;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) cur |= (((wv >> (8 * k)) & 255u) ? 1u : 0u) << (k + 1);
+    if (y > 0) {
+        const unsigned uw = load_mask_word<VEC>(m, i0 - w);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) up |= (((uw >> (8 * k)) & 255u) ? 1u : 0u) << (k + 1);
+        if (x0 > 0 && m[i0 - w - 1]) up |= 1u;
+        if (x0 + VEC < w && m[i0 - w + VEC]) up |= 1u << (VEC + 1);
+    }
+    const bool left_set = x0 > 0 && m[i0 - 1];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-        if (!((wv >> (8 * k)) & 255u)) continue;
-        const int i = i0 + k, x = x0 + k;
-        const bool left = (k > 0) ? (((wv >> (8 * (k - 1))) & 255u) != 0) : (x > 0 && m[i - 1]);
-        if (left) uf_union(par, i, i - 1);
-        if (y > 0) {
-            if (m[i - w]) uf_union(par, i, i - w);
-            else {
-                // with the pixel above set, both diagonals are already joined through it
-                if (x > 0 && m[i - w - 1]) uf_union(par, i, i - w - 1);
-                if (x + 1 < w && m[i - w + 1]) uf_union(par, i, i - w + 1);
-            }
+        if (!((cur >> (k + 1)) & 1u)) continue;
+        if ((cur >> k) & 1u) continue;             // not a run start (bit 0 of cur is never set, so k == 0 always is)
+        int e = k;
+        while (e + 1 < VEC && ((cur >> (e + 2)) & 1u)) ++e;        // run [k, e]
+        const int i = i0 + k;
+        if (k == 0 && left_set) uf_union(par, i, i - 1);
+        // upper-row columns k-1 .. e+1 are bits k .. e+2 of `up`; join at every 0 -> 1 transition in that range
+        bool prev = false;
+        for (int c = k; c <= e + 2; ++c) {
+            const bool u = (up >> c) & 1u;
+            if (u && !prev) uf_union(par, i, i0 - w + (c - 1));
+            prev = u;
         }
     }
 }
