@@ -141,6 +141,9 @@ int mavd_farneback_tap(mavd_handle h, int32_t kind, int32_t level, int32_t index
 /* ---- stage 1.5: Detector.derotate — src/detector.py:70-117.  d_out is (H, W, 2) float64. ---- */
 int mavd_derotate(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, double* d_out,
                   void* stream);
+/* The same for a flow that is already float64 (NumPy promotes nothing then: flow - derotation, src/detector.py:117). */
+int mavd_derotate_f64(mavd_handle h, const double* d_flow, int32_t n, const mavd_imu* h_imu, double* d_out,
+                      void* stream);
 
 /* ---- stage 2: FocusOfExpansion.get_FOE_dense + ransac — src/focus_of_expansion.py:32-86 ----
  * d_samples: per frame MAVD_SAMPLES_PER_FRAME int32 laid out [ry(2000) | rx(2000)], the two

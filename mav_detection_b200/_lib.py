@@ -73,6 +73,7 @@ SIGNATURES = {
     'mavd_farneback': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     'mavd_farneback_tap': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'mavd_derotate': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), _P, _P]),
+    'mavd_derotate_f64': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), _P, _P]),
     'mavd_foe': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P, _P, _P, _P]),
     'mavd_foe_dense': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(DetectParams), _P, _P, _P, _P]),
     'mavd_ransac': (C.c_int, [_P, _P, C.c_int32, C.c_double, _P, _P]),

@@ -525,7 +525,15 @@ int mavd_derotate(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu*
     if (n == 0) return MAVD_OK;
     MAVD_REQUIRE(d_flow && d_out, MAVD_ERR_INVALID, "derotate: NULL buffer");
     TRY(upload_imu(h, h_imu, n, (cudaStream_t)stream, nullptr, nullptr));
-    return derotate_run(h, d_flow, n, h->d_imu, d_out, (cudaStream_t)stream);
+    return derotate_run(h, d_flow, 0, n, h->d_imu, d_out, (cudaStream_t)stream);
+}
+
+int mavd_derotate_f64(mavd_handle h, const double* d_flow, int32_t n, const mavd_imu* h_imu, double* d_out, void* stream) {
+    TRY(check_batch(h, n, "derotate_f64"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_flow && d_out, MAVD_ERR_INVALID, "derotate_f64: NULL buffer");
+    TRY(upload_imu(h, h_imu, n, (cudaStream_t)stream, nullptr, nullptr));
+    return derotate_run(h, d_flow, 1, n, h->d_imu, d_out, (cudaStream_t)stream);
 }
 
 int mavd_foe(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,

@@ -173,7 +173,8 @@ int farneback_run(mavd_handle h, const uint8_t* d_frames, int n_pairs, int pair_
 int farneback_tap(mavd_handle h, int kind, int level, int index, float* d_out, cudaStream_t s);
 // detect.cu
 int bgr2gray_run(const uint8_t* d_bgr, uint8_t* d_gray, int64_t n, cudaStream_t s);
-int derotate_run(mavd_handle h, const float* d_flow, int n, const mavd_imu* d_imu, double* d_out, cudaStream_t s);
+int derotate_run(mavd_handle h, const void* d_flow, int flow_is_f64, int n, const mavd_imu* d_imu, double* d_out,
+                 cudaStream_t s);
 int foe_run(mavd_handle h, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu,
             const mavd_detect_params& prm, const int32_t* d_samples, double* d_foe, int32_t* d_ninter, cudaStream_t s);
 int ransac_run(const double* d_estimates, int K, double threshold, double* d_out, cudaStream_t s);

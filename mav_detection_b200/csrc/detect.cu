@@ -85,22 +85,27 @@ __device__ __forceinline__ void derot_at(const Derot& d, int x, int y, double& r
     r1 = __dmul_rn(u, d.s1);
 }
 
-__global__ void __launch_bounds__(256) derotate_kernel(const float2* __restrict__ flow, const mavd_imu* __restrict__ imu,
+template <typename T2>
+__global__ void __launch_bounds__(256) derotate_kernel(const T2* __restrict__ flow, const mavd_imu* __restrict__ imu,
                                                       int w, int h, double2* __restrict__ out) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
     if (x >= w) return;
     const Derot d = make_derot(imu[f], w, h);
     const size_t o = ((size_t)f * h + y) * w + x;
-    const float2 v = flow[o];
+    const T2 v = flow[o];
     double r0 = 0.0, r1 = 0.0;
     if (d.on) derot_at(d, x, y, r0, r1);
     out[o] = make_double2(d.on ? __dsub_rn((double)v.x, r0) : (double)v.x,
                           d.on ? __dsub_rn((double)v.y, r1) : (double)v.y);
 }
 
-int derotate_run(mavd_handle H, const float* d_flow, int n, const mavd_imu* d_imu, double* d_out, cudaStream_t s) {
+int derotate_run(mavd_handle H, const void* d_flow, int flow_is_f64, int n, const mavd_imu* d_imu, double* d_out,
+                 cudaStream_t s) {
     dim3 g(ceil_div(H->cfg.width, 256), H->cfg.height, n);
-    derotate_kernel<<<g, 256, 0, s>>>((const float2*)d_flow, d_imu, H->cfg.width, H->cfg.height, (double2*)d_out);
+    if (flow_is_f64)
+        derotate_kernel<double2><<<g, 256, 0, s>>>((const double2*)d_flow, d_imu, H->cfg.width, H->cfg.height, (double2*)d_out);
+    else
+        derotate_kernel<float2><<<g, 256, 0, s>>>((const float2*)d_flow, d_imu, H->cfg.width, H->cfg.height, (double2*)d_out);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }

@@ -69,11 +69,8 @@ class Detector:
         ang, dt, _ = self.imu_for(previous_frame_index, current_frame_index)
         eng = self._eng()
         flow = np.ascontiguousarray(flow_uv)
-        if flow.dtype != np.float32:
-            # float64 flow: flow - derotation with the float32 zero field gives the derotation itself
-            zero = torch.zeros((1,) + flow.shape, dtype=torch.float32, device=eng.device)
-            rot = -eng.derotate(zero, engine.make_imu(1, ang[None], dt, derotate=True))[0]
-            return flow - rot.cpu().numpy()
+        if flow.dtype not in (np.float32, np.float64):
+            flow = flow.astype(np.float64)
         out = eng.derotate(torch.from_numpy(flow[None]).to(eng.device), engine.make_imu(1, ang[None], dt, derotate=True))
         return out[0].cpu().numpy()
 

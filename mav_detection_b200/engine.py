@@ -139,9 +139,12 @@ class Engine:
 
     # -- stage 1.5 ----------------------------------------------------------------------------
     def derotate(self, flow: torch.Tensor, imu) -> torch.Tensor:
+        """Detector.derotate for a batch — detector.py:70-117.  float32 or float64 (n, H, W, 2) in, float64 out."""
         n = flow.shape[0]
+        kind = self._flow_kind(flow)
         out = torch.empty(flow.shape, dtype=torch.float64, device=self.device)
-        check(self.lib.mavd_derotate(self._h, flow.data_ptr(), n, imu, out.data_ptr(), self._stream()))
+        fn = self.lib.mavd_derotate_f64 if kind else self.lib.mavd_derotate
+        check(fn(self._h, flow.data_ptr(), n, imu, out.data_ptr(), self._stream()))
         return out
 
     # -- stage 2 -----------------------------------------------------------------------------

@@ -221,3 +221,17 @@ def test_farneback_class_process():
         assert ref_invalid == expect_invalid, name
         assert (int(scratch[2].item()) == 0) == expect_invalid, name
         assert np.array_equal(out_d.cpu().numpy(), ref_img), name
+
+
+def test_detector_derotate_float64_input():
+    """Detector.derotate on a flow that is already float64 (detector.py:117: flow - derotation, no promotion)."""
+    from mav_detection_b200.detector import Detector
+    from oracle import detect_np as dn
+    w, h = 96, 72
+    ang, dt = np.array([0.003, -0.002, 0.001]), 0.04
+    rng = np.random.default_rng(2)
+    flow64 = rng.normal(0, 3, (h, w, 2))
+    det = Detector(FakeDataset(w, h, ang, dt))
+    out = det.derotate(4, 5, flow64)
+    assert out.dtype == np.float64 and np.array_equal(out, dn.derotate(5, flow64, ang, dt))
+    assert det.derotate(-1, 0, flow64) is flow64                 # frame index < 1: untouched, same object
