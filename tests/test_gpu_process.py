@@ -69,3 +69,25 @@ def test_whole_path_matches_chained_oracle(host):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_empty_batches_are_no_ops():
+    """n = 0 through every batched entry point: status OK, nothing written, no launch."""
+    import torch
+    from mav_detection_b200 import engine
+    W, H = 64, 48
+    eng = engine.Engine(W, H, engine.SAMPLE_PARAMS, max_pairs=2)
+    before = eng.launch_count()
+    one = torch.zeros((1, H, W), dtype=torch.uint8, device='cuda')
+    flow = eng.farneback(one)                                   # one frame = zero pairs
+    assert tuple(flow.shape) == (0, H, W, 2)
+    imu = engine.make_imu(1)
+    samples = torch.zeros((0, 4000), dtype=torch.int32, device='cuda')
+    rec = eng.process(one, imu, samples, n_pairs=0)
+    assert tuple(rec.shape) == (0, engine.RECORD_DTYPE.itemsize)
+    rec = eng.detect(torch.zeros((0, H, W, 2), dtype=torch.float32, device='cuda'), imu, samples)
+    assert rec.shape[0] == 0
+    assert eng.launch_count() == before
+    with pytest.raises(ValueError):
+        eng.farneback(torch.zeros((4, H, W), dtype=torch.uint8, device='cuda'))      # 3 pairs > max_pairs 2
+    eng.close()
