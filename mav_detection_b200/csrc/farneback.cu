@@ -188,7 +188,7 @@ __device__ __forceinline__ void blur3_words(uint32_t a, uint32_t b, uint32_t c, 
 // N_ > 0: poly_n known at compile time (5, 7 and 8 are instantiated: OpenCV's sample value, its other GPU value
 // and the reference's) so the tap loops carry no predicates; N_ == 0: any poly_n <= 8 at run time.
 template <bool U8, int N_>
-__global__ void __launch_bounds__(256) polyexp_kernel(const void* __restrict__ src_base, size_t src_stride, int w,
+__global__ void __launch_bounds__(256, 4) polyexp_kernel(const void* __restrict__ src_base, size_t src_stride, int w,
                                                      int h, int pitch, int u8_aligned, PolyConst pc,
                                                      float* __restrict__ R, size_t plane) {
     __shared__ __align__(16) float raw[(PE_TY + 2 * PE_H) * PE_RW];
@@ -249,17 +249,43 @@ __global__ void __launch_bounds__(256) polyexp_kernel(const void* __restrict__ s
                 }
             }
         } else {
-            for (int idx = tid; idx < rows * PE_RW; idx += 256) {
-                int rr = idx / PE_RW, cc = idx - rr * PE_RW;
-                int gy = clampi(y0 - n + rr, 0, h - 1);
-                int gx = clampi(x0 - PE_H + cc, 0, w - 1);
+            // border tiles: every staged row picks its own three source rows (replicated row for the expansion's
+            // halo, REFLECT_101 neighbours for the 3x3 blur); groups of four cells whose three words lie inside the
+            // row still use whole words, the few groups on the left / right image border go cell by cell
+            const int g = tid % 20;
+            const int gx0 = x0 - PE_H + 4 * g;
+            const bool words = u8_aligned && gx0 - 4 >= 0 && gx0 + 8 <= w;
+            for (int rr = tid / 20; rr < rows && tid < 240; rr += 12) {
+                const int gy = clampi(y0 - n + rr, 0, h - 1);
                 const int ym = reflect101(gy - 1, h), yp = reflect101(gy + 1, h);
-                const int xm = reflect101(gx - 1, w), xp = reflect101(gx + 1, w);
-                const uint8_t *q0 = src + (size_t)ym * w, *q1 = src + (size_t)gy * w, *q2 = src + (size_t)yp * w;
-                const float h0 = 0.25f * q0[xm] + 0.5f * q0[gx] + 0.25f * q0[xp];
-                const float h1 = 0.25f * q1[xm] + 0.5f * q1[gx] + 0.25f * q1[xp];
-                const float h2 = 0.25f * q2[xm] + 0.5f * q2[gx] + 0.25f * q2[xp];
-                raw[(rr + PE_H - n) * PE_RW + cc] = 0.25f * h0 + 0.5f * h1 + 0.25f * h2;
+                float4 v;
+                if (words) {
+                    const uint32_t* qa = reinterpret_cast<const uint32_t*>(src + (size_t)ym * w + (gx0 - 4));
+                    const uint32_t* qb = reinterpret_cast<const uint32_t*>(src + (size_t)gy * w + (gx0 - 4));
+                    const uint32_t* qc = reinterpret_cast<const uint32_t*>(src + (size_t)yp * w + (gx0 - 4));
+                    float hp[4], hc[4], hn[4];
+                    blur3_words(__ldg(qa), __ldg(qa + 1), __ldg(qa + 2), hp);
+                    blur3_words(__ldg(qb), __ldg(qb + 1), __ldg(qb + 2), hc);
+                    blur3_words(__ldg(qc), __ldg(qc + 1), __ldg(qc + 2), hn);
+                    v.x = 0.25f * hp[0] + 0.5f * hc[0] + 0.25f * hn[0];
+                    v.y = 0.25f * hp[1] + 0.5f * hc[1] + 0.25f * hn[1];
+                    v.z = 0.25f * hp[2] + 0.5f * hc[2] + 0.25f * hn[2];
+                    v.w = 0.25f * hp[3] + 0.5f * hc[3] + 0.25f * hn[3];
+                } else {
+                    const uint8_t *q0 = src + (size_t)ym * w, *q1 = src + (size_t)gy * w, *q2 = src + (size_t)yp * w;
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int gx = clampi(gx0 + k, 0, w - 1);
+                        const int xm = reflect101(gx - 1, w), xp = reflect101(gx + 1, w);
+                        const float h0 = 0.25f * q0[xm] + 0.5f * q0[gx] + 0.25f * q0[xp];
+                        const float h1 = 0.25f * q1[xm] + 0.5f * q1[gx] + 0.25f * q1[xp];
+                        const float h2 = 0.25f * q2[xm] + 0.5f * q2[gx] + 0.25f * q2[xp];
+                        o[k] = 0.25f * h0 + 0.5f * h1 + 0.25f * h2;
+                    }
+                    v = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                *reinterpret_cast<float4*>(&raw[(rr + PE_H - n) * PE_RW + 4 * g]) = v;
             }
         }
     }
