@@ -1101,16 +1101,17 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
     const size_t frame_bytes = (size_t)W * Hh;
 
     // pyramid images of every coarser level for all frames: two launches
-    auto build_pyramid = [&](cudaStream_t st) -> int {
-        if (H->n_levels <= 1) return MAVD_OK;
+    // pyramid images of levels lo..hi (1 <= lo <= hi) for all frames: two launches
+    auto build_pyramid = [&](cudaStream_t st, int lo, int hi) -> int {
+        if (H->n_levels <= 1 || lo > hi) return MAVD_OK;
         ProfScope ps(&H->prof, MAVD_PROF_PYRAMID, st);
         const int Wp = round_up(W, 4);
         PyrDesc d;
-        d.n = H->n_levels - 1;
+        d.n = hi - lo + 1;
         int vb = 0, hb = 0;
-        for (int li = 1; li < H->n_levels; ++li) {
+        for (int li = lo; li <= hi; ++li) {
             const Level& L = H->lv[li];
-            PyrLevel& P = d.lv[li - 1];
+            PyrLevel& P = d.lv[li - lo];
             P.w = L.w; P.h = L.h; P.pitch = L.pitch; P.taps = round_up(L.ksz + 1, 4);
             P.xbase = L.xbase; P.xtab = L.xtab; P.ybase = L.ybase; P.ytab = L.ytab;
             P.tmp = L.tmp; P.img = L.img; P.tmp_stride = (size_t)L.h * Wp; P.img_stride = L.plane;
@@ -1220,11 +1221,12 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
     // high-priority side stream while the caller's stream does the two big expansions, and join before level 1's
     // matrices need the level-2 flow.  Stream order as seen by the caller is unchanged.
     const bool fork = H->n_levels >= 3 && H->s_aux != nullptr && H->overlap_mode != 0;
+    const int top_level = H->n_levels - 1;
     if (fork && H->overlap_mode == 2) {
         // the pyramid too goes to the side stream: level 0's expansion reads only the u8 frames
         MAVD_CUDA(cudaEventRecord(H->ev_fork, s));
         MAVD_CUDA(cudaStreamWaitEvent(H->s_aux, H->ev_fork, 0));
-        TRY_RC(build_pyramid(H->s_aux));
+        TRY_RC(build_pyramid(H->s_aux, 1, top_level));
         MAVD_CUDA(cudaEventRecord(H->ev_pyr, H->s_aux));
         for (int li = H->n_levels - 1; li >= 2; --li) {
             TRY_RC(expand_level(li, H->s_aux));
@@ -1238,7 +1240,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         TRY_RC(solve_level(1, s));
         TRY_RC(solve_level(0, s));
     } else if (fork) {
-        TRY_RC(build_pyramid(s));
+        TRY_RC(build_pyramid(s, 1, top_level));
         MAVD_CUDA(cudaEventRecord(H->ev_fork, s));
         MAVD_CUDA(cudaStreamWaitEvent(H->s_aux, H->ev_fork, 0));
         for (int li = H->n_levels - 1; li >= 2; --li) {
@@ -1252,7 +1254,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         TRY_RC(solve_level(1, s));
         TRY_RC(solve_level(0, s));
     } else {
-        TRY_RC(build_pyramid(s));
+        TRY_RC(build_pyramid(s, 1, top_level));
         for (int li = H->n_levels - 1; li >= 0; --li) {
             TRY_RC(expand_level(li, s));
             TRY_RC(solve_level(li, s));
