@@ -278,6 +278,9 @@ typedef struct mavd_profile {
 } mavd_profile;
 int mavd_profile_enable(mavd_handle h, int32_t on); /* also clears the counters */
 int mavd_profile_read(mavd_handle h, mavd_profile* out); /* waits for the recorded events */
+/* Start / end of every timed launch group recorded since enable, relative to the first one, as (class, start ms,
+ * end ms) triples in launch order (does not clear the records).  For timeline views of the two-stream schedule. */
+int mavd_profile_timeline(mavd_handle h, double* out, int32_t max_records, int32_t* n_out);
 
 /* Tests: route the Farneback iterations through the generic (non-TMA) kernel, which production uses only
  * for Gaussian windows and for winsize/2 outside 5..8. */

@@ -103,6 +103,7 @@ SIGNATURES = {
     'mavd_debug_force_exact_residual': (C.c_int, [_P, C.c_int32]),
     'mavd_profile_enable': (C.c_int, [_P, C.c_int32]),
     'mavd_profile_read': (C.c_int, [_P, C.POINTER(Profile)]),
+    'mavd_profile_timeline': (C.c_int, [_P, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_int32)]),
 }
 
 _lib: Optional[C.CDLL] = None

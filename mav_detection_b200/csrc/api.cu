@@ -452,6 +452,26 @@ int mavd_profile_read(mavd_handle h, mavd_profile* out) {
     return MAVD_OK;
 }
 
+int mavd_profile_timeline(mavd_handle h, double* out, int32_t max_records, int32_t* n_out) {
+    MAVD_REQUIRE(h && out && n_out, MAVD_ERR_INVALID, "profile_timeline: NULL argument");
+    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    int n = 0;
+    if (!h->prof.recs.empty()) {
+        cudaEvent_t base = h->prof.recs[0].a;
+        for (auto& r : h->prof.recs) {
+            if (n >= max_records) break;
+            MAVD_CUDA(cudaEventSynchronize(r.b));
+            float t0 = 0.f, t1 = 0.f;
+            MAVD_CUDA(cudaEventElapsedTime(&t0, base, r.a));
+            MAVD_CUDA(cudaEventElapsedTime(&t1, base, r.b));
+            out[3 * n] = r.cls; out[3 * n + 1] = t0; out[3 * n + 2] = t1;
+            ++n;
+        }
+    }
+    *n_out = n;
+    return MAVD_OK;
+}
+
 int mavd_debug_force_generic_iteration(mavd_handle h, int32_t on) {
     MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "handle is NULL");
     h->force_generic_iter = on != 0;
@@ -743,7 +763,8 @@ static int submit_host_impl(mavd_handle h, int32_t slot, const uint8_t* h_frames
     if (h_sky) MAVD_CUDA(cudaMemcpyAsync(S.d_sky, h_sky, sky_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, h->s_in));
     if (h_seg) MAVD_CUDA(cudaMemcpyAsync(S.d_seg, h_seg, seg_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, h->s_in));
     MAVD_CUDA(cudaEventRecord(S.ev_in, h->s_in));
-    // compute stream (the caller's)
+    // compute stream (the caller's).  (Running the detection stages of a batch on a second stream, concurrently with
+    // the next batch's Farneback, was measured: no gain, the GPU is already full and the work is only re-ordered.)
     MAVD_CUDA(cudaStreamWaitEvent(s, S.ev_in, 0));
     TRY(mavd_process(h, S.d_frames, n_pairs, pair_stride, h_imu, prm, S.d_samples, h_sky ? S.d_sky : nullptr, sky_stride,
                      h_seg ? S.d_seg : nullptr, seg_stride, h_flow_out ? S.d_flow : nullptr, nullptr, S.d_fixed,

@@ -385,6 +385,15 @@ class Engine:
         check(self.lib.mavd_profile_read(self._h, C.byref(prof)))
         return {n: (prof.ms[i], int(prof.launches[i])) for i, n in enumerate(_lib.PROF_NAMES)}
 
+    def profile_timeline(self, max_records: int = 4096):
+        """[(kernel class, start ms, end ms)] of every timed launch group since profile_enable(), in launch order."""
+        buf = (C.c_double * (3 * max_records))()
+        n = C.c_int32()
+        check(self.lib.mavd_profile_timeline(self._h, buf, max_records, C.byref(n)))
+        names = _lib.PROF_NAMES
+        return [(names[int(buf[3 * i])] if int(buf[3 * i]) < len(names) else str(int(buf[3 * i])), buf[3 * i + 1],
+                 buf[3 * i + 2]) for i in range(n.value)]
+
     def launch_count(self) -> int:
         return int(self.lib.mavd_launch_count())
 
