@@ -20,6 +20,11 @@ detect_np      NumPy restatement of derotate / get_FOE_dense / ransac / get_phi 
                im_helpers.py:55-84,150-159,244-252, utils.py:183-197).
                Pinned against the reference modules imported in this container
                (tests/golden/make_golden.py writes the vectors).
+vis_np         the HSV visualisation Farneback.process() returns
+               (/root/reference/src/farneback.py:83-99): the reference's own cv2
+               statement sequence, plus a NumPy restatement of the arithmetic cv2
+               4.13.0 performs, pinned bit-exactly against it
+               (tests/test_oracle_vis.py).
 ccl_np         8-connected component labelling with raster-first-appearance
                label numbering.  NOT a reference feature: parity
                for labels is "unpinned by the reference"; the oracle is pinned
