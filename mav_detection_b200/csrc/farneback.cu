@@ -777,14 +777,22 @@ __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h,
 // UpdateMatrices with the R1 footprint read from a shared-memory box [5][RH][RW] whose cell (0, 0) is image pixel
 // (bx, by); footprints that leave the box fall back to global loads.  Same operations, same order as
 // update_matrices_fast: identical results.
+struct R0Px { float y, x, yy, xx, xy; };     // the five expansion coefficients of one pixel of the first frame
+
+__device__ __forceinline__ R0Px load_r0(const float* __restrict__ R0, int o, int plane) {
+    R0Px r;
+    r.y = __ldg(R0 + o); r.x = __ldg(R0 + (o + plane)); r.yy = __ldg(R0 + (o + 2 * plane));
+    r.xx = __ldg(R0 + (o + 3 * plane)); r.xy = __ldg(R0 + (o + 4 * plane));
+    return r;
+}
+
 template <int RW, int RH>
 __device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, int pitch, int plane, bool edge, float dx,
-                                                    float dy, const float* __restrict__ R0, const float* __restrict__ R1,
+                                                    float dy, const R0Px& r0, const float* __restrict__ R1,
                                                     float* __restrict__ Mout, const float* box, int bx, int by) {
     constexpr int CH = RH * RW;
     const int o = y * pitch + x;
-    const float r0y = __ldg(R0 + o), r0x = __ldg(R0 + (o + plane)), r0yy = __ldg(R0 + (o + 2 * plane)),
-                r0xx = __ldg(R0 + (o + 3 * plane)), r0xy = __ldg(R0 + (o + 4 * plane));
+    const float r0y = r0.y, r0x = r0.x, r0yy = r0.yy, r0xx = r0.xx, r0xy = r0.xy;
     float fx = (float)x + dx, fy = (float)y + dy;
     const float flx = floorf(fx), fly = floorf(fy);
     const int x1 = (int)fminf(fmaxf(flx, -2.f), 1.0e6f), y1 = (int)fminf(fmaxf(fly, -2.f), 1.0e6f);
@@ -995,14 +1003,24 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
             mbar_expect_tx(&bar, 5 * CH * (uint32_t)sizeof(float));
             tma_load_3d(box, &tmapRbox, bx, by, (p * a.pair_stride + 1) * 5, &bar);
         }
+        // R0 of the first pixel is requested before waiting for the box, and R0 of pixel j + 1 while pixel j is being
+        // worked on: the (L2-prefetched) loads are never waited for
+        const int cxp = tid & 63, xp = x0 + cxp;
+        const bool col_ok = xp < w;
+        auto r0_of = [&](int j) {
+            const int y = y0 + ((j * NT + tid) >> 6);
+            return (col_ok && y < h) ? load_r0(R0, y * pitch + xp, plane) : R0Px{0.f, 0.f, 0.f, 0.f, 0.f};
+        };
+        R0Px cur = r0_of(0);
         mbar_wait(&bar, 1);
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {     // fully unrolled: ffx / ffy stay in registers
-            const int idx = j * NT + tid;
-            const int cx = idx & 63, r = idx >> 6;
-            const int x = x0 + cx, y = y0 + r;
-            if (x >= w || y >= h) continue;
-            update_matrices_box<RW, RH>(x, y, w, h, pitch, plane, edge, ffx[j], ffy[j], R0, R1, Mout, box, bx, by);
+            const int y = y0 + ((j * NT + tid) >> 6);
+            R0Px nxt = cur;
+            if (j + 1 < PPT) nxt = r0_of(j + 1);
+            if (col_ok && y < h)
+                update_matrices_box<RW, RH>(xp, y, w, h, pitch, plane, edge, ffx[j], ffy[j], cur, R1, Mout, box, bx, by);
+            cur = nxt;
         }
         return;
     }
