@@ -363,6 +363,7 @@ struct ResidualArgs {
     uint8_t* total_out;
     uint8_t* fixed_out;
     char* stats_base; size_t stats_stride;
+    int* chunk_flags; int n_chunks;   // nullable: occupancy of the fixed mask per 4096-pixel chunk (see ccl_*)
 };
 
 __device__ __forceinline__ unsigned long long dmax_key(double v) { return (unsigned long long)__double_as_longlong(v); }
@@ -506,11 +507,14 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
         // every mode is launched over the whole batch; each handles only its own frames
         if ((im.derotate != 0) != (MODE == 0)) return;
         if (MODE == 0) {
-            dr.o0 = __ddiv_rn(im.ang[0], im.dt);
-            dr.o1 = __ddiv_rn(im.ang[1], im.dt);
-            dr.o2 = __ddiv_rn(im.ang[2], im.dt);
-            dr.s0 = __ddiv_rn(__dmul_rn((double)A.w, im.dt), 2.0);
-            dr.s1 = __ddiv_rn(__dmul_rn((double)A.h, im.dt), 2.0);
+            // the five float64 divisions are done once per block (one thread each), not once per thread: they were
+            // 150 of the ~2200 instructions a thread executes
+            __shared__ double s_dr[5];
+            if (threadIdx.x < 3) s_dr[threadIdx.x] = __ddiv_rn(im.ang[threadIdx.x], im.dt);
+            else if (threadIdx.x == 3) s_dr[3] = __ddiv_rn(__dmul_rn((double)A.w, im.dt), 2.0);
+            else if (threadIdx.x == 4) s_dr[4] = __ddiv_rn(__dmul_rn((double)A.h, im.dt), 2.0);
+            __syncthreads();
+            dr.o0 = s_dr[0]; dr.o1 = s_dr[1]; dr.o2 = s_dr[2]; dr.s0 = s_dr[3]; dr.s1 = s_dr[4];
             // omega == 0 and finite scales: the derotation field is exactly (+-)0 and flow - 0 == flow
             dr.on = !(dr.o0 == 0.0 && dr.o1 == 0.0 && dr.o2 == 0.0 && fabs(dr.s0) < 1e300 && fabs(dr.s1) < 1e300);
         }
@@ -616,6 +620,12 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
             }
             totw |= (mt ? 1u : 0u) << (8 * k);
             fixw |= (mf ? 1u : 0u) << (8 * k);
+        }
+        if (A.chunk_flags && fixw) {
+            // tell the labelling which chunks of the fixed mask hold foreground (sparse: a handful of atomics per frame)
+            int* fl = A.chunk_flags + (size_t)f * A.n_chunks + (i0 >> 12);
+            const int bit = 1 << ((i0 >> 7) & 31);           // 128-pixel unit of the 4096-pixel chunk
+            if ((*reinterpret_cast<volatile int*>(fl) & bit) == 0) atomicOr(fl, bit);
         }
         if (want_stats) {
             // counts on whole words: mask bytes are 0/1, segmentation bytes are tested with per-byte compares
@@ -766,7 +776,8 @@ static int launch_residual(const ResidualArgs& A, const FastPrm& fp, int n, bool
 int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu,
                  const mavd_detect_params& p, const double* d_foe, const uint8_t* d_sky, int64_t sky_stride,
                  const uint8_t* d_seg, int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed,
-                 mavd_frame_stats* d_stats, size_t stats_stride, int run_f64, int run_f32, cudaStream_t s) {
+                 mavd_frame_stats* d_stats, size_t stats_stride, int run_f64, int run_f32, cudaStream_t s,
+                 int* d_chunk_flags) {
     ProfScope ps(&H->prof, MAVD_PROF_RESIDUAL, s);
     const int w = H->cfg.width, h = H->cfg.height;
     const int64_t npx = (int64_t)w * h;
@@ -791,6 +802,7 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
     A.sky = d_sky; A.sky_stride = sky_stride; A.seg = d_seg; A.seg_stride = seg_stride; A.seg_max = seg_max;
     A.phi_out = d_phi; A.total_out = d_total; A.fixed_out = d_fixed;
     A.stats_base = (char*)d_stats; A.stats_stride = stats_stride;
+    A.chunk_flags = d_fixed ? d_chunk_flags : nullptr; A.n_chunks = ccl_n_chunks(H);
     auto gate_guard = [](double t) { const double g = 1e-5 * (t > 1.0 ? t : 1.0); return (float)(2.0 * t * g + g * g); };
     const double fixed_rad = p.fixed_angle * (3.14159265358979323846 / 180.0);
     const FastPrm fp{(float)(p.dyn_offset + p.dyn_base), (float)p.dyn_gain,
@@ -1015,7 +1027,27 @@ int flow_vis_run(const float* d_flow, int64_t n, uint8_t* d_bgr, uint32_t* d_scr
 // written only when the caller asks for it.  VEC = 1 (one pixel per thread) covers widths that are
 // not a multiple of 4 and unaligned masks.
 // ------------------------------------------------------------------------------------------------
+// find with path halving (as in ECL-CC): every node passed on the way is re-pointed at its grandparent with a plain
+// store.  Safe next to the concurrent atomicMin links of uf_union: a stored value is always an ancestor of the node
+// (same set) with a smaller index (no cycles), and a link that such a store overwrites was only ever made redundant by
+// uf_union continuing with the node's previous parent.  Tall thin structures (a column of pixels links into a chain as
+// long as the column) are what makes this matter: without it every find walks the whole chain through L2.
 __device__ __forceinline__ int uf_find(int* parent, int i) {
+    int cur = parent[i];
+    if (cur != i) {
+        int prev = i, next;
+        while (cur > (next = parent[cur])) {
+            parent[prev] = next;
+            prev = cur;
+            cur = next;
+        }
+    }
+    return cur;
+}
+
+// read-only find for the flatten pass: there every pixel is finally pointed at its ROOT, and a halving store from another
+// thread landing after that write would leave a pixel on a mere ancestor
+__device__ __forceinline__ int uf_find_ro(const int* parent, int i) {
     int p = parent[i];
     while (p != i) {
         i = p;
@@ -1042,23 +1074,94 @@ __device__ __forceinline__ unsigned load_mask_word(const uint8_t* __restrict__ m
     return m[i0];
 }
 
+constexpr int CCL_CHUNK = 4096;  // pixels per chunk task (256 threads x 4 words of 4 pixels)
+constexpr int CCL_TPB = 8;       // consecutive chunk tasks per block
+
+// Every pass walks "chunk tasks" t = frame * n_chunks + chunk, CCL_TPB consecutive tasks per block.  flags[t] is a
+// 32-bit occupancy mask of the chunk: bit u is set when the 128-pixel unit u of the chunk (the 32 words one warp loads
+// at once) holds a foreground pixel.  The producer of the mask fills the flags (residual_kernel, a few atomics per
+// frame) or, for a caller-supplied mask, the init pass does while it streams the mask once.  Every other pass reads
+// the flags of its tasks with one load, skips empty chunks and touches only the occupied units: on detection masks
+// (0.1 % foreground, 2 % of the units occupied) the labelling no longer streams the mask five times.
+struct CclTask {
+    size_t base;     // first pixel of the frame in the batch
+    int c0, c1;      // pixel range of the chunk inside the frame
+};
+__device__ __forceinline__ CclTask ccl_task(int t, int n_chunks, int npx) {
+    const int f = t / n_chunks, c = t - f * n_chunks;
+    CclTask k;
+    k.base = (size_t)f * npx;
+    k.c0 = c * CCL_CHUNK;
+    k.c1 = min(k.c0 + CCL_CHUNK, npx);
+    return k;
+}
+constexpr int CCL_WPT = CCL_CHUNK / (256 * 4);   // words per thread and chunk on the VEC == 4 path
+
+// flags of the block's CCL_TPB tasks: one load per warp, lane l holds task t0 + l
+__device__ __forceinline__ unsigned ccl_block_flags(const int* __restrict__ flags, int t0, int n_tasks) {
+    const int l = threadIdx.x & 31;
+    return (l < CCL_TPB && t0 + l < n_tasks) ? (unsigned)flags[t0 + l] : 0u;
+}
+
+// the (up to) CCL_WPT mask words of this thread in chunk k, all requested before any is used; units whose occupancy
+// bit is clear are not read.  Word j of the thread is pixel k.c0 + (j * 256 + threadIdx.x) * 4, unit j * 8 + warp.
+__device__ __forceinline__ void ccl_load_words(const uint8_t* __restrict__ m, const CclTask& k, unsigned bits,
+                                               unsigned (&wv)[CCL_WPT]) {
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < CCL_WPT; ++j) {
+        const int i0 = k.c0 + (j * 256 + threadIdx.x) * 4;
+        wv[j] = (((bits >> (j * 8 + warp)) & 1u) && i0 < k.c1) ? load_mask_word<4>(m, i0) : 0u;
+    }
+}
+
 // init: every foreground pixel points at the first pixel of its run INSIDE its 4-pixel word, so the links between
 // horizontally adjacent pixels of a word never touch memory again (the run start has the smallest raster index of
 // the run, consistent with "smaller index = root")
 template <int VEC>
-__global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int npx) {
-    const size_t base = (size_t)blockIdx.y * npx;
-    const int ngrp = npx / VEC;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ngrp; q += gridDim.x * blockDim.x) {
-        const int i0 = q * VEC;
-        const unsigned wv = load_mask_word<VEC>(mask + base, i0);
-        if (wv == 0) continue;
-        int start = 0;
+__global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int npx,
+                                                      int n_chunks, int n_tasks, int* __restrict__ flags,
+                                                      int flags_ready) {
+    __shared__ unsigned s_bits;
+    const int t0 = blockIdx.x * CCL_TPB;
+    const unsigned mine = flags_ready ? ccl_block_flags(flags, t0, n_tasks) : 0u;
+    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
+        const int t = t0 + tt;
+        const unsigned bits = flags_ready ? __shfl_sync(0xffffffffu, mine, tt) : 0xffffffffu;
+        if (bits == 0) continue;                      // the producer of the mask already knows the chunk is empty
+        const CclTask k = ccl_task(t, n_chunks, npx);
+        if (!flags_ready) {
+            if (threadIdx.x == 0) s_bits = 0;
+            __syncthreads();
+        }
+        if (VEC == 4) {
+            unsigned wv[CCL_WPT];
+            ccl_load_words(mask + k.base, k, bits, wv);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            const bool fg = ((wv >> (8 * k)) & 255u) != 0;
-            if (!fg) { start = k + 1; continue; }
-            parent[base + i0 + k] = i0 + start;
+            for (int j = 0; j < CCL_WPT; ++j) {
+                if (!flags_ready) {
+                    const bool any = __any_sync(0xffffffffu, wv[j] != 0);
+                    if (any && (threadIdx.x & 31) == 0) atomicOr(&s_bits, 1u << (j * 8 + (threadIdx.x >> 5)));
+                }
+                if (wv[j] == 0) continue;
+                const int i0 = k.c0 + (j * 256 + threadIdx.x) * 4;
+                int start = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const bool fg = ((wv[j] >> (8 * b)) & 255u) != 0;
+                    if (!fg) { start = b + 1; continue; }
+                    parent[k.base + i0 + b] = i0 + start;
+                }
+            }
+        } else {
+            bool any = false;
+            for (int i = k.c0 + threadIdx.x; i < k.c1; i += 256)
+                if (mask[k.base + i]) { any = true; parent[k.base + i] = i; }
+            if (!flags_ready && any) atomicOr(&s_bits, 1u);       // one-pixel words: occupancy is not tracked per unit
+        }
+        if (!flags_ready) {
+            __syncthreads();
+            if (threadIdx.x == 0) flags[t] = (int)s_bits;
         }
     }
 }
@@ -1068,16 +1171,8 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict
 //   up     every upper-row run that touches columns s-1 .. e+1 (8-connectivity) is joined once, at its first
 //          pixel inside that column range
 template <int VEC>
-__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w, int h) {
-    const int npx = w * h;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= npx / VEC) return;
-    const size_t base = (size_t)blockIdx.y * npx;
-    const uint8_t* m = mask + base;
-    const int i0 = q * VEC;
-    const unsigned wv = load_mask_word<VEC>(m, i0);
-    if (wv == 0) return;
-    int* par = parent + base;
+__device__ __forceinline__ void ccl_merge_word(const uint8_t* __restrict__ m, int* __restrict__ par, int w, int i0,
+                                               unsigned wv) {
     const int y = i0 / w, x0 = i0 - y * w;
     // bit k + 1 of `cur`: pixel k of this word is set; `up`: pixel k of the row above (bit 0 = the pixel up-left of
     // the word, bit VEC + 1 = the pixel up-right of it)
@@ -1110,35 +1205,82 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restric
     }
 }
 
-constexpr int CCL_CHUNK = 4096;  // pixels per block in the root-ranking passes
-
 template <int VEC>
-__global__ void __launch_bounds__(256) ccl_flatten_count_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent,
-                                                               int npx, int* __restrict__ chunk_cnt, int n_chunks) {
-    const size_t base = (size_t)blockIdx.y * npx;
-    int* par = parent + base;
-    const int c0 = blockIdx.x * CCL_CHUNK, c1 = min(c0 + CCL_CHUNK, npx);
-    int cnt = 0;
-    for (int i0 = c0 + threadIdx.x * VEC; i0 < c1; i0 += 256 * VEC) {
-        const unsigned wv = load_mask_word<VEC>(mask + base, i0);
-        if (wv == 0) continue;
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w,
+                                                       int npx, int n_chunks, int n_tasks,
+                                                       const int* __restrict__ flags) {
+    const int t0 = blockIdx.x * CCL_TPB;
+    const unsigned mine = ccl_block_flags(flags, t0, n_tasks);
+    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
+        const unsigned bits = __shfl_sync(0xffffffffu, mine, tt);
+        if (bits == 0) continue;
+        const CclTask k = ccl_task(t0 + tt, n_chunks, npx);
+        const uint8_t* m = mask + k.base;
+        int* par = parent + k.base;
+        if (VEC == 4) {
+            unsigned wv[CCL_WPT];
+            ccl_load_words(m, k, bits, wv);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            if (!((wv >> (8 * k)) & 255u)) continue;
-            const int i = i0 + k;
-            const int r = uf_find(par, i);
-            par[i] = r;   // benign race: every writer stores a valid ancestor, roots never change here
-            cnt += (r == i);
+            for (int j = 0; j < CCL_WPT; ++j)
+                if (wv[j]) ccl_merge_word<4>(m, par, w, k.c0 + (j * 256 + threadIdx.x) * 4, wv[j]);
+        } else {
+            for (int i0 = k.c0 + threadIdx.x; i0 < k.c1; i0 += 256) {
+                const unsigned wv = m[i0];
+                if (wv) ccl_merge_word<1>(m, par, w, i0, wv);
+            }
         }
     }
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
+}
+
+// flatten + count roots per chunk (chunk_cnt[t], 0 for empty chunks)
+template <int VEC>
+__global__ void __launch_bounds__(256) ccl_flatten_count_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent,
+                                                               int npx, int* __restrict__ chunk_cnt, int n_chunks,
+                                                               int n_tasks, const int* __restrict__ flags) {
     __shared__ int wsum[8];
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int k = 0; k < 8; ++k) t += wsum[k];
-        chunk_cnt[(size_t)blockIdx.y * n_chunks + blockIdx.x] = t;
+    const int t0 = blockIdx.x * CCL_TPB;
+    const unsigned mine = ccl_block_flags(flags, t0, n_tasks);
+    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
+        const int t = t0 + tt;
+        const unsigned bits = __shfl_sync(0xffffffffu, mine, tt);
+        if (bits == 0) {
+            if (threadIdx.x == 0) chunk_cnt[t] = 0;
+            continue;
+        }
+        const CclTask k = ccl_task(t, n_chunks, npx);
+        int* par = parent + k.base;
+        int cnt = 0;
+        auto flatten_word = [&](int i0, unsigned wv) {
+#pragma unroll
+            for (int b = 0; b < VEC; ++b) {
+                if (!((wv >> (8 * b)) & 255u)) continue;
+                const int i = i0 + b;
+                const int r = uf_find_ro(par, i);
+                par[i] = r;   // benign race: every writer stores a valid ancestor, roots never change here
+                cnt += (r == i);
+            }
+        };
+        if (VEC == 4) {
+            unsigned wv[CCL_WPT];
+            ccl_load_words(mask + k.base, k, bits, wv);
+#pragma unroll
+            for (int j = 0; j < CCL_WPT; ++j)
+                if (wv[j]) flatten_word(k.c0 + (j * 256 + threadIdx.x) * 4, wv[j]);
+        } else {
+            for (int i0 = k.c0 + threadIdx.x; i0 < k.c1; i0 += 256) {
+                const unsigned wv = mask[k.base + i0];
+                if (wv) flatten_word(i0, wv);
+            }
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int j = 0; j < 8; ++j) tot += wsum[j];
+            chunk_cnt[t] = tot;
+        }
+        __syncthreads();      // wsum is reused by the block's next task
     }
 }
 
@@ -1181,54 +1323,72 @@ __global__ void __launch_bounds__(1024) ccl_scan_kernel(int* __restrict__ chunk_
     if (threadIdx.x == 0) *reinterpret_cast<int32_t*>(nlabels_base + (size_t)blockIdx.x * nlabels_stride) = carry_s;
 }
 
-// rank[root] = canonical label of the component rooted at `root` (roots ordered by raster index)
+// rank[root] = canonical label of the component rooted at `root` (roots ordered by raster index).  The raster order
+// inside a chunk is word j = 0..3 of thread 0..255, so the prefix runs over (j, thread).
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_rank_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ parent,
                                                       int npx, const int* __restrict__ chunk_off, int n_chunks,
+                                                      int n_tasks, const int* __restrict__ flags,
                                                       int* __restrict__ rank) {
-    const size_t base = (size_t)blockIdx.y * npx;
-    const int* par = parent + base;
-    int* rk = rank + base;
-    const int c0 = blockIdx.x * CCL_CHUNK, c1 = min(c0 + CCL_CHUNK, npx);
     __shared__ int wsum[8];
     __shared__ int running;
-    if (threadIdx.x == 0) running = chunk_off[(size_t)blockIdx.y * n_chunks + blockIdx.x];
-    __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int s0 = c0; s0 < c1; s0 += 256 * VEC) {
-        const int i0 = s0 + threadIdx.x * VEC;
-        unsigned roots = 0;   // bit k: pixel i0 + k is a root
-        if (i0 < c1) {
-            const unsigned wv = load_mask_word<VEC>(mask + base, i0);
-            if (wv) {
+    const int t0 = blockIdx.x * CCL_TPB;
+    const unsigned mine_f = ccl_block_flags(flags, t0, n_tasks);
+    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
+        const int t = t0 + tt;
+        const unsigned bits = __shfl_sync(0xffffffffu, mine_f, tt);
+        if (bits == 0) continue;
+        const CclTask k = ccl_task(t, n_chunks, npx);
+        const int* par = parent + k.base;
+        int* rk = rank + k.base;
+        if (threadIdx.x == 0) running = chunk_off[t];
+        unsigned wv4[CCL_WPT];
+        if (VEC == 4) ccl_load_words(mask + k.base, k, bits, wv4);
+        __syncthreads();
+        constexpr int STEPS = VEC == 4 ? CCL_WPT : CCL_CHUNK / 256;
+        for (int j = 0; j < STEPS; ++j) {
+            const int i0 = k.c0 + (j * 256 + threadIdx.x) * VEC;
+            unsigned roots = 0;   // bit b: pixel i0 + b is a root
+            if (VEC == 4) {
+                // a run-time j would put wv4 in local memory: select with compares instead
+                unsigned wv = 0;
 #pragma unroll
-                for (int k = 0; k < VEC; ++k)
-                    if (((wv >> (8 * k)) & 255u) && par[i0 + k] == i0 + k) roots |= 1u << k;
+                for (int q = 0; q < CCL_WPT; ++q) wv = (q == j) ? wv4[q] : wv;
+                if (wv) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (((wv >> (8 * b)) & 255u) && par[i0 + b] == i0 + b) roots |= 1u << b;
+                }
+            } else if (i0 < k.c1) {
+                if (mask[k.base + i0] && par[i0] == i0) roots = 1u;
             }
-        }
-        const int mine = __popc(roots);
-        int incl = mine;
+            // whole step without a root (the common case): nothing to rank, `running` stays
+            if (!__syncthreads_or(roots != 0)) continue;
+            const int mine = __popc(roots);
+            int incl = mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) wsum[wid] = incl;
-        __syncthreads();
-        if (mine) {
-            int off = running + incl - mine;
-            for (int k = 0; k < wid; ++k) off += wsum[k];
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) wsum[wid] = incl;
+            __syncthreads();
+            if (mine) {
+                int off = running + incl - mine;
+                for (int q = 0; q < wid; ++q) off += wsum[q];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                if (roots & (1u << k)) rk[i0 + k] = ++off;
+                for (int b = 0; b < VEC; ++b)
+                    if (roots & (1u << b)) rk[i0 + b] = ++off;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = 0;
+                for (int q = 0; q < 8; ++q) tot += wsum[q];
+                running += tot;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int k = 0; k < 8; ++k) t += wsum[k];
-            running += t;
-        }
-        __syncthreads();
     }
 }
 
@@ -1240,37 +1400,56 @@ __global__ void ccl_boxes_init_kernel(int32_t* boxes, size_t boxes_stride, int m
     p[0] = 0x7fffffff; p[1] = 0x7fffffff; p[2] = -1; p[3] = -1; p[4] = 0;
 }
 
-// labels_out may alias parent (each thread reads only its own parent entries before writing them)
+// labels_out may alias parent (each thread reads only its own parent entries before writing them); empty chunks and
+// empty units get their zeros without a look at the mask
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_relabel_kernel(const uint8_t* __restrict__ mask, const int* parent,
-                                                         const int* __restrict__ rank, int w, int h, int* labels_out,
+                                                         const int* __restrict__ rank, int w, int npx, int n_chunks,
+                                                         int n_tasks, const int* __restrict__ flags, int* labels_out,
                                                          int32_t* __restrict__ boxes, size_t boxes_stride, int max_boxes) {
-    const int npx = w * h;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= npx / VEC) return;
-    const size_t base = (size_t)blockIdx.y * npx;
-    const int i0 = q * VEC;
-    const unsigned wv = load_mask_word<VEC>(mask + base, i0);
-    int lab[VEC];
+    const int t0 = blockIdx.x * CCL_TPB;
+    const unsigned mine = ccl_block_flags(flags, t0, n_tasks);
+    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
+        const int t = t0 + tt;
+        const unsigned bits = __shfl_sync(0xffffffffu, mine, tt);
+        if (bits == 0 && !labels_out) continue;
+        const CclTask k = ccl_task(t, n_chunks, npx);
+        const int f = t / n_chunks;
+        auto relabel_word = [&](int i0, unsigned wv) {
+            int lab[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) lab[k] = 0;
-    if (wv) {
-        const int y = i0 / w, x0 = i0 - y * w;
+            for (int b = 0; b < VEC; ++b) lab[b] = 0;
+            if (wv) {
+                const int y = i0 / w, x0 = i0 - y * w;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            if (!((wv >> (8 * k)) & 255u)) continue;
-            const int l = rank[base + parent[base + i0 + k]];
-            lab[k] = l;
-            if (boxes && l <= max_boxes) {
-                int32_t* b = boxes + (size_t)blockIdx.y * boxes_stride + (l - 1) * 5;
-                const int x = x0 + k;
-                atomicMin(b + 0, x); atomicMin(b + 1, y); atomicMax(b + 2, x); atomicMax(b + 3, y); atomicAdd(b + 4, 1);
+                for (int b = 0; b < VEC; ++b) {
+                    if (!((wv >> (8 * b)) & 255u)) continue;
+                    const int l = rank[k.base + parent[k.base + i0 + b]];
+                    lab[b] = l;
+                    if (boxes && l <= max_boxes) {
+                        int32_t* bx = boxes + (size_t)f * boxes_stride + (l - 1) * 5;
+                        const int x = x0 + b;
+                        atomicMin(bx + 0, x); atomicMin(bx + 1, y); atomicMax(bx + 2, x); atomicMax(bx + 3, y);
+                        atomicAdd(bx + 4, 1);
+                    }
+                }
             }
+            if (labels_out) {
+                if (VEC == 4) *reinterpret_cast<int4*>(labels_out + k.base + i0) = make_int4(lab[0], lab[VEC > 1 ? 1 : 0], lab[VEC > 2 ? 2 : 0], lab[VEC > 3 ? 3 : 0]);
+                else labels_out[k.base + i0] = lab[0];
+            }
+        };
+        if (VEC == 4) {
+            unsigned wv[CCL_WPT];
+            ccl_load_words(mask + k.base, k, bits, wv);
+#pragma unroll
+            for (int j = 0; j < CCL_WPT; ++j) {
+                const int i0 = k.c0 + (j * 256 + threadIdx.x) * 4;
+                if (i0 < k.c1 && (wv[j] || labels_out)) relabel_word(i0, wv[j]);
+            }
+        } else {
+            for (int i0 = k.c0 + threadIdx.x; i0 < k.c1; i0 += 256) relabel_word(i0, bits ? mask[k.base + i0] : 0u);
         }
-    }
-    if (labels_out) {
-        if (VEC == 4) *reinterpret_cast<int4*>(labels_out + base + i0) = make_int4(lab[0], lab[1], lab[2], lab[3]);
-        else labels_out[base + i0] = lab[0];
     }
 }
 
@@ -1285,29 +1464,32 @@ __global__ void ccl_boxes_final_kernel(int32_t* boxes, size_t boxes_stride, int 
 
 template <int VEC>
 static int ccl_launch(mavd_handle H, const uint8_t* d_mask, int n, int* parent, int32_t* labels_out, int32_t* d_boxes,
-                      size_t boxes_stride, int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s) {
+                      size_t boxes_stride, int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s,
+                      bool flags_ready) {
     const int w = H->cfg.width, h = H->cfg.height, npx = w * h;
     const int n_chunks = ceil_div(npx, CCL_CHUNK);
+    const int n_tasks = n * n_chunks;
     int* rank = H->d_scan;                                        // [n][npx], written and read at roots only
     int* chunk_cnt = H->d_scan + (size_t)H->cfg.max_pairs * npx;  // [n][n_chunks]
-    const int ngrp = npx / VEC;
-    ccl_init_kernel<VEC><<<dim3(min(ceil_div(ngrp, 256), 148 * 8), n), 256, 0, s>>>(d_mask, parent, npx);
+    int* flags = ccl_chunk_flags(H);                               // [n][n_chunks]: chunk holds foreground
+    const int g = ceil_div(n_tasks, CCL_TPB);
+    ccl_init_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, npx, n_chunks, n_tasks, flags, flags_ready ? 1 : 0);
     MAVD_LAUNCHED();
-    dim3 g(ceil_div(ngrp, 256), n);
-    ccl_merge_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, w, h);
+    ccl_merge_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, w, npx, n_chunks, n_tasks, flags);
     MAVD_LAUNCHED();
-    ccl_flatten_count_kernel<VEC><<<dim3(n_chunks, n), 256, 0, s>>>(d_mask, parent, npx, chunk_cnt, n_chunks);
+    ccl_flatten_count_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, npx, chunk_cnt, n_chunks, n_tasks, flags);
     MAVD_LAUNCHED();
     ccl_scan_kernel<<<n, 1024, 0, s>>>(chunk_cnt, n_chunks, (char*)d_n_labels, nlabels_stride);
     MAVD_LAUNCHED();
-    ccl_rank_kernel<VEC><<<dim3(n_chunks, n), 256, 0, s>>>(d_mask, parent, npx, chunk_cnt, n_chunks, rank);
+    ccl_rank_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, npx, chunk_cnt, n_chunks, n_tasks, flags, rank);
     MAVD_LAUNCHED();
     if (d_boxes) {
         ccl_boxes_init_kernel<<<ceil_div(n * max_boxes, 128), 128, 0, s>>>(d_boxes, boxes_stride, max_boxes, n);
         MAVD_LAUNCHED();
     }
     if (d_boxes || labels_out) {
-        ccl_relabel_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, rank, w, h, labels_out, d_boxes, boxes_stride, max_boxes);
+        ccl_relabel_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, rank, w, npx, n_chunks, n_tasks, flags, labels_out,
+                                                   d_boxes, boxes_stride, max_boxes);
         MAVD_LAUNCHED();
     }
     if (d_boxes) {
@@ -1317,17 +1499,23 @@ static int ccl_launch(mavd_handle H, const uint8_t* d_mask, int n, int* parent, 
     return MAVD_OK;
 }
 
+int ccl_n_chunks(mavd_handle H) { return ceil_div(H->cfg.width * H->cfg.height, CCL_CHUNK); }
+int* ccl_chunk_flags(mavd_handle H) {
+    const size_t npx = (size_t)H->cfg.width * H->cfg.height;
+    return H->d_scan + (size_t)H->cfg.max_pairs * npx + (size_t)H->cfg.max_pairs * ccl_n_chunks(H);
+}
+
 // d_labels: the caller's label image (also used as the union-find array), or NULL when only the
 // component count / boxes are wanted (the handle's scratch then holds the union-find array).
 int ccl_run(mavd_handle H, const uint8_t* d_mask, int n, int32_t* d_labels, int32_t* d_boxes, size_t boxes_stride,
-            int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s) {
+            int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s, bool flags_ready) {
     ProfScope ps(&H->prof, MAVD_PROF_CCL, s);
     const int w = H->cfg.width, h = H->cfg.height;
     int* parent = d_labels ? d_labels : H->d_labels;
     const bool vec4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_mask) & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(parent) & 15) == 0) && (((size_t)w * h) % 4 == 0);
-    if (vec4) return ccl_launch<4>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s);
-    return ccl_launch<1>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s);
+    if (vec4) return ccl_launch<4>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s, flags_ready);
+    return ccl_launch<1>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s, flags_ready);
 }
 
 }  // namespace mavd

@@ -435,32 +435,47 @@ __device__ __forceinline__ void resize_coord(int d, double scale, int src, int& 
     i0 = s;
 }
 
-template <bool TABLES>
+// COORD selects how the resize coordinates are obtained: 0 = recomputed with resize_coord's double operations,
+// 1 = read from the host-built tables, 2 = recomputed in float32, valid (and bit-identical) when both scales are
+// powers of two, e.g. 1920 -> 960: (d + 0.5) * 2^-k - 0.5 is then exact in float32 as well
+enum { MI_COORD_F64 = 0, MI_COORD_TABLES = 1, MI_COORD_POW2 = 2 };
+
+__device__ __forceinline__ void resize_coord_pow2(int d, float scale, int src, int& i0, float& a) {
+    const float f = __fsub_rn(__fmul_rn(__fadd_rn((float)d, 0.5f), scale), 0.5f);
+    int s = (int)floorf(f);
+    a = f - (float)s;
+    if (s < 0) { s = 0; a = 0.f; }
+    if (s >= src - 1) { s = src - 1; a = 0.f; }
+    i0 = s;
+}
+
+template <int COORD>
 __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
-                                                           int pitch, int pair_stride,
+                                                           int pitch, size_t R_pair_stride,
                                                            const float2* __restrict__ cflow, int cw, int ch,
                                                            int cpitch, size_t cflow_stride,
                                                            const int* __restrict__ fxi0,
                                                            const float* __restrict__ fxa,
                                                            const int* __restrict__ fyi0,
                                                            const float* __restrict__ fya, float up_scale,
-                                                           float* __restrict__ M, float2* __restrict__ flow_dbg,
-                                                           int flow_dbg_pitch, size_t flow_dbg_stride, int n_pairs,
-                                                           int tiles_x, double xscale, double yscale) {
-    // 1-D grid, pair index fastest (same L2 sharing of R between consecutive pairs as in iter_box_tma_kernel; one
-    // pixel per thread, so the index arithmetic is kept to two divisions: grouping the pairs costs more than it saves)
-    const int p = blockIdx.x % n_pairs, tile = blockIdx.x / n_pairs;
-    const int ty = tile / tiles_x;
-    const int x = (tile - ty * tiles_x) * 64 + (threadIdx.x & 63);
-    const int y = ty * 4 + (threadIdx.x >> 6);
+                                                           float* __restrict__ M, double xscale, double yscale) {
+    // 3-D grid (pairs, tiles_x, tiles_y): blocks are scheduled x-fastest, so the pair index is fastest (same L2 sharing
+    // of R between consecutive pairs as in iter_box_tma_kernel) and no thread pays for an integer division: with one
+    // pixel per thread the two divisions of a 1-D grid were 55 of the kernel's 400 instructions
+    const int p = blockIdx.x;
+    const int x = blockIdx.y * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.z * 4 + (threadIdx.x >> 6);
     if (x >= w || y >= h) return;
     float dx = 0.f, dy = 0.f;
     if (cflow) {
         const float2* cf = cflow + (size_t)p * cflow_stride;
         int xa0, ya0;
         float ax, ay;
-        if (TABLES) {
+        if (COORD == MI_COORD_TABLES) {
             xa0 = fxi0[x]; ya0 = fyi0[y]; ax = fxa[x]; ay = fya[y];
+        } else if (COORD == MI_COORD_POW2) {
+            resize_coord_pow2(x, (float)xscale, cw, xa0, ax);
+            resize_coord_pow2(y, (float)yscale, ch, ya0, ay);
         } else {
             // one dependent memory round trip less than reading the tables
             resize_coord(x, xscale, cw, xa0, ax);
@@ -474,8 +489,7 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
         dx = (tx0 * (1.f - ay) + tx1 * ay) * up_scale;
         dy = (ty0 * (1.f - ay) + ty1 * ay) * up_scale;
     }
-    if (flow_dbg) flow_dbg[(size_t)p * flow_dbg_stride + (size_t)y * flow_dbg_pitch + x] = make_float2(dx, dy);
-    const float* R0 = R + (size_t)(p * pair_stride) * 5 * plane;
+    const float* R0 = R + (size_t)p * R_pair_stride;
     // One pixel per thread at 32 registers (full occupancy) is the fastest form measured: the 32-bit-offset
     // UpdateMatrices of the fused iteration (> 32 registers: 0.87 vs 0.675 ms per 16-pair step) and variants with
     // 8 pixels per thread that halve the instruction count (2.45-2.67 vs 2.22 ms per 64-pair step), and a tiled
@@ -1183,12 +1197,18 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             const bool top = (li == H->n_levels - 1);
             const Level* C = top ? nullptr : &H->lv[li + 1];
             static const bool tables = getenv("MAVD_MAT_TABLES") && getenv("MAVD_MAT_TABLES")[0] == '1';
+            static const bool no_pow2 = getenv("MAVD_MAT_POW2") && getenv("MAVD_MAT_POW2")[0] == '0';
             const double xscale = top ? 1.0 : 1.0 / ((double)L.w / C->w), yscale = top ? 1.0 : 1.0 / ((double)L.h / C->h);
-#define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, pair_stride, top ? nullptr : (const float2*)C->flow,                    \
-                top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch, top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0,          \
-                L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], nullptr, 0, 0, n_pairs, (int)g.x, xscale, yscale
-            if (tables) matrices_init_kernel<true><<<dim3(g.x * g.y * g.z), 256, 0, st>>>(MI_ARGS);
-            else matrices_init_kernel<false><<<dim3(g.x * g.y * g.z), 256, 0, st>>>(MI_ARGS);
+            auto is_pow2 = [](double v) { int e; return v > 0.0 && frexp(v, &e) == 0.5 && e > -20 && e <= 1; };
+            const int coord = tables ? MI_COORD_TABLES
+                                     : (!no_pow2 && is_pow2(xscale) && is_pow2(yscale)) ? MI_COORD_POW2 : MI_COORD_F64;
+            const dim3 g3(g.z, g.x, g.y);       // pair index fastest
+#define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, (size_t)pair_stride * 5 * L.plane,                                     \
+                top ? nullptr : (const float2*)C->flow, top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch,             \
+                top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale
+            if (coord == MI_COORD_TABLES) matrices_init_kernel<MI_COORD_TABLES><<<g3, 256, 0, st>>>(MI_ARGS);
+            else if (coord == MI_COORD_POW2) matrices_init_kernel<MI_COORD_POW2><<<g3, 256, 0, st>>>(MI_ARGS);
+            else matrices_init_kernel<MI_COORD_F64><<<g3, 256, 0, st>>>(MI_ARGS);
 #undef MI_ARGS
             MAVD_LAUNCHED();
         }
