@@ -361,7 +361,7 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
     C_TRY(A.alloc(&H->d_foe, 2 * (size_t)B));
     C_TRY(A.alloc(&H->d_ninter, B));
     C_TRY(A.alloc(&H->d_labels, B * npx));
-    C_TRY(A.alloc(&H->d_scan, B * npx + 2 * (size_t)B * (npx / 4096 + 2) + 64));   // rank, chunk counts, chunk flags
+    C_TRY(A.alloc(&H->d_scan, B * npx + 2 * (size_t)B * (npx / 128 + 2) + 64));   // rank, unit counts, unit list (ccl_*)
     C_TRY(A.alloc(&H->d_total, B * npx));
     C_TRY(A.alloc(&H->d_fixed, B * npx));
     C_TRY(A.alloc(&H->d_flow, B * npx * 2));
@@ -668,13 +668,12 @@ static int detect_run(mavd_handle h, const float* flow, int n, const mavd_detect
                       cudaStream_t s) {
     TRY(foe_run(h, flow, 0, n, h->d_imu, p, d_samples, h->d_foe, h->d_ninter, s));
     char* stats0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, stats);
-    // the residual kernel marks the 4096-pixel chunks of the fixed mask that hold foreground; the labelling passes
-    // then visit only those (detection masks are almost empty)
-    int* chunk_flags = ccl_chunk_flags(h);
-    MAVD_CUDA(cudaMemsetAsync(chunk_flags, 0, sizeof(int) * (size_t)n * ccl_n_chunks(h), s));
+    // the residual kernel lists the 128-pixel units of the fixed mask that hold foreground; the labelling passes then
+    // visit only those (detection masks are almost empty)
+    TRY(ccl_list_reset(h, n, s));
     TRY(residual_run(h, flow, 0, n, h->d_imu, p, h->d_foe, d_sky, sky_stride, d_seg, seg_stride, nullptr, d_total_out,
                      fixed, reinterpret_cast<mavd_frame_stats*>(stats0), sizeof(mavd_frame_record), n64 > 0, n32 > 0, s,
-                     chunk_flags));
+                     true));
     int32_t* boxes0 = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, boxes));
     char* nl0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, n_labels);
     TRY(ccl_run(h, fixed, n, nullptr, boxes0, sizeof(mavd_frame_record) / sizeof(int32_t), MAVD_MAX_BOXES,

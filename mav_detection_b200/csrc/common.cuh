@@ -182,16 +182,18 @@ int gather_max_phi_run(const mavd_frame_stats* d_stats, int n, double* d_out, cu
 int residual_run(mavd_handle h, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu, const mavd_detect_params& prm,
                  const double* d_foe, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
                  int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
-                 size_t stats_stride_bytes, int run_f64, int run_f32, cudaStream_t s, int* d_chunk_flags = nullptr);
-// per-chunk occupancy flags of the labelling passes ([max_pairs][ccl_n_chunks] ints in the handle's scratch): zeroed
-// by the caller and filled by residual_run (d_chunk_flags) while it writes the fixed mask, so that ccl_run
-// (flags_ready) never has to stream the mask to find the occupied chunks
-int* ccl_chunk_flags(mavd_handle h);
-int ccl_n_chunks(mavd_handle h);
+                 size_t stats_stride_bytes, int run_f64, int run_f32, cudaStream_t s, bool list_fixed_units = false);
+// The labelling passes walk a list of occupied 128-pixel units of the mask.  residual_run(list_fixed_units) appends the
+// units of the fixed mask while it writes it (after ccl_list_reset), so that ccl_run(list_ready) never streams the mask.
+int ccl_list_reset(mavd_handle h, int n, cudaStream_t s);
+int ccl_n_units(mavd_handle h);
+int* ccl_unit_marks(mavd_handle h);
+int* ccl_unit_list(mavd_handle h);
+int* ccl_unit_count(mavd_handle h);
 int magnitude_run(const void* d_flow, int is_f64, int64_t n, void* d_out, cudaStream_t s);
 int simple_bbox_run(const uint8_t* d_img, int w, int h, int c, int32_t* d_out5, cudaStream_t s);
 int tpr_fpr_run(const uint8_t* d_gt, const int64_t* d_img, int64_t n, int64_t* d_counts4, cudaStream_t s);
 int flow_vis_run(const float* d_flow, int64_t n, uint8_t* d_bgr, uint32_t* d_scratch3, cudaStream_t s);
 int ccl_run(mavd_handle h, const uint8_t* d_mask, int n, int32_t* d_labels, int32_t* d_boxes, size_t boxes_stride,
-            int max_boxes, int32_t* d_n_labels, size_t nlabels_stride_bytes, cudaStream_t s, bool flags_ready = false);
+            int max_boxes, int32_t* d_n_labels, size_t nlabels_stride_bytes, cudaStream_t s, bool list_ready = false);
 }  // namespace mavd

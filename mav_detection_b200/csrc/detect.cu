@@ -363,7 +363,7 @@ struct ResidualArgs {
     uint8_t* total_out;
     uint8_t* fixed_out;
     char* stats_base; size_t stats_stride;
-    int* chunk_flags; int n_chunks;   // nullable: occupancy of the fixed mask per 4096-pixel chunk (see ccl_*)
+    int* unit_marks; int* unit_list; int* unit_count; int n_units;   // nullable: list of occupied units of the fixed mask (see ccl_*)
 };
 
 __device__ __forceinline__ unsigned long long dmax_key(double v) { return (unsigned long long)__double_as_longlong(v); }
@@ -621,11 +621,11 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
             totw |= (mt ? 1u : 0u) << (8 * k);
             fixw |= (mf ? 1u : 0u) << (8 * k);
         }
-        if (A.chunk_flags && fixw) {
-            // tell the labelling which chunks of the fixed mask hold foreground (sparse: a handful of atomics per frame)
-            int* fl = A.chunk_flags + (size_t)f * A.n_chunks + (i0 >> 12);
-            const int bit = 1 << ((i0 >> 7) & 31);           // 128-pixel unit of the 4096-pixel chunk
-            if ((*reinterpret_cast<volatile int*>(fl) & bit) == 0) atomicOr(fl, bit);
+        if (A.unit_marks && fixw) {
+            // append the 128-pixel unit to the list the labelling passes walk (once per unit: the mark decides)
+            const int e = f * A.n_units + (i0 >> 7);
+            if (*reinterpret_cast<volatile int*>(A.unit_marks + e) == 0 && atomicExch(A.unit_marks + e, 1) == 0)
+                A.unit_list[atomicAdd(A.unit_count, 1)] = e;
         }
         if (want_stats) {
             // counts on whole words: mask bytes are 0/1, segmentation bytes are tested with per-byte compares
@@ -777,7 +777,7 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
                  const mavd_detect_params& p, const double* d_foe, const uint8_t* d_sky, int64_t sky_stride,
                  const uint8_t* d_seg, int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed,
                  mavd_frame_stats* d_stats, size_t stats_stride, int run_f64, int run_f32, cudaStream_t s,
-                 int* d_chunk_flags) {
+                 bool list_fixed_units) {
     ProfScope ps(&H->prof, MAVD_PROF_RESIDUAL, s);
     const int w = H->cfg.width, h = H->cfg.height;
     const int64_t npx = (int64_t)w * h;
@@ -802,7 +802,9 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
     A.sky = d_sky; A.sky_stride = sky_stride; A.seg = d_seg; A.seg_stride = seg_stride; A.seg_max = seg_max;
     A.phi_out = d_phi; A.total_out = d_total; A.fixed_out = d_fixed;
     A.stats_base = (char*)d_stats; A.stats_stride = stats_stride;
-    A.chunk_flags = d_fixed ? d_chunk_flags : nullptr; A.n_chunks = ccl_n_chunks(H);
+    const bool listing = list_fixed_units && d_fixed != nullptr;
+    A.unit_marks = listing ? ccl_unit_marks(H) : nullptr; A.unit_list = listing ? ccl_unit_list(H) : nullptr;
+    A.unit_count = listing ? ccl_unit_count(H) : nullptr; A.n_units = ccl_n_units(H);
     auto gate_guard = [](double t) { const double g = 1e-5 * (t > 1.0 ? t : 1.0); return (float)(2.0 * t * g + g * g); };
     const double fixed_rad = p.fixed_angle * (3.14159265358979323846 / 180.0);
     const FastPrm fp{(float)(p.dyn_offset + p.dyn_base), (float)p.dyn_gain,
@@ -1020,18 +1022,21 @@ int flow_vis_run(const float* d_flow, int64_t n, uint8_t* d_bgr, uint32_t* d_scr
 // Connected components (8-connectivity), union-find with the smaller raster index as the root, so a
 // component's root is its first pixel in raster order and ranking the roots gives canonical labels.
 //
-// Detection masks are sparse, so every pass scans the uint8 mask one 32-bit word (4 pixels) per
-// thread and does nothing for all-zero words; parent[] is only ever touched at foreground pixels
-// (background entries are never initialised nor read).  Passes: init -> merge -> flatten+count roots
-// per 4096-pixel chunk -> scan -> rank roots -> relabel (+ per-component boxes).  The label image is
-// written only when the caller asks for it.  VEC = 1 (one pixel per thread) covers widths that are
-// not a multiple of 4 and unaligned masks.
+// Detection masks are sparse (0.1 % foreground on the synthetic sequences, but spread over a third of
+// the image rows), so the passes do not scan the image: they walk a LIST of occupied 128-pixel units
+// (the 32 words of 4 pixels one warp loads at once), one warp per unit.  The list is appended to by
+// whoever produces the mask: residual_kernel while it writes the fixed mask (one atomic per occupied
+// unit), or ccl_list_kernel, which streams a caller-supplied mask once.  Passes over the list:
+// init -> merge -> flatten + count roots per unit -> scan of the unit counts (per frame) -> rank roots
+// -> relabel (+ per-component boxes).  parent[] is only ever touched at foreground pixels; a label
+// image, when the caller asks for one, is zero-filled up front and written at foreground pixels only.
+// VEC = 4: a lane owns one aligned word of 4 pixels of the same row; VEC = 1 (widths that are not a
+// multiple of 4, unaligned masks): a lane owns 4 single pixels, 32 apart.
 // ------------------------------------------------------------------------------------------------
 // find with path halving (as in ECL-CC): every node passed on the way is re-pointed at its grandparent with a plain
 // store.  Safe next to the concurrent atomicMin links of uf_union: a stored value is always an ancestor of the node
 // (same set) with a smaller index (no cycles), and a link that such a store overwrites was only ever made redundant by
-// uf_union continuing with the node's previous parent.  Tall thin structures (a column of pixels links into a chain as
-// long as the column) are what makes this matter: without it every find walks the whole chain through L2.
+// uf_union continuing with the node's previous parent.
 __device__ __forceinline__ int uf_find(int* parent, int i) {
     int cur = parent[i];
     if (cur != i) {
@@ -1074,44 +1079,49 @@ __device__ __forceinline__ unsigned load_mask_word(const uint8_t* __restrict__ m
     return m[i0];
 }
 
-constexpr int CCL_CHUNK = 4096;  // pixels per chunk task (256 threads x 4 words of 4 pixels)
-constexpr int CCL_TPB = 8;       // consecutive chunk tasks per block
+constexpr int CCL_UNIT = 128;                       // pixels per list entry
+constexpr int CCL_SUB = 4;                          // VEC == 1: single pixels per lane and unit
+constexpr int CCL_GRID = 148 * 8;                   // blocks of 8 warps for the list passes
 
-// Every pass walks "chunk tasks" t = frame * n_chunks + chunk, CCL_TPB consecutive tasks per block.  flags[t] is a
-// 32-bit occupancy mask of the chunk: bit u is set when the 128-pixel unit u of the chunk (the 32 words one warp loads
-// at once) holds a foreground pixel.  The producer of the mask fills the flags (residual_kernel, a few atomics per
-// frame) or, for a caller-supplied mask, the init pass does while it streams the mask once.  Every other pass reads
-// the flags of its tasks with one load, skips empty chunks and touches only the occupied units: on detection masks
-// (0.1 % foreground, 2 % of the units occupied) the labelling no longer streams the mask five times.
-struct CclTask {
-    size_t base;     // first pixel of the frame in the batch
-    int c0, c1;      // pixel range of the chunk inside the frame
+struct CclList {
+    const int* entries;      // frame * n_units + unit, in no particular order
+    const int* count;
+    int n_units;             // units per frame
 };
-__device__ __forceinline__ CclTask ccl_task(int t, int n_chunks, int npx) {
-    const int f = t / n_chunks, c = t - f * n_chunks;
-    CclTask k;
-    k.base = (size_t)f * npx;
-    k.c0 = c * CCL_CHUNK;
-    k.c1 = min(k.c0 + CCL_CHUNK, npx);
-    return k;
-}
-constexpr int CCL_WPT = CCL_CHUNK / (256 * 4);   // words per thread and chunk on the VEC == 4 path
 
-// flags of the block's CCL_TPB tasks: one load per warp, lane l holds task t0 + l
-__device__ __forceinline__ unsigned ccl_block_flags(const int* __restrict__ flags, int t0, int n_tasks) {
-    const int l = threadIdx.x & 31;
-    return (l < CCL_TPB && t0 + l < n_tasks) ? (unsigned)flags[t0 + l] : 0u;
+// the warp's items of unit `u` of a frame: VEC == 4: word j = 0 is pixels u*128 + lane*4 .. +3; VEC == 1: "word" j is
+// the single pixel u*128 + j*32 + lane.  Raster order inside the unit is (j, lane, byte).
+template <int VEC>
+__device__ __forceinline__ int ccl_item_px(int u, int j) {
+    const int lane = threadIdx.x & 31;
+    return VEC == 4 ? u * CCL_UNIT + lane * 4 : u * CCL_UNIT + j * 32 + lane;
 }
+template <int VEC> struct CclItems { static constexpr int N = VEC == 4 ? 1 : CCL_SUB; };
 
-// the (up to) CCL_WPT mask words of this thread in chunk k, all requested before any is used; units whose occupancy
-// bit is clear are not read.  Word j of the thread is pixel k.c0 + (j * 256 + threadIdx.x) * 4, unit j * 8 + warp.
-__device__ __forceinline__ void ccl_load_words(const uint8_t* __restrict__ m, const CclTask& k, unsigned bits,
-                                               unsigned (&wv)[CCL_WPT]) {
-    const int warp = threadIdx.x >> 5;
+template <int VEC>
+__device__ __forceinline__ void ccl_load_unit(const uint8_t* __restrict__ m, int u, int npx, unsigned (&wv)[CclItems<VEC>::N]) {
 #pragma unroll
-    for (int j = 0; j < CCL_WPT; ++j) {
-        const int i0 = k.c0 + (j * 256 + threadIdx.x) * 4;
-        wv[j] = (((bits >> (j * 8 + warp)) & 1u) && i0 < k.c1) ? load_mask_word<4>(m, i0) : 0u;
+    for (int j = 0; j < CclItems<VEC>::N; ++j) {
+        const int i0 = ccl_item_px<VEC>(u, j);
+        wv[j] = i0 < npx ? load_mask_word<VEC>(m, i0) : 0u;     // VEC == 4 implies npx % 4 == 0
+    }
+}
+
+// list of occupied units of a caller-supplied mask (one streaming read); unit_mark doubles as the per-unit root count
+// later, so only its zero / non-zero state matters here
+template <int VEC>
+__global__ void __launch_bounds__(256) ccl_list_kernel(const uint8_t* __restrict__ mask, int npx, int n_units, int n,
+                                                      int* __restrict__ entries, int* __restrict__ count) {
+    const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int total = n * n_units;
+    for (int e = gw; e < total; e += warps) {
+        const int f = e / n_units, u = e - f * n_units;
+        unsigned wv[CclItems<VEC>::N];
+        ccl_load_unit<VEC>(mask + (size_t)f * npx, u, npx, wv);
+        unsigned any = 0;
+#pragma unroll
+        for (int j = 0; j < CclItems<VEC>::N; ++j) any |= wv[j];
+        if (__any_sync(0xffffffffu, any != 0) && (threadIdx.x & 31) == 0) entries[atomicAdd(count, 1)] = e;
     }
 }
 
@@ -1120,48 +1130,26 @@ __device__ __forceinline__ void ccl_load_words(const uint8_t* __restrict__ m, co
 // the run, consistent with "smaller index = root")
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int npx,
-                                                      int n_chunks, int n_tasks, int* __restrict__ flags,
-                                                      int flags_ready) {
-    __shared__ unsigned s_bits;
-    const int t0 = blockIdx.x * CCL_TPB;
-    const unsigned mine = flags_ready ? ccl_block_flags(flags, t0, n_tasks) : 0u;
-    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
-        const int t = t0 + tt;
-        const unsigned bits = flags_ready ? __shfl_sync(0xffffffffu, mine, tt) : 0xffffffffu;
-        if (bits == 0) continue;                      // the producer of the mask already knows the chunk is empty
-        const CclTask k = ccl_task(t, n_chunks, npx);
-        if (!flags_ready) {
-            if (threadIdx.x == 0) s_bits = 0;
-            __syncthreads();
-        }
-        if (VEC == 4) {
-            unsigned wv[CCL_WPT];
-            ccl_load_words(mask + k.base, k, bits, wv);
+                                                      CclList L) {
+    const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int cnt = *L.count;
+    for (int q = gw; q < cnt; q += warps) {
+        const int e = L.entries[q];
+        const int f = e / L.n_units, u = e - f * L.n_units;
+        const size_t base = (size_t)f * npx;
+        unsigned wv[CclItems<VEC>::N];
+        ccl_load_unit<VEC>(mask + base, u, npx, wv);
 #pragma unroll
-            for (int j = 0; j < CCL_WPT; ++j) {
-                if (!flags_ready) {
-                    const bool any = __any_sync(0xffffffffu, wv[j] != 0);
-                    if (any && (threadIdx.x & 31) == 0) atomicOr(&s_bits, 1u << (j * 8 + (threadIdx.x >> 5)));
-                }
-                if (wv[j] == 0) continue;
-                const int i0 = k.c0 + (j * 256 + threadIdx.x) * 4;
-                int start = 0;
+        for (int j = 0; j < CclItems<VEC>::N; ++j) {
+            if (wv[j] == 0) continue;
+            const int i0 = ccl_item_px<VEC>(u, j);
+            int start = 0;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const bool fg = ((wv[j] >> (8 * b)) & 255u) != 0;
-                    if (!fg) { start = b + 1; continue; }
-                    parent[k.base + i0 + b] = i0 + start;
-                }
+            for (int b = 0; b < VEC; ++b) {
+                const bool fg = ((wv[j] >> (8 * b)) & 255u) != 0;
+                if (!fg) { start = b + 1; continue; }
+                parent[base + i0 + b] = i0 + start;
             }
-        } else {
-            bool any = false;
-            for (int i = k.c0 + threadIdx.x; i < k.c1; i += 256)
-                if (mask[k.base + i]) { any = true; parent[k.base + i] = i; }
-            if (!flags_ready && any) atomicOr(&s_bits, 1u);       // one-pixel words: occupancy is not tracked per unit
-        }
-        if (!flags_ready) {
-            __syncthreads();
-            if (threadIdx.x == 0) flags[t] = (int)s_bits;
         }
     }
 }
@@ -1207,96 +1195,70 @@ __device__ __forceinline__ void ccl_merge_word(const uint8_t* __restrict__ m, in
 
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w,
-                                                       int npx, int n_chunks, int n_tasks,
-                                                       const int* __restrict__ flags) {
-    const int t0 = blockIdx.x * CCL_TPB;
-    const unsigned mine = ccl_block_flags(flags, t0, n_tasks);
-    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
-        const unsigned bits = __shfl_sync(0xffffffffu, mine, tt);
-        if (bits == 0) continue;
-        const CclTask k = ccl_task(t0 + tt, n_chunks, npx);
-        const uint8_t* m = mask + k.base;
-        int* par = parent + k.base;
-        if (VEC == 4) {
-            unsigned wv[CCL_WPT];
-            ccl_load_words(m, k, bits, wv);
+                                                       int npx, CclList L) {
+    const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int cnt = *L.count;
+    for (int q = gw; q < cnt; q += warps) {
+        const int e = L.entries[q];
+        const int f = e / L.n_units, u = e - f * L.n_units;
+        const uint8_t* m = mask + (size_t)f * npx;
+        int* par = parent + (size_t)f * npx;
+        unsigned wv[CclItems<VEC>::N];
+        ccl_load_unit<VEC>(m, u, npx, wv);
 #pragma unroll
-            for (int j = 0; j < CCL_WPT; ++j)
-                if (wv[j]) ccl_merge_word<4>(m, par, w, k.c0 + (j * 256 + threadIdx.x) * 4, wv[j]);
-        } else {
-            for (int i0 = k.c0 + threadIdx.x; i0 < k.c1; i0 += 256) {
-                const unsigned wv = m[i0];
-                if (wv) ccl_merge_word<1>(m, par, w, i0, wv);
-            }
-        }
+        for (int j = 0; j < CclItems<VEC>::N; ++j)
+            if (wv[j]) ccl_merge_word<VEC>(m, par, w, ccl_item_px<VEC>(u, j), wv[j]);
     }
 }
 
-// flatten + count roots per chunk (chunk_cnt[t], 0 for empty chunks)
+// flatten + count the roots of every listed unit (unit_cnt[e]; units that are not listed keep their zero)
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_flatten_count_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent,
-                                                               int npx, int* __restrict__ chunk_cnt, int n_chunks,
-                                                               int n_tasks, const int* __restrict__ flags) {
-    __shared__ int wsum[8];
-    const int t0 = blockIdx.x * CCL_TPB;
-    const unsigned mine = ccl_block_flags(flags, t0, n_tasks);
-    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
-        const int t = t0 + tt;
-        const unsigned bits = __shfl_sync(0xffffffffu, mine, tt);
-        if (bits == 0) {
-            if (threadIdx.x == 0) chunk_cnt[t] = 0;
-            continue;
-        }
-        const CclTask k = ccl_task(t, n_chunks, npx);
-        int* par = parent + k.base;
-        int cnt = 0;
-        auto flatten_word = [&](int i0, unsigned wv) {
+                                                               int npx, CclList L, int* __restrict__ unit_cnt) {
+    const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int cnt = *L.count;
+    for (int q = gw; q < cnt; q += warps) {
+        const int e = L.entries[q];
+        const int f = e / L.n_units, u = e - f * L.n_units;
+        int* par = parent + (size_t)f * npx;
+        unsigned wv[CclItems<VEC>::N];
+        ccl_load_unit<VEC>(mask + (size_t)f * npx, u, npx, wv);
+        int roots = 0;
+#pragma unroll
+        for (int j = 0; j < CclItems<VEC>::N; ++j) {
+            if (wv[j] == 0) continue;
+            const int i0 = ccl_item_px<VEC>(u, j);
 #pragma unroll
             for (int b = 0; b < VEC; ++b) {
-                if (!((wv >> (8 * b)) & 255u)) continue;
+                if (!((wv[j] >> (8 * b)) & 255u)) continue;
                 const int i = i0 + b;
                 const int r = uf_find_ro(par, i);
-                par[i] = r;   // benign race: every writer stores a valid ancestor, roots never change here
-                cnt += (r == i);
-            }
-        };
-        if (VEC == 4) {
-            unsigned wv[CCL_WPT];
-            ccl_load_words(mask + k.base, k, bits, wv);
-#pragma unroll
-            for (int j = 0; j < CCL_WPT; ++j)
-                if (wv[j]) flatten_word(k.c0 + (j * 256 + threadIdx.x) * 4, wv[j]);
-        } else {
-            for (int i0 = k.c0 + threadIdx.x; i0 < k.c1; i0 += 256) {
-                const unsigned wv = mask[k.base + i0];
-                if (wv) flatten_word(i0, wv);
+                par[i] = r;   // benign race: every writer stores the root, roots never change here
+                roots += (r == i);
             }
         }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int j = 0; j < 8; ++j) tot += wsum[j];
-            chunk_cnt[t] = tot;
-        }
-        __syncthreads();      // wsum is reused by the block's next task
+        roots = __reduce_add_sync(0xffffffffu, roots);
+        if ((threadIdx.x & 31) == 0) unit_cnt[e] = roots;     // overwrites the producer's "listed" mark
     }
 }
 
-// exclusive scan of the per-chunk root counts, one block per frame; writes the total label count
-__global__ void __launch_bounds__(1024) ccl_scan_kernel(int* __restrict__ chunk_cnt, int n_chunks, char* nlabels_base,
+// exclusive scan of the per-unit root counts, one block per frame; writes the total label count
+__global__ void __launch_bounds__(1024) ccl_scan_kernel(int* __restrict__ unit_cnt, int n_units, char* nlabels_base,
                                                        size_t nlabels_stride) {
     __shared__ int wtot[32];
     __shared__ int carry_s;
-    int* c = chunk_cnt + (size_t)blockIdx.x * n_chunks;
+    int* c = unit_cnt + (size_t)blockIdx.x * n_units;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < n_chunks; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < n_chunks ? c[i] : 0;
-        int incl = v;
+    // 4 consecutive units per thread: a 1080p frame (16 200 units) is four rounds
+    for (int base = 0; base < n_units; base += 4096) {
+        const int i = base + threadIdx.x * 4;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = i + k < n_units ? c[i + k] : 0;
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -1315,56 +1277,45 @@ __global__ void __launch_bounds__(1024) ccl_scan_kernel(int* __restrict__ chunk_
         }
         __syncthreads();
         const int carry = carry_s;
-        if (i < n_chunks) c[i] = carry + wtot[wid] + incl - v;
+        int off = carry + wtot[wid] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < n_units) c[i + k] = off;
+            off += v[k];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + wtot[wid] + incl;
+        if (threadIdx.x == 1023) carry_s = off;
         __syncthreads();
     }
     if (threadIdx.x == 0) *reinterpret_cast<int32_t*>(nlabels_base + (size_t)blockIdx.x * nlabels_stride) = carry_s;
 }
 
-// rank[root] = canonical label of the component rooted at `root` (roots ordered by raster index).  The raster order
-// inside a chunk is word j = 0..3 of thread 0..255, so the prefix runs over (j, thread).
+// rank[root] = canonical label of the component rooted at `root` (roots ordered by raster index): the unit's offset
+// from the scan plus the raster-order prefix inside the unit
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_rank_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ parent,
-                                                      int npx, const int* __restrict__ chunk_off, int n_chunks,
-                                                      int n_tasks, const int* __restrict__ flags,
+                                                      int npx, CclList L, const int* __restrict__ unit_off,
                                                       int* __restrict__ rank) {
-    __shared__ int wsum[8];
-    __shared__ int running;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int t0 = blockIdx.x * CCL_TPB;
-    const unsigned mine_f = ccl_block_flags(flags, t0, n_tasks);
-    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
-        const int t = t0 + tt;
-        const unsigned bits = __shfl_sync(0xffffffffu, mine_f, tt);
-        if (bits == 0) continue;
-        const CclTask k = ccl_task(t, n_chunks, npx);
-        const int* par = parent + k.base;
-        int* rk = rank + k.base;
-        if (threadIdx.x == 0) running = chunk_off[t];
-        unsigned wv4[CCL_WPT];
-        if (VEC == 4) ccl_load_words(mask + k.base, k, bits, wv4);
-        __syncthreads();
-        constexpr int STEPS = VEC == 4 ? CCL_WPT : CCL_CHUNK / 256;
-        for (int j = 0; j < STEPS; ++j) {
-            const int i0 = k.c0 + (j * 256 + threadIdx.x) * VEC;
+    const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int cnt = *L.count;
+    for (int q = gw; q < cnt; q += warps) {
+        const int e = L.entries[q];
+        const int f = e / L.n_units, u = e - f * L.n_units;
+        const int* par = parent + (size_t)f * npx;
+        int* rk = rank + (size_t)f * npx;
+        unsigned wv[CclItems<VEC>::N];
+        ccl_load_unit<VEC>(mask + (size_t)f * npx, u, npx, wv);
+        int running = unit_off[e];
+#pragma unroll
+        for (int j = 0; j < CclItems<VEC>::N; ++j) {
+            const int i0 = ccl_item_px<VEC>(u, j);
             unsigned roots = 0;   // bit b: pixel i0 + b is a root
-            if (VEC == 4) {
-                // a run-time j would put wv4 in local memory: select with compares instead
-                unsigned wv = 0;
+            if (wv[j]) {
 #pragma unroll
-                for (int q = 0; q < CCL_WPT; ++q) wv = (q == j) ? wv4[q] : wv;
-                if (wv) {
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (((wv >> (8 * b)) & 255u) && par[i0 + b] == i0 + b) roots |= 1u << b;
-                }
-            } else if (i0 < k.c1) {
-                if (mask[k.base + i0] && par[i0] == i0) roots = 1u;
+                for (int b = 0; b < VEC; ++b)
+                    if (((wv[j] >> (8 * b)) & 255u) && par[i0 + b] == i0 + b) roots |= 1u << b;
             }
-            // whole step without a root (the common case): nothing to rank, `running` stays
-            if (!__syncthreads_or(roots != 0)) continue;
             const int mine = __popc(roots);
             int incl = mine;
 #pragma unroll
@@ -1372,22 +1323,11 @@ __global__ void __launch_bounds__(256) ccl_rank_kernel(const uint8_t* __restrict
                 int v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-            if (lane == 31) wsum[wid] = incl;
-            __syncthreads();
-            if (mine) {
-                int off = running + incl - mine;
-                for (int q = 0; q < wid; ++q) off += wsum[q];
+            int off = running + incl - mine;
 #pragma unroll
-                for (int b = 0; b < VEC; ++b)
-                    if (roots & (1u << b)) rk[i0 + b] = ++off;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int tot = 0;
-                for (int q = 0; q < 8; ++q) tot += wsum[q];
-                running += tot;
-            }
-            __syncthreads();
+            for (int b = 0; b < VEC; ++b)
+                if (roots & (1u << b)) rk[i0 + b] = ++off;
+            running += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
@@ -1400,55 +1340,38 @@ __global__ void ccl_boxes_init_kernel(int32_t* boxes, size_t boxes_stride, int m
     p[0] = 0x7fffffff; p[1] = 0x7fffffff; p[2] = -1; p[3] = -1; p[4] = 0;
 }
 
-// labels_out may alias parent (each thread reads only its own parent entries before writing them); empty chunks and
-// empty units get their zeros without a look at the mask
+// labels_out may alias parent (each thread reads only its own parent entries before writing them); background pixels
+// were zeroed before the init pass
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_relabel_kernel(const uint8_t* __restrict__ mask, const int* parent,
-                                                         const int* __restrict__ rank, int w, int npx, int n_chunks,
-                                                         int n_tasks, const int* __restrict__ flags, int* labels_out,
-                                                         int32_t* __restrict__ boxes, size_t boxes_stride, int max_boxes) {
-    const int t0 = blockIdx.x * CCL_TPB;
-    const unsigned mine = ccl_block_flags(flags, t0, n_tasks);
-    for (int tt = 0; tt < CCL_TPB && t0 + tt < n_tasks; ++tt) {
-        const int t = t0 + tt;
-        const unsigned bits = __shfl_sync(0xffffffffu, mine, tt);
-        if (bits == 0 && !labels_out) continue;
-        const CclTask k = ccl_task(t, n_chunks, npx);
-        const int f = t / n_chunks;
-        auto relabel_word = [&](int i0, unsigned wv) {
-            int lab[VEC];
+                                                         const int* __restrict__ rank, int w, int npx, CclList L,
+                                                         int* labels_out, int32_t* __restrict__ boxes,
+                                                         size_t boxes_stride, int max_boxes) {
+    const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int cnt = *L.count;
+    for (int q = gw; q < cnt; q += warps) {
+        const int e = L.entries[q];
+        const int f = e / L.n_units, u = e - f * L.n_units;
+        const size_t base = (size_t)f * npx;
+        unsigned wv[CclItems<VEC>::N];
+        ccl_load_unit<VEC>(mask + base, u, npx, wv);
 #pragma unroll
-            for (int b = 0; b < VEC; ++b) lab[b] = 0;
-            if (wv) {
-                const int y = i0 / w, x0 = i0 - y * w;
+        for (int j = 0; j < CclItems<VEC>::N; ++j) {
+            if (wv[j] == 0) continue;
+            const int i0 = ccl_item_px<VEC>(u, j);
+            const int y = i0 / w, x0 = i0 - y * w;
 #pragma unroll
-                for (int b = 0; b < VEC; ++b) {
-                    if (!((wv >> (8 * b)) & 255u)) continue;
-                    const int l = rank[k.base + parent[k.base + i0 + b]];
-                    lab[b] = l;
-                    if (boxes && l <= max_boxes) {
-                        int32_t* bx = boxes + (size_t)f * boxes_stride + (l - 1) * 5;
-                        const int x = x0 + b;
-                        atomicMin(bx + 0, x); atomicMin(bx + 1, y); atomicMax(bx + 2, x); atomicMax(bx + 3, y);
-                        atomicAdd(bx + 4, 1);
-                    }
+            for (int b = 0; b < VEC; ++b) {
+                if (!((wv[j] >> (8 * b)) & 255u)) continue;
+                const int l = rank[base + parent[base + i0 + b]];
+                if (labels_out) labels_out[base + i0 + b] = l;
+                if (boxes && l <= max_boxes) {
+                    int32_t* bx = boxes + (size_t)f * boxes_stride + (l - 1) * 5;
+                    const int x = x0 + b;
+                    atomicMin(bx + 0, x); atomicMin(bx + 1, y); atomicMax(bx + 2, x); atomicMax(bx + 3, y);
+                    atomicAdd(bx + 4, 1);
                 }
             }
-            if (labels_out) {
-                if (VEC == 4) *reinterpret_cast<int4*>(labels_out + k.base + i0) = make_int4(lab[0], lab[VEC > 1 ? 1 : 0], lab[VEC > 2 ? 2 : 0], lab[VEC > 3 ? 3 : 0]);
-                else labels_out[k.base + i0] = lab[0];
-            }
-        };
-        if (VEC == 4) {
-            unsigned wv[CCL_WPT];
-            ccl_load_words(mask + k.base, k, bits, wv);
-#pragma unroll
-            for (int j = 0; j < CCL_WPT; ++j) {
-                const int i0 = k.c0 + (j * 256 + threadIdx.x) * 4;
-                if (i0 < k.c1 && (wv[j] || labels_out)) relabel_word(i0, wv[j]);
-            }
-        } else {
-            for (int i0 = k.c0 + threadIdx.x; i0 < k.c1; i0 += 256) relabel_word(i0, bits ? mask[k.base + i0] : 0u);
         }
     }
 }
@@ -1462,34 +1385,50 @@ __global__ void ccl_boxes_final_kernel(int32_t* boxes, size_t boxes_stride, int 
     else { p[2] = p[2] - p[0] + 1; p[3] = p[3] - p[1] + 1; }
 }
 
+// scratch behind the rank array: [count (4 ints)] [unit_cnt: max_pairs x n_units] [entries: max_pairs x n_units]
+int ccl_n_units(mavd_handle H) { return ceil_div(H->cfg.width * H->cfg.height, CCL_UNIT); }
+static int* ccl_count_ptr(mavd_handle H) { return H->d_scan + (size_t)H->cfg.max_pairs * H->cfg.width * H->cfg.height; }
+int* ccl_unit_marks(mavd_handle H) { return ccl_count_ptr(H) + 4; }
+int* ccl_unit_list(mavd_handle H) { return ccl_unit_marks(H) + (size_t)H->cfg.max_pairs * ccl_n_units(H); }
+int* ccl_unit_count(mavd_handle H) { return ccl_count_ptr(H); }
+
+int ccl_list_reset(mavd_handle H, int n, cudaStream_t s) {
+    MAVD_CUDA(cudaMemsetAsync(ccl_count_ptr(H), 0, sizeof(int) * (4 + (size_t)n * ccl_n_units(H)), s));
+    return MAVD_OK;
+}
+
 template <int VEC>
 static int ccl_launch(mavd_handle H, const uint8_t* d_mask, int n, int* parent, int32_t* labels_out, int32_t* d_boxes,
                       size_t boxes_stride, int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s,
-                      bool flags_ready) {
+                      bool list_ready) {
     const int w = H->cfg.width, h = H->cfg.height, npx = w * h;
-    const int n_chunks = ceil_div(npx, CCL_CHUNK);
-    const int n_tasks = n * n_chunks;
-    int* rank = H->d_scan;                                        // [n][npx], written and read at roots only
-    int* chunk_cnt = H->d_scan + (size_t)H->cfg.max_pairs * npx;  // [n][n_chunks]
-    int* flags = ccl_chunk_flags(H);                               // [n][n_chunks]: chunk holds foreground
-    const int g = ceil_div(n_tasks, CCL_TPB);
-    ccl_init_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, npx, n_chunks, n_tasks, flags, flags_ready ? 1 : 0);
+    const int n_units = ccl_n_units(H);
+    int* rank = H->d_scan;                     // [n][npx], written and read at roots only
+    int* unit_cnt = ccl_unit_marks(H);         // [n][n_units]: "listed" mark, then root count, then label offset
+    CclList L{ccl_unit_list(H), ccl_unit_count(H), n_units};
+    if (!list_ready) {
+        TRY_RC(ccl_list_reset(H, n, s));
+        ccl_list_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, npx, n_units, n, ccl_unit_list(H), ccl_unit_count(H));
+        MAVD_LAUNCHED();
+    }
+    if (labels_out) MAVD_CUDA(cudaMemsetAsync(labels_out, 0, sizeof(int32_t) * (size_t)n * npx, s));
+    ccl_init_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, npx, L);
     MAVD_LAUNCHED();
-    ccl_merge_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, w, npx, n_chunks, n_tasks, flags);
+    ccl_merge_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, w, npx, L);
     MAVD_LAUNCHED();
-    ccl_flatten_count_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, npx, chunk_cnt, n_chunks, n_tasks, flags);
+    ccl_flatten_count_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, npx, L, unit_cnt);
     MAVD_LAUNCHED();
-    ccl_scan_kernel<<<n, 1024, 0, s>>>(chunk_cnt, n_chunks, (char*)d_n_labels, nlabels_stride);
+    ccl_scan_kernel<<<n, 1024, 0, s>>>(unit_cnt, n_units, (char*)d_n_labels, nlabels_stride);
     MAVD_LAUNCHED();
-    ccl_rank_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, npx, chunk_cnt, n_chunks, n_tasks, flags, rank);
+    ccl_rank_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, npx, L, unit_cnt, rank);
     MAVD_LAUNCHED();
     if (d_boxes) {
         ccl_boxes_init_kernel<<<ceil_div(n * max_boxes, 128), 128, 0, s>>>(d_boxes, boxes_stride, max_boxes, n);
         MAVD_LAUNCHED();
     }
     if (d_boxes || labels_out) {
-        ccl_relabel_kernel<VEC><<<g, 256, 0, s>>>(d_mask, parent, rank, w, npx, n_chunks, n_tasks, flags, labels_out,
-                                                   d_boxes, boxes_stride, max_boxes);
+        ccl_relabel_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, rank, w, npx, L, labels_out, d_boxes,
+                                                          boxes_stride, max_boxes);
         MAVD_LAUNCHED();
     }
     if (d_boxes) {
@@ -1499,23 +1438,17 @@ static int ccl_launch(mavd_handle H, const uint8_t* d_mask, int n, int* parent, 
     return MAVD_OK;
 }
 
-int ccl_n_chunks(mavd_handle H) { return ceil_div(H->cfg.width * H->cfg.height, CCL_CHUNK); }
-int* ccl_chunk_flags(mavd_handle H) {
-    const size_t npx = (size_t)H->cfg.width * H->cfg.height;
-    return H->d_scan + (size_t)H->cfg.max_pairs * npx + (size_t)H->cfg.max_pairs * ccl_n_chunks(H);
-}
-
 // d_labels: the caller's label image (also used as the union-find array), or NULL when only the
 // component count / boxes are wanted (the handle's scratch then holds the union-find array).
+// list_ready: the producer of the mask already appended its occupied units (ccl_list_reset before it ran).
 int ccl_run(mavd_handle H, const uint8_t* d_mask, int n, int32_t* d_labels, int32_t* d_boxes, size_t boxes_stride,
-            int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s, bool flags_ready) {
+            int max_boxes, int32_t* d_n_labels, size_t nlabels_stride, cudaStream_t s, bool list_ready) {
     ProfScope ps(&H->prof, MAVD_PROF_CCL, s);
-    const int w = H->cfg.width, h = H->cfg.height;
+    const int w = H->cfg.width;
     int* parent = d_labels ? d_labels : H->d_labels;
-    const bool vec4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_mask) & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(parent) & 15) == 0) && (((size_t)w * h) % 4 == 0);
-    if (vec4) return ccl_launch<4>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s, flags_ready);
-    return ccl_launch<1>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s, flags_ready);
+    const bool vec4 = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_mask) & 3) == 0);
+    if (vec4) return ccl_launch<4>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s, list_ready);
+    return ccl_launch<1>(H, d_mask, n, parent, d_labels, d_boxes, boxes_stride, max_boxes, d_n_labels, nlabels_stride, s, list_ready);
 }
 
 }  // namespace mavd
