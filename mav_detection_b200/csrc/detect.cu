@@ -363,6 +363,7 @@ struct ResidualArgs {
     uint8_t* total_out;
     uint8_t* fixed_out;
     char* stats_base; size_t stats_stride;
+    unsigned row_magic;      // 0, or M with i0 / w == __umulhi(i0, M) for every pixel index of a frame (host-checked)
     int* unit_marks; int* unit_list; int* unit_count; int n_units;   // nullable: list of occupied units of the fixed mask (see ccl_*)
 };
 
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
         seg_min = (int)floor(thr) + 1;
     }
 
-    int c_tot = 0, c_fix = 0, c_pos = 0, c_neg = 0, c_tpt = 0, c_fpt = 0, c_tpf = 0, c_fpf = 0;
+    int c_tot = 0, c_fix = 0, c_pos = 0, c_tpt = 0, c_fpt = 0, c_tpf = 0, c_fpf = 0, n_px = 0;
     int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;
     double sfx = 0.0, sfy = 0.0, maxphi = 0.0;
 
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
         const int q = (blockIdx.x * RES_ITEMS + it) * 256 + threadIdx.x;
         if (q >= ngrp) break;
         const int i0 = q * VEC;
-        const int y = i0 / w, x0 = i0 - y * w;
+        const int y = A.row_magic ? (int)__umulhi((unsigned)i0, A.row_magic) : i0 / w, x0 = i0 - y * w;
         // ---- loads ----
         double vx[VEC], vy[VEC];
         float vfx[VEC], vfy[VEC];
@@ -627,8 +628,11 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
             if (*reinterpret_cast<volatile int*>(A.unit_marks + e) == 0 && atomicExch(A.unit_marks + e, 1) == 0)
                 A.unit_list[atomicAdd(A.unit_count, 1)] = e;
         }
-        if (want_stats) {
+        n_px += VEC;
+        if (want_stats && (totw | fixw | segw)) {
             // counts on whole words: mask bytes are 0/1, segmentation bytes are tested with per-byte compares
+            // (words with empty masks and an empty segmentation, almost all of them, add nothing but negatives,
+            // which are counted as pixels seen minus positives at the end)
             c_tot += __popc(totw); c_fix += __popc(fixw);
             if (seg) {
                 const unsigned live = VEC == 4 ? 0xffffffffu : 0xffu;
@@ -636,7 +640,6 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
                 const unsigned nz = __vcmpne4(segw, 0u) & 0x01010101u & live;          // g >= 1
                 const unsigned n255 = __vcmpne4(segw, 0xffffffffu) & 0x01010101u & live;   // g <= 254
                 c_pos += __popc(hi);
-                c_neg += VEC - __popc(hi);
                 c_tpt += __popc(totw & nz); c_fpt += __popc(totw & n255);
                 c_tpf += __popc(fixw & nz); c_fpf += __popc(fixw & n255);
                 const unsigned smin = (unsigned)min(seg_min, 256);
@@ -687,6 +690,7 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
         if (lane == 0 && mk) atomicMax(&s_max, mk);
     }
     if (seg) {
+        int c_neg = n_px - c_pos;      // 255 - g > 127 <=> not (g > 127)
         c_pos = __reduce_add_sync(FULL, c_pos); c_neg = __reduce_add_sync(FULL, c_neg);
         c_tpt = __reduce_add_sync(FULL, c_tpt); c_fpt = __reduce_add_sync(FULL, c_fpt);
         c_tpf = __reduce_add_sync(FULL, c_tpf); c_fpf = __reduce_add_sync(FULL, c_fpf);
@@ -802,6 +806,11 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
     A.sky = d_sky; A.sky_stride = sky_stride; A.seg = d_seg; A.seg_stride = seg_stride; A.seg_max = seg_max;
     A.phi_out = d_phi; A.total_out = d_total; A.fixed_out = d_fixed;
     A.stats_base = (char*)d_stats; A.stats_stride = stats_stride;
+    // i / w by multiplication: M = floor(2^32 / w) + 1 is exact for i * (M * w - 2^32) < 2^32
+    {
+        const unsigned long long M = (1ull << 32) / (unsigned)w + 1, err = M * (unsigned)w - (1ull << 32);
+        A.row_magic = (M < (1ull << 32) && (unsigned long long)npx * err < (1ull << 32)) ? (unsigned)M : 0u;
+    }
     const bool listing = list_fixed_units && d_fixed != nullptr;
     A.unit_marks = listing ? ccl_unit_marks(H) : nullptr; A.unit_list = listing ? ccl_unit_list(H) : nullptr;
     A.unit_count = listing ? ccl_unit_count(H) : nullptr; A.n_units = ccl_n_units(H);

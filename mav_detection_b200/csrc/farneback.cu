@@ -522,6 +522,7 @@ struct IterArgs {
     const float* gk;        // Gaussian half kernel [m+1] (device) or nullptr
     int n_pairs, tiles_x;   // TMA kernel: 1-D grid (see iter_box_tma_kernel)
     int group;              // pairs interleaved per tile in the 1-D grid order
+    int last_fused;         // TMA kernel, last iteration: horizontal sums + solve in registers (a.flow must be set)
 };
 
 template <int M_>
@@ -953,6 +954,54 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
     }
     __syncthreads();
 
+    if (LAST && a.last_fused) {
+        // ---- last iteration: horizontal sums of the five planes and the 2x2 solve in registers ----
+        // thread = 4 adjacent pixels of one row: no sums are written back to shared memory, no third barrier, and the
+        // flow leaves as two 16-byte stores (same hsum_box / same solve expressions: results identical to the
+        // staged form below)
+        const int q4 = tid & 15, rsub = tid >> 4;
+        constexpr int ROWS_PER_IT = NT / 16;
+        float2* fl = a.flow + (size_t)p * a.flow_stride;
+        const float scale = a.scale;
+        const bool vec_ok = (a.flow_pitch & 1) == 0 && (reinterpret_cast<uintptr_t>(fl) & 15) == 0;
+#pragma unroll 1
+        for (int it = 0; it < IT_TY / ROWS_PER_IT; ++it) {
+            const int r = it * ROWS_PER_IT + rsub;
+            float o[5][4];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const float* row = box + c * CH + r * RW + 4 * q4;
+                float u[20];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + 4 * j);
+                    u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w;
+                }
+                hsum_box<M_>(u, o[c]);
+            }
+            const int x = x0 + 4 * q4, y = y0 + r;
+            if (y >= h || x >= w) continue;
+            float2 f[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float g11 = o[0][k] * scale, g12 = o[1][k] * scale, g22 = o[2][k] * scale, h1 = o[3][k] * scale,
+                            h2 = o[4][k] * scale;
+                const float idet = __frcp_rn(g11 * g22 - g12 * g12 + 1e-3f);
+                f[k] = make_float2((g11 * h2 - g12 * h1) * idet, (g22 * h1 - g12 * h2) * idet);
+            }
+            float2* dst = fl + (size_t)y * a.flow_pitch + x;
+            if (vec_ok && x + 4 <= w) {
+                reinterpret_cast<float4*>(dst)[0] = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
+                reinterpret_cast<float4*>(dst)[1] = make_float4(f[2].x, f[2].y, f[3].x, f[3].y);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (x + k < w) dst[k] = f[k];
+            }
+        }
+        return;
+    }
+
     // ---- horizontal sums, in place: half-warp = one row, thread = 4 outputs ----
     {
         const int q4 = tid & 15, rsub = tid >> 4;
@@ -1237,6 +1286,8 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             a.n_pairs = n_pairs;
             a.tiles_x = g.x;
             a.group = pair_group;
+            static const bool last_fused_env = !(getenv("MAVD_LAST_FUSED") && getenv("MAVD_LAST_FUSED")[0] == '0');
+            a.last_fused = (last && last_fused_env) ? 1 : 0;
             const dim3 g1(g.x * g.y * g.z);
             const int RW = IT_TX + 2 * hx, RH = IT_TY + 2 * m;
             const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
