@@ -307,7 +307,18 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
                         tab[(size_t)d * taps + j] = (1.f - a[d]) * k0 + a[d] * k1;
                     }
                 }
-                if (axis == 0) { C_TRY(A.upload(&L.xbase, base)); C_TRY(A.upload(&L.xtab, tab)); }
+                if (axis == 0) {
+                    C_TRY(A.upload(&L.xbase, base)); C_TRY(A.upload(&L.xtab, tab));
+                    std::vector<float> tabT((size_t)dst * taps);
+                    for (int d = 0; d < dst; ++d)
+                        for (int j = 0; j < taps; ++j) tabT[(size_t)j * dst + d] = tab[(size_t)d * taps + j];
+                    C_TRY(A.upload(&L.xtabT, tabT));
+                    L.hspan_max = 0;
+                    L.hstride_min = dst > 1 ? src : 0;
+                    for (int d0 = 0; d0 < dst; d0 += 64)
+                        L.hspan_max = std::max(L.hspan_max, base[std::min(d0 + 63, dst - 1)] + taps - base[d0]);
+                    for (int d = 1; d < dst; ++d) L.hstride_min = std::min(L.hstride_min, base[d] - base[d - 1]);
+                }
                 else           { C_TRY(A.upload(&L.ybase, base)); C_TRY(A.upload(&L.ytab, tab)); }
             }
             C_TRY(A.alloc(&L.tmp, (size_t)F * L.h * round_up(W, 4)));   // vertical-pass output [F][h_l][Wp]

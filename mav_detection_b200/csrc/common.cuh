@@ -62,6 +62,9 @@ struct Level {
     float sigma = 0.f;
     // pyramid tables (full-res -> this level): combined blur+resize filter of ksz+1 taps per output sample
     int* xbase = nullptr;  float* xtab = nullptr;   // [w], [w][ksz+1]
+    float* xtabT = nullptr;                         // [taps][w]: xtab tap-major (staged horizontal pyramid pass)
+    int hspan_max = 0;                              // largest source span of 64 adjacent outputs (+ taps)
+    int hstride_min = 0;                            // smallest distance between the sources of adjacent outputs
     int* ybase = nullptr;  float* ytab = nullptr;   // [h], [h][ksz+1]
     float* tmp = nullptr;                           // [frames][h][Wp] vertical pass output (levels >= 1)
     // flow upsample tables (next-coarser level -> this level)

@@ -50,11 +50,15 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 struct PyrLevel {
     int w, h, pitch, taps;
     const int* xbase; const float* xtab;   // [w], [w][taps]
+    const float* xtabT;                     // [taps][w]: the same weights, tap-major (pyr_hsecond_staged_kernel)
+    int staged;                             // horizontal pass through shared memory (source stride >= 8, span fits)
     const int* ybase; const float* ytab;   // [h], [h][taps]
     float* tmp; float* img;
     size_t tmp_stride, img_stride;          // floats per frame
-    int vblk0, vtiles_x;                    // pyr_vfirst: first block of this level, 256-column tiles per row
-    int hblk0, htiles_x;                    // pyr_hsecond: first block of this level, 64-pixel tiles per row
+    // both passes run on a 3-D grid (tile column, row tile of any level, frame): no integer division per thread; the
+    // levels share the y range ([row0, row0 + ceil(h / 4)) belongs to this level), blocks right of a narrow level exit
+    int row0;                               // first row tile (4 rows) of this level in grid.y
+    int htiles_x;                           // pyr_hsecond: 64-pixel tiles per row (pyr_vfirst: ceil(W / 256) for all)
 };
 struct PyrDesc {
     int n;
@@ -69,13 +73,11 @@ __device__ __forceinline__ float byte_to_float(uint32_t v, uint32_t selector) {
 __global__ void __launch_bounds__(256) pyr_vfirst_kernel(const uint8_t* __restrict__ frames, size_t frame_stride, int W,
                                                         int H, int Wp, int word_ok, const __grid_constant__ PyrDesc d) {
     int l = 0;
-    while (l + 1 < d.n && (int)blockIdx.x >= d.lv[l + 1].vblk0) ++l;
+    while (l + 1 < d.n && (int)blockIdx.y >= d.lv[l + 1].row0) ++l;
     const PyrLevel& L = d.lv[l];
-    const int b = blockIdx.x - L.vblk0;
-    const int bx = b % L.vtiles_x, by = b / L.vtiles_x;
-    const int x = (bx * 64 + (threadIdx.x & 63)) * 4, dy = by * 4 + (threadIdx.x >> 6);
+    const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, dy = (blockIdx.y - L.row0) * 4 + (threadIdx.x >> 6);
     if (x >= W || dy >= L.h) return;
-    const uint8_t* src = frames + (size_t)blockIdx.y * frame_stride + x;
+    const uint8_t* src = frames + (size_t)blockIdx.z * frame_stride + x;
     const int base = __ldg(L.ybase + dy);
     const float* tab = L.ytab + dy * L.taps;
     const int taps = L.taps;
@@ -120,19 +122,19 @@ __global__ void __launch_bounds__(256) pyr_vfirst_kernel(const uint8_t* __restri
             if (nx > 3) a3 += t * (float)q[3];
         }
     }
-    float* out = L.tmp + (size_t)blockIdx.y * L.tmp_stride + (size_t)dy * Wp + x;
+    float* out = L.tmp + (size_t)blockIdx.z * L.tmp_stride + (size_t)dy * Wp + x;
     *reinterpret_cast<float4*>(out) = make_float4(a0, a1, a2, a3);   // Wp is a multiple of 4: the pad is never read
 }
 
-__global__ void __launch_bounds__(256) pyr_hsecond_kernel(int W, int Wp, const __grid_constant__ PyrDesc d) {
+__global__ void __launch_bounds__(256) pyr_hsecond_kernel(int W, int Wp, int row_begin, const __grid_constant__ PyrDesc d) {
+    const int by = blockIdx.y + row_begin;
     int l = 0;
-    while (l + 1 < d.n && (int)blockIdx.x >= d.lv[l + 1].hblk0) ++l;
+    while (l + 1 < d.n && by >= d.lv[l + 1].row0) ++l;
     const PyrLevel& L = d.lv[l];
-    const int b = blockIdx.x - L.hblk0;
-    const int bx = b % L.htiles_x, by = b / L.htiles_x;
-    const int dx = bx * 64 + (threadIdx.x & 63), dy = by * 4 + (threadIdx.x >> 6);
+    if ((int)blockIdx.x >= L.htiles_x || L.staged) return;
+    const int dx = blockIdx.x * 64 + (threadIdx.x & 63), dy = (by - L.row0) * 4 + (threadIdx.x >> 6);
     if (dx >= L.w || dy >= L.h) return;
-    const float* src = L.tmp + (size_t)blockIdx.y * L.tmp_stride + (size_t)dy * Wp;
+    const float* src = L.tmp + (size_t)blockIdx.z * L.tmp_stride + (size_t)dy * Wp;
     const int base = __ldg(L.xbase + dx);
     const float* tab = L.xtab + dx * L.taps;
     const int taps = L.taps;
@@ -148,7 +150,54 @@ __global__ void __launch_bounds__(256) pyr_hsecond_kernel(int W, int Wp, const _
     } else {
         for (int j = 0; j < taps; ++j) acc += __ldg(tab + j) * src[reflect101(base + j, W)];
     }
-    L.img[(size_t)blockIdx.y * L.img_stride + (size_t)dy * L.pitch + dx] = acc;
+    L.img[(size_t)blockIdx.z * L.img_stride + (size_t)dy * L.pitch + dx] = acc;
+}
+
+// Horizontal pass of the coarse levels (source stride >= 8 floats between adjacent outputs).  Read directly, the 32
+// lanes of a warp touch 8 .. 32 different 128-byte lines per tap; here the block first copies the source span of its
+// 64 outputs x 4 rows into shared memory with coalesced loads, stored with one pad word per 32 (index e + e / 32) so
+// that lanes a power-of-two stride apart fall into different banks, and reads the weights tap-major (coalesced).
+// Same products, same order of accumulation as pyr_hsecond_kernel.
+constexpr int PYR_SPAN_MAX = 2208;                               // source floats per row a block may stage
+constexpr int PYR_SPAN_PAD = PYR_SPAN_MAX + PYR_SPAN_MAX / 32 + 3;
+
+__global__ void __launch_bounds__(256) pyr_hsecond_staged_kernel(int W, int Wp, int row_begin,
+                                                                const __grid_constant__ PyrDesc d) {
+    __shared__ float s_src[4][PYR_SPAN_PAD];
+    const int by = blockIdx.y + row_begin;
+    int l = 0;
+    while (l + 1 < d.n && by >= d.lv[l + 1].row0) ++l;
+    const PyrLevel& L = d.lv[l];
+    if ((int)blockIdx.x >= L.htiles_x || !L.staged) return;
+    const int i = threadIdx.x & 63, ry = threadIdx.x >> 6;
+    const int dx0 = blockIdx.x * 64, dx = dx0 + i, dy = (by - L.row0) * 4 + ry;
+    const int taps = L.taps;
+    const int lo = __ldg(L.xbase + dx0), hi = __ldg(L.xbase + min(dx0 + 63, L.w - 1)) + taps;
+    const int n = hi - lo;                                   // <= PYR_SPAN_MAX (checked on the host)
+    if (dy < L.h) {
+        const float* src = L.tmp + (size_t)blockIdx.z * L.tmp_stride + (size_t)dy * Wp;
+        float* dst = s_src[ry];
+        if (lo >= 0 && hi <= W) {
+            for (int e = i; e < n; e += 64) dst[e + (e >> 5)] = src[lo + e];
+        } else {
+            for (int e = i; e < n; e += 64) dst[e + (e >> 5)] = src[reflect101(lo + e, W)];
+        }
+    }
+    __syncthreads();
+    if (dx >= L.w || dy >= L.h) return;
+    const float* row = s_src[ry];
+    const float* wt = L.xtabT + dx;
+    const int b = __ldg(L.xbase + dx) - lo;
+    const int w = L.w;
+    float acc = 0.f;
+    for (int j = 0; j < taps; j += 4) {     // taps is a multiple of 4 (zero padded)
+        const int e = b + j;
+        acc += __ldg(wt + (size_t)j * w) * row[e + (e >> 5)];
+        acc += __ldg(wt + (size_t)(j + 1) * w) * row[(e + 1) + ((e + 1) >> 5)];
+        acc += __ldg(wt + (size_t)(j + 2) * w) * row[(e + 2) + ((e + 2) >> 5)];
+        acc += __ldg(wt + (size_t)(j + 3) * w) * row[(e + 3) + ((e + 3) >> 5)];
+    }
+    L.img[(size_t)blockIdx.z * L.img_stride + (size_t)dy * L.pitch + dx] = acc;
 }
 
 // level-0 image on its own (tests / taps only): 3x3 [1/4 1/2 1/4] blur of the u8 frame, REFLECT_101
@@ -1189,23 +1238,36 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         const int Wp = round_up(W, 4);
         PyrDesc d;
         d.n = hi - lo + 1;
-        int vb = 0, hb = 0;
+        static const bool pyr_staged_env = !(getenv("MAVD_PYR_STAGED") && getenv("MAVD_PYR_STAGED")[0] == '0');
+        int rows = 0, hx_max = 1;
         for (int li = lo; li <= hi; ++li) {
             const Level& L = H->lv[li];
             PyrLevel& P = d.lv[li - lo];
             P.w = L.w; P.h = L.h; P.pitch = L.pitch; P.taps = round_up(L.ksz + 1, 4);
             P.xbase = L.xbase; P.xtab = L.xtab; P.ybase = L.ybase; P.ytab = L.ytab;
             P.tmp = L.tmp; P.img = L.img; P.tmp_stride = (size_t)L.h * Wp; P.img_stride = L.plane;
-            P.vblk0 = vb; P.vtiles_x = ceil_div(W, 256);
-            vb += P.vtiles_x * ceil_div(L.h, 4);
-            P.hblk0 = hb; P.htiles_x = ceil_div(L.w, 64);
-            hb += P.htiles_x * ceil_div(L.h, 4);
+            P.xtabT = L.xtabT;
+            P.staged = (pyr_staged_env && L.hspan_max <= PYR_SPAN_MAX && L.hstride_min >= 8) ? 1 : 0;
+            P.row0 = rows;
+            rows += ceil_div(L.h, 4);
+            P.htiles_x = ceil_div(L.w, 64);
+            hx_max = max(hx_max, P.htiles_x);
         }
+        MAVD_REQUIRE(rows <= 65535 && n_frames <= 65535, MAVD_ERR_UNSUPPORTED, "pyramid: grid too large");
         const int word_ok = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) ? 1 : 0;
-        pyr_vfirst_kernel<<<dim3(vb, n_frames), 256, 0, st>>>(d_frames, frame_bytes, W, Hh, Wp, word_ok, d);
+        pyr_vfirst_kernel<<<dim3(ceil_div(W, 256), rows, n_frames), 256, 0, st>>>(d_frames, frame_bytes, W, Hh, Wp, word_ok, d);
         MAVD_LAUNCHED();
-        pyr_hsecond_kernel<<<dim3(hb, n_frames), 256, 0, st>>>(W, Wp, d);
-        MAVD_LAUNCHED();
+        // levels whose outputs are >= 8 source samples apart go through the shared-memory variant: one launch per run
+        // of consecutive levels of the same kind (normally two: the fine levels direct, the coarse tail staged)
+        for (int a0 = 0; a0 < d.n;) {
+            int a1 = a0, hx = 0;
+            while (a1 < d.n && d.lv[a1].staged == d.lv[a0].staged) { hx = max(hx, d.lv[a1].htiles_x); ++a1; }
+            const int r0 = d.lv[a0].row0, r1 = a1 < d.n ? d.lv[a1].row0 : rows;
+            if (d.lv[a0].staged) pyr_hsecond_staged_kernel<<<dim3(hx, r1 - r0, n_frames), 256, 0, st>>>(W, Wp, r0, d);
+            else pyr_hsecond_kernel<<<dim3(hx, r1 - r0, n_frames), 256, 0, st>>>(W, Wp, r0, d);
+            MAVD_LAUNCHED();
+            a0 = a1;
+        }
         return MAVD_OK;
     };
     // consecutive pairs share an R plane (R1 of pair p is R0 of pair p+1): interleaving the pairs of a tile in
