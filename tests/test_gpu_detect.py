@@ -314,3 +314,43 @@ def test_ccl_without_label_image():
         k = min(32, stats.shape[0])
         assert np.array_equal(boxes[i, :k].cpu().numpy(), stats[:k])
     eng.close()
+
+
+def test_ccl_sparse_full_hd_masks_with_tall_thin_structures():
+    """Detection-like masks (0.1 % foreground): the labelling walks a list of occupied 128-pixel units instead of the
+    image.  Columns of pixels (chains as long as the image is tall for the union-find), diagonal lines (8-connectivity
+    across unit and row boundaries), specks, a blob that straddles unit boundaries, and one empty frame; the same
+    engine is used twice so that a stale list or stale unit counts from the first call would show."""
+    import torch
+    from oracle import ccl_np
+    rng = np.random.default_rng(21)
+    h, w = 1080, 1920
+    masks = np.zeros((4, h, w), np.uint8)
+    masks[0, :, 0] = 1                                  # left border column
+    masks[0, :, w - 1] = 1                              # right border column
+    masks[0, 100:900, 637] = 1
+    masks[0, 500, 200:1500] = 1                         # a row crossing many units, touching column 637
+    for k in range(600):                                # diagonals, both directions
+        masks[1, 100 + k, 300 + k] = 1
+        masks[1, 100 + k, 1500 - k] = 1
+    masks[1, 400:420, 120:136] = 1                      # blob across a 128-pixel unit boundary (x = 128)
+    ys, xs = rng.integers(0, h, 1500), rng.integers(0, w, 1500)
+    masks[2, ys, xs] = 1                                # specks
+    masks[2, 0, :] = 1
+    masks[2, h - 1, ::2] = 1
+    # masks[3] stays empty
+    eng = _engine(w, h, 4)
+    md = torch.from_numpy(masks).cuda()
+    for rep in range(2):
+        sel = md if rep == 0 else torch.flip(md, dims=[0]).contiguous()
+        ref_masks = masks if rep == 0 else masks[::-1]
+        labels, boxes, cnt = eng.ccl(sel)
+        labels, boxes, cnt = labels.cpu().numpy(), boxes.cpu().numpy(), cnt.cpu().numpy()
+        for i in range(4):
+            ref, stats = ccl_np.label(np.ascontiguousarray(ref_masks[i]))
+            assert cnt[i] == ref.max(), (rep, i)
+            assert np.array_equal(labels[i], ref), (rep, i)
+            k = min(32, stats.shape[0])
+            assert np.array_equal(boxes[i, :k], stats[:k]), (rep, i)
+    eng.close()
+
