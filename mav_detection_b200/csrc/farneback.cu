@@ -507,13 +507,15 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
                                                            const float* __restrict__ fxa,
                                                            const int* __restrict__ fyi0,
                                                            const float* __restrict__ fya, float up_scale,
-                                                           float* __restrict__ M, double xscale, double yscale) {
+                                                           float* __restrict__ M, double xscale, double yscale,
+                                                           int txlog) {
     // 3-D grid (pairs, tiles_x, tiles_y): blocks are scheduled x-fastest, so the pair index is fastest (same L2 sharing
     // of R between consecutive pairs as in iter_box_tma_kernel) and no thread pays for an integer division: with one
     // pixel per thread the two divisions of a 1-D grid were 55 of the kernel's 400 instructions
+    // block = 2^txlog x 2^(8 - txlog) pixels (64 x 4 by default)
     const int p = blockIdx.x;
-    const int x = blockIdx.y * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.z * 4 + (threadIdx.x >> 6);
+    const int x = (blockIdx.y << txlog) + (threadIdx.x & ((1 << txlog) - 1));
+    const int y = (blockIdx.z << (8 - txlog)) + (threadIdx.x >> txlog);
     if (x >= w || y >= h) return;
     float dx = 0.f, dy = 0.f;
     if (cflow) {
@@ -1313,10 +1315,11 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             auto is_pow2 = [](double v) { int e; return v > 0.0 && frexp(v, &e) == 0.5 && e > -20 && e <= 1; };
             const int coord = tables ? MI_COORD_TABLES
                                      : (!no_pow2 && is_pow2(xscale) && is_pow2(yscale)) ? MI_COORD_POW2 : MI_COORD_F64;
-            const dim3 g3(g.z, g.x, g.y);       // pair index fastest
+            static const int txlog = getenv("MAVD_MAT_TXLOG") ? atoi(getenv("MAVD_MAT_TXLOG")) : 6;
+            const dim3 g3(g.z, ceil_div(L.w, 1 << txlog), ceil_div(L.h, 256 >> txlog));       // pair index fastest
 #define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, (size_t)pair_stride * 5 * L.plane,                                     \
                 top ? nullptr : (const float2*)C->flow, top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch,             \
-                top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale
+                top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale, txlog
             if (coord == MI_COORD_TABLES) matrices_init_kernel<MI_COORD_TABLES><<<g3, 256, 0, st>>>(MI_ARGS);
             else if (coord == MI_COORD_POW2) matrices_init_kernel<MI_COORD_POW2><<<g3, 256, 0, st>>>(MI_ARGS);
             else matrices_init_kernel<MI_COORD_F64><<<g3, 256, 0, st>>>(MI_ARGS);
