@@ -421,12 +421,20 @@ __global__ void __launch_bounds__(256, 4) polyexp_kernel(const void* __restrict_
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float border_factor(int d) { return d < 2 ? 0.14f : 0.4472f; }
 
+struct R0Px { float y, x, yy, xx, xy; };     // the five expansion coefficients of one pixel of the first frame
+
+__device__ __forceinline__ R0Px load_r0_px(const float* __restrict__ R0, size_t o, size_t plane) {
+    R0Px r;
+    r.y = __ldg(R0 + o); r.x = __ldg(R0 + plane + o); r.yy = __ldg(R0 + 2 * plane + o);
+    r.xx = __ldg(R0 + 3 * plane + o); r.xy = __ldg(R0 + 4 * plane + o);
+    return r;
+}
+
 __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, int pitch, size_t plane, float dx,
-                                                   float dy, const float* __restrict__ R0,
+                                                   float dy, const R0Px& r0,
                                                    const float* __restrict__ R1, float* __restrict__ Mout) {
     const size_t o = (size_t)y * pitch + x;
-    const float r0y = __ldg(R0 + o), r0x = __ldg(R0 + plane + o), r0yy = __ldg(R0 + 2 * plane + o),
-                r0xx = __ldg(R0 + 3 * plane + o), r0xy = __ldg(R0 + 4 * plane + o);
+    const float r0y = r0.y, r0x = r0.x, r0yy = r0.yy, r0xx = r0.xx, r0xy = r0.xy;
     float fx = (float)x + dx, fy = (float)y + dy;
     const float flx = floorf(fx), fly = floorf(fy);
     // keep the int conversion safe for wild displacements
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
                                                            const int* __restrict__ fyi0,
                                                            const float* __restrict__ fya, float up_scale,
                                                            float* __restrict__ M, double xscale, double yscale,
-                                                           int txlog) {
+                                                           int txlog, int r0_first) {
     // 3-D grid (pairs, tiles_x, tiles_y): blocks are scheduled x-fastest, so the pair index is fastest (same L2 sharing
     // of R between consecutive pairs as in iter_box_tma_kernel) and no thread pays for an integer division: with one
     // pixel per thread the two divisions of a 1-D grid were 55 of the kernel's 400 instructions
@@ -517,6 +525,11 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
     const int x = (blockIdx.y << txlog) + (threadIdx.x & ((1 << txlog) - 1));
     const int y = (blockIdx.z << (8 - txlog)) + (threadIdx.x >> txlog);
     if (x >= w || y >= h) return;
+    // R0 does not depend on the flow: its five loads go out first and travel with the coarse-flow loads, so that the
+    // second memory round trip of the thread is the R1 gather alone
+    const float* R0 = R + (size_t)p * R_pair_stride;
+    R0Px r0;
+    if (r0_first) r0 = load_r0_px(R0, (size_t)y * pitch + x, plane);
     float dx = 0.f, dy = 0.f;
     if (cflow) {
         const float2* cf = cflow + (size_t)p * cflow_stride;
@@ -540,13 +553,13 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
         dx = (tx0 * (1.f - ay) + tx1 * ay) * up_scale;
         dy = (ty0 * (1.f - ay) + ty1 * ay) * up_scale;
     }
-    const float* R0 = R + (size_t)p * R_pair_stride;
+    if (!r0_first) r0 = load_r0_px(R0, (size_t)y * pitch + x, plane);
     // One pixel per thread at 32 registers (full occupancy) is the fastest form measured: the 32-bit-offset
     // UpdateMatrices of the fused iteration (> 32 registers: 0.87 vs 0.675 ms per 16-pair step) and variants with
     // 8 pixels per thread that halve the instruction count (2.45-2.67 vs 2.22 ms per 64-pair step), and a tiled
     // variant with the R1 footprint staged by TMA like the fused iteration's (2.57 ms), all lose more to occupancy
     // than they save: the kernel is bound by the latency of its dependent memory round trips.
-    update_matrices_px(x, y, w, h, pitch, plane, dx, dy, R0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
+    update_matrices_px(x, y, w, h, pitch, plane, dx, dy, r0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -736,7 +749,7 @@ __global__ void __launch_bounds__(256, 3) iter_kernel(IterArgs a) {
         const float fx = (g11 * h2 - g12 * h1) * idet;
         const float fy = (g22 * h1 - g12 * h2) * idet;
         if (a.flow) a.flow[(size_t)p * a.flow_stride + (size_t)y * a.flow_pitch + x] = make_float2(fx, fy);
-        if (!LAST) update_matrices_px(x, y, w, h, pitch, plane, fx, fy, R0, R1, Mout);
+        if (!LAST) update_matrices_px(x, y, w, h, pitch, plane, fx, fy, load_r0_px(R0, (size_t)y * pitch + x, plane), R1, Mout);
     }
 }
 
@@ -843,7 +856,6 @@ __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h,
 // UpdateMatrices with the R1 footprint read from a shared-memory box [5][RH][RW] whose cell (0, 0) is image pixel
 // (bx, by); footprints that leave the box fall back to global loads.  Same operations, same order as
 // update_matrices_fast: identical results.
-struct R0Px { float y, x, yy, xx, xy; };     // the five expansion coefficients of one pixel of the first frame
 
 __device__ __forceinline__ R0Px load_r0(const float* __restrict__ R0, int o, int plane) {
     R0Px r;
@@ -1315,11 +1327,12 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             auto is_pow2 = [](double v) { int e; return v > 0.0 && frexp(v, &e) == 0.5 && e > -20 && e <= 1; };
             const int coord = tables ? MI_COORD_TABLES
                                      : (!no_pow2 && is_pow2(xscale) && is_pow2(yscale)) ? MI_COORD_POW2 : MI_COORD_F64;
+            static const int r0_first = getenv("MAVD_MAT_R0FIRST") ? atoi(getenv("MAVD_MAT_R0FIRST")) : 1;
             static const int txlog = getenv("MAVD_MAT_TXLOG") ? atoi(getenv("MAVD_MAT_TXLOG")) : 6;
             const dim3 g3(g.z, ceil_div(L.w, 1 << txlog), ceil_div(L.h, 256 >> txlog));       // pair index fastest
 #define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, (size_t)pair_stride * 5 * L.plane,                                     \
                 top ? nullptr : (const float2*)C->flow, top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch,             \
-                top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale, txlog
+                top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale, txlog, r0_first
             if (coord == MI_COORD_TABLES) matrices_init_kernel<MI_COORD_TABLES><<<g3, 256, 0, st>>>(MI_ARGS);
             else if (coord == MI_COORD_POW2) matrices_init_kernel<MI_COORD_POW2><<<g3, 256, 0, st>>>(MI_ARGS);
             else matrices_init_kernel<MI_COORD_F64><<<g3, 256, 0, st>>>(MI_ARGS);
