@@ -218,6 +218,8 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries the JSON line and nothing else: NCCL's own log (the box sets NCCL_DEBUG=VERSION) goes to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     wl = build_workload(args.workload, rank, args.pairs)
     W, H, B, params = wl['W'], wl['H'], wl['B'], wl['params']
