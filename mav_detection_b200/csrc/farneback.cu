@@ -4,11 +4,12 @@
 // HBM layout: every per-level field is PLANAR with a row pitch that is a multiple of 64 floats
 // (256 B): image [frame][h][pitch]; R [frame][5][h][pitch]; M [pair][5][h][pitch] (ping-pong);
 // flow [pair][h][pitch] float2.  64-wide tiles therefore never cross a row end and every tile row is
-// 16-byte aligned (float4 / cp.async / TMA friendly).  Batch elements sit in grid.z, or are interleaved into
-// a 1-D grid where the CTA order matters for L2 (consecutive pairs share an R plane).
+// 16-byte aligned (float4 / cp.async / TMA friendly).  Batch elements sit in grid.z, or lead the grid (grid.x, or
+// interleaved into a 1-D grid) where the CTA order matters for L2 (consecutive pairs share an R plane).
 //
 // Kernels (algorithmic bytes per level pixel P):
-//   pyr_vfirst / pyr_hsecond  blur+resize from full-res u8 for all coarse levels, two launches
+//   pyr_vfirst / pyr_hsecond / pyr_hsecond_staged
+//                             blur+resize from full-res u8 for all coarse levels, three launches
 //   polyexp_kernel            separable polynomial expansion, smem tile          4P -> 20P (level 0: 1P -> 20P)
 //   matrices_init_kernel      flow upsample (x 1/pyr_scale) fused with UpdateMatrices   (8P' +) 40P -> 20P
 //   iter_box_tma_kernel       box blur of M + 2x2 solve + UpdateMatrices, TMA-staged     88P (28P for the last)
