@@ -21,6 +21,8 @@ import time
 
 import numpy as np
 
+JSON_OUT = sys.stdout     # main() swaps this for a private handle on the real stdout
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -205,7 +207,7 @@ def run_reference(args):
                                       float(np.mean([x[2] for x in vals])), os.cpu_count() or 0)},
         'e2e': {'value': v, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 def run_b200(args):
@@ -218,8 +220,6 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries the JSON line and nothing else: NCCL's own log (the box sets NCCL_DEBUG=VERSION) goes to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     wl = build_workload(args.workload, rank, args.pairs)
     W, H, B, params = wl['W'], wl['H'], wl['B'], wl['params']
@@ -382,7 +382,7 @@ def run_b200(args):
             'kernel_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1] > 0},
             'cpu_baseline': cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -399,6 +399,12 @@ def main():
     ap.add_argument('--pairs', type=int, default=0, help='frame pairs per step (default: the workload\'s)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    # stdout carries the JSON line and nothing else: keep a private handle on the real stdout for it and point file
+    # descriptor 1 at stderr, so that whatever a library prints (NCCL's version banner, worker processes) lands there
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
