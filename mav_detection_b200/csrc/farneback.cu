@@ -926,7 +926,11 @@ __device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, 
     Mout[o + 4 * plane] = r6 * r2 + r5 * r3;
 }
 
-template <int M_, bool LAST, int NT, bool R1S>
+// FUSE (not-last iterations with R1S; default, MAVD_ITER_FUSE=0 selects the staged form): the horizontal sums and the
+// solve are done in registers as in the last iteration and the flow vectors, not the five sums, go through shared
+// memory to reach the x-fastest pixel mapping of the update phase (640 -> 256 wavefronts per tile for that hand-over,
+// one more barrier; same hsum_box, same solve expressions: identical results).
+template <int M_, bool LAST, int NT, bool R1S, bool FUSE = false>
 __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                              const __grid_constant__ CUtensorMap tmapR,
                                                                              const __grid_constant__ CUtensorMap tmapRbox,
@@ -1067,7 +1071,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
     }
 
     // ---- horizontal sums, in place: half-warp = one row, thread = 4 outputs ----
-    {
+    if (!(FUSE && R1S && !LAST)) {
         const int q4 = tid & 15, rsub = tid >> 4;
         constexpr int ROWS_PER_IT = NT / 16;
 #pragma unroll 2
@@ -1086,8 +1090,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
             __syncwarp();
             *reinterpret_cast<float4*>(row + 8) = make_float4(o[0], o[1], o[2], o[3]);
         }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- per pixel: solve, then UpdateMatrices ----
     const float* R0 = a.R + (size_t)(p * a.pair_stride) * 5 * a.plane;
@@ -1106,16 +1110,63 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         constexpr int PPT = (IT_TX * IT_TY) / NT;
         __shared__ int s_org[2];
         float ffx[PPT], ffy[PPT];
+        if (FUSE) {
+            // (a0) horizontal sums of the five planes + solve for 4 adjacent pixels per task, in registers
+            static_assert(!FUSE || NT == 256, "FUSE assumes 16 rows per pass");
+            const int q4 = tid & 15, rsub = tid >> 4;
+            float4 gx[2], gy[2];
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int r = it * 16 + rsub;
+                float o[5][4];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const float* row = box + c * CH + r * RW + 4 * q4;
+                    float u[20];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const float4 v = *reinterpret_cast<const float4*>(row + 4 * j);
+                        u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w;
+                    }
+                    hsum_box<M_>(u, o[c]);
+                }
+                float fx4[4], fy4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float g11 = o[0][k] * scale, g12 = o[1][k] * scale, g22 = o[2][k] * scale,
+                                h1 = o[3][k] * scale, h2 = o[4][k] * scale;
+                    const float idet = __frcp_rn(g11 * g22 - g12 * g12 + 1e-3f);
+                    fx4[k] = (g11 * h2 - g12 * h1) * idet;
+                    fy4[k] = (g22 * h1 - g12 * h2) * idet;
+                }
+                gx[it] = make_float4(fx4[0], fx4[1], fx4[2], fx4[3]);
+                gy[it] = make_float4(fy4[0], fy4[1], fy4[2], fy4[3]);
+            }
+            __syncthreads();                   // every vertical sum has been consumed: the box is free
+            // (a1) the flow vectors through shared memory: [2][32][64] floats at the start of the box
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int o4 = (it * 16 + rsub) * IT_TX + 4 * q4;
+                *reinterpret_cast<float4*>(box + o4) = gx[it];
+                *reinterpret_cast<float4*>(box + IT_TX * IT_TY + o4) = gy[it];
+            }
+            __syncthreads();
+        }
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
             const int idx = j * NT + tid;
             const int cx = idx & 63, r = idx >> 6;
-            const float* sp = box + r * RW + 8 + cx;
-            const float g11 = sp[0] * scale, g12 = sp[CH] * scale, g22 = sp[2 * CH] * scale, h1 = sp[3 * CH] * scale,
-                        h2 = sp[4 * CH] * scale;
-            const float idet = __frcp_rn(g11 * g22 - g12 * g12 + 1e-3f);
-            ffx[j] = (g11 * h2 - g12 * h1) * idet;
-            ffy[j] = (g22 * h1 - g12 * h2) * idet;
+            if (FUSE) {
+                ffx[j] = box[idx];
+                ffy[j] = box[IT_TX * IT_TY + idx];
+            } else {
+                const float* sp = box + r * RW + 8 + cx;
+                const float g11 = sp[0] * scale, g12 = sp[CH] * scale, g22 = sp[2 * CH] * scale, h1 = sp[3 * CH] * scale,
+                            h2 = sp[4 * CH] * scale;
+                const float idet = __frcp_rn(g11 * g22 - g12 * g12 + 1e-3f);
+                ffx[j] = (g11 * h2 - g12 * h1) * idet;
+                ffy[j] = (g22 * h1 - g12 * h2) * idet;
+            }
             if (cx == IT_TX / 2 && r == IT_TY / 2) {
                 // box origin: tile origin displaced by the centre pixel's flow, x a multiple of 4
                 const float cfx = fminf(fmaxf(ffx[j], -1.0e5f), 1.0e5f), cfy = fminf(fmaxf(ffy[j], -1.0e5f), 1.0e5f);
@@ -1199,17 +1250,17 @@ static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s
     return MAVD_OK;
 }
 
-template <int M_, bool LAST, int NT, bool R1S>
+template <int M_, bool LAST, int NT, bool R1S, bool FUSE = false>
 static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const CUtensorMap& mapRbox, const IterArgs& a,
                            dim3 grid, cudaStream_t s) {
     constexpr size_t smem = sizeof(float) * 5 * (IT_TY + 2 * M_) * (IT_TX + 16);
     static bool configured = false;
     if (!configured) {
-        MAVD_CUDA(cudaFuncSetAttribute(iter_box_tma_kernel<M_, LAST, NT, R1S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+        MAVD_CUDA(cudaFuncSetAttribute(iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    iter_box_tma_kernel<M_, LAST, NT, R1S><<<grid, NT, smem, s>>>(map, mapR, mapRbox, a);
+    iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE><<<grid, NT, smem, s>>>(map, mapR, mapRbox, a);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
@@ -1219,6 +1270,17 @@ static int launch_iter_tma_m(int m, const CUtensorMap& map, const CUtensorMap& m
                              const IterArgs& a, dim3 grid, cudaStream_t s) {
     // R1 staged in shared memory by a second TMA load: 4.36 vs 4.56 ms per 64-pair step (MAVD_R1S=0 switches it off)
     static const bool r1s = !(getenv("MAVD_R1S") && getenv("MAVD_R1S")[0] == '0');
+    // horizontal sums + solve in registers for the not-last iterations too, flow vectors handed to the update phase
+    // through shared memory: iter_full 4.27 vs 4.39 ms per 64-pair step (MAVD_ITER_FUSE=0 switches it off)
+    static const bool fuse = !(getenv("MAVD_ITER_FUSE") && getenv("MAVD_ITER_FUSE")[0] == '0');
+    if (r1s && !LAST && fuse) {
+        switch (m) {
+            case 5: return launch_iter_tma<5, false, 256, true, true>(map, mapR, mapRbox, a, grid, s);
+            case 6: return launch_iter_tma<6, false, 256, true, true>(map, mapR, mapRbox, a, grid, s);
+            case 7: return launch_iter_tma<7, false, 256, true, true>(map, mapR, mapRbox, a, grid, s);
+            default: return launch_iter_tma<8, false, 256, true, true>(map, mapR, mapRbox, a, grid, s);
+        }
+    }
     if (r1s && !LAST) {
         switch (m) {
             case 5: return launch_iter_tma<5, LAST, 256, true>(map, mapR, mapRbox, a, grid, s);
