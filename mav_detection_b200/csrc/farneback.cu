@@ -929,8 +929,10 @@ __device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, 
 // FUSE (not-last iterations with R1S; default, MAVD_ITER_FUSE=0 selects the staged form): the horizontal sums and the
 // solve are done in registers as in the last iteration and the flow vectors, not the five sums, go through shared
 // memory to reach the x-fastest pixel mapping of the update phase (640 -> 256 wavefronts per tile for that hand-over,
-// one more barrier; same hsum_box, same solve expressions: identical results).
-template <int M_, bool LAST, int NT, bool R1S, bool FUSE = false>
+// one more barrier; same hsum_box, same solve expressions: identical results).  FUSE == 2 (experimental, not yet
+// measured, MAVD_ITER_FUSE=2, window half-widths >= 6): the flow vectors are written straight into the box rows below
+// the 32 rows of vertical sums (raw rows that nobody reads after the vertical pass), which saves that extra barrier.
+template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0>
 __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                              const __grid_constant__ CUtensorMap tmapR,
                                                                              const __grid_constant__ CUtensorMap tmapRbox,
@@ -1142,13 +1144,26 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                 gx[it] = make_float4(fx4[0], fx4[1], fx4[2], fx4[3]);
                 gy[it] = make_float4(fy4[0], fy4[1], fy4[2], fy4[3]);
             }
-            __syncthreads();                   // every vertical sum has been consumed: the box is free
-            // (a1) the flow vectors through shared memory: [2][32][64] floats at the start of the box
+            if (FUSE == 2) {
+                // (a1') rows IT_TY .. RH-1 of every plane box still hold raw M rows that are dead since the vertical
+                // pass: DR floats per plane, 4096 flow values spread over them in order, no barrier needed first
+                constexpr int DR = (RH - IT_TY) * RW;
+                static_assert(FUSE != 2 || 5 * DR >= 2 * IT_TX * IT_TY, "dead rows too small for the flow vectors");
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const int o4 = (it * 16 + rsub) * IT_TX + 4 * q4;
-                *reinterpret_cast<float4*>(box + o4) = gx[it];
-                *reinterpret_cast<float4*>(box + IT_TX * IT_TY + o4) = gy[it];
+                for (int it = 0; it < 2; ++it) {
+                    const int ix = (it * 16 + rsub) * IT_TX + 4 * q4, iy = IT_TX * IT_TY + ix;
+                    *reinterpret_cast<float4*>(box + (ix / DR) * CH + IT_TY * RW + (ix % DR)) = gx[it];
+                    *reinterpret_cast<float4*>(box + (iy / DR) * CH + IT_TY * RW + (iy % DR)) = gy[it];
+                }
+            } else {
+                __syncthreads();                   // every vertical sum has been consumed: the box is free
+                // (a1) the flow vectors through shared memory: [2][32][64] floats at the start of the box
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int o4 = (it * 16 + rsub) * IT_TX + 4 * q4;
+                    *reinterpret_cast<float4*>(box + o4) = gx[it];
+                    *reinterpret_cast<float4*>(box + IT_TX * IT_TY + o4) = gy[it];
+                }
             }
             __syncthreads();
         }
@@ -1156,7 +1171,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         for (int j = 0; j < PPT; ++j) {
             const int idx = j * NT + tid;
             const int cx = idx & 63, r = idx >> 6;
-            if (FUSE) {
+            if (FUSE == 2) {
+                constexpr int DR = (RH - IT_TY) * RW;
+                const int iy = IT_TX * IT_TY + idx;
+                ffx[j] = box[(idx / DR) * CH + IT_TY * RW + (idx % DR)];
+                ffy[j] = box[(iy / DR) * CH + IT_TY * RW + (iy % DR)];
+            } else if (FUSE) {
                 ffx[j] = box[idx];
                 ffy[j] = box[IT_TX * IT_TY + idx];
             } else {
@@ -1250,7 +1270,7 @@ static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s
     return MAVD_OK;
 }
 
-template <int M_, bool LAST, int NT, bool R1S, bool FUSE = false>
+template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0>
 static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const CUtensorMap& mapRbox, const IterArgs& a,
                            dim3 grid, cudaStream_t s) {
     constexpr size_t smem = sizeof(float) * 5 * (IT_TY + 2 * M_) * (IT_TX + 16);
@@ -1272,13 +1292,20 @@ static int launch_iter_tma_m(int m, const CUtensorMap& map, const CUtensorMap& m
     static const bool r1s = !(getenv("MAVD_R1S") && getenv("MAVD_R1S")[0] == '0');
     // horizontal sums + solve in registers for the not-last iterations too, flow vectors handed to the update phase
     // through shared memory: iter_full 4.27 vs 4.39 ms per 64-pair step (MAVD_ITER_FUSE=0 switches it off)
-    static const bool fuse = !(getenv("MAVD_ITER_FUSE") && getenv("MAVD_ITER_FUSE")[0] == '0');
-    if (r1s && !LAST && fuse) {
+    static const int fuse = getenv("MAVD_ITER_FUSE") ? atoi(getenv("MAVD_ITER_FUSE")) : 1;
+    if (r1s && !LAST && fuse == 2 && m >= 6) {      // experimental: hand-over through the dead box rows
         switch (m) {
-            case 5: return launch_iter_tma<5, false, 256, true, true>(map, mapR, mapRbox, a, grid, s);
-            case 6: return launch_iter_tma<6, false, 256, true, true>(map, mapR, mapRbox, a, grid, s);
-            case 7: return launch_iter_tma<7, false, 256, true, true>(map, mapR, mapRbox, a, grid, s);
-            default: return launch_iter_tma<8, false, 256, true, true>(map, mapR, mapRbox, a, grid, s);
+            case 6: return launch_iter_tma<6, false, 256, true, 2>(map, mapR, mapRbox, a, grid, s);
+            case 7: return launch_iter_tma<7, false, 256, true, 2>(map, mapR, mapRbox, a, grid, s);
+            default: return launch_iter_tma<8, false, 256, true, 2>(map, mapR, mapRbox, a, grid, s);
+        }
+    }
+    if (r1s && !LAST && fuse != 0) {
+        switch (m) {
+            case 5: return launch_iter_tma<5, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
+            case 6: return launch_iter_tma<6, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
+            case 7: return launch_iter_tma<7, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
+            default: return launch_iter_tma<8, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
         }
     }
     if (r1s && !LAST) {
