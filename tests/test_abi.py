@@ -32,6 +32,24 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert sorted(_lib.SIGNATURES) == names
 
 
+def test_ctypes_signatures_have_the_header_arity_and_return_types():
+    """A binding that drifts from include/mavd.h corrupts the call silently: every prototype's parameter count and
+    return type (int status / int64 counter / const char*) must be what mav_detection_b200/_lib.py declares."""
+    from mav_detection_b200 import _lib
+    src = open(os.path.join(ROOT, 'include', 'mavd.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    src = re.sub(r'//[^\n]*', '', src)
+    decls = re.findall(r'\b(int64_t|int|void|const char\*)\s+(mavd_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S)
+    assert sorted(d[1] for d in decls) == _declared_functions()
+    restype = {'int': C.c_int, 'int64_t': C.c_int64, 'const char*': C.c_char_p, 'void': None}
+    for ret, name, args in decls:
+        args = args.strip()
+        n = 0 if args in ('', 'void') else len(args.split(','))
+        res, argtypes = _lib.SIGNATURES[name]
+        assert len(argtypes) == n, '%s: header has %d parameters, ctypes %d' % (name, n, len(argtypes))
+        assert res is restype[ret], '%s: header returns %s' % (name, ret)
+
+
 def test_abi_version_and_defaults(lib):
     from mav_detection_b200 import _lib
     assert lib.mavd_abi_version() == 1
