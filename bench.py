@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of the mav-detection hot path (Farneback flow -> derotate -> FoE -> phi/masks -> components).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c2|c2rot|c2dense|c2ref|c1|c3|c4|all] [--tune field=value,...]
 
 One "step" = one pass of the whole hot path over one batch of frame pairs taken from a synthetic
 sequence that is resident in HBM (device arm) / in pinned host memory (e2e).  Prints ONE JSON line.
 Metric: BASELINE.json -> 1080p frame-pairs/sec (flow+FoE+mask), plus % of HBM roofline of the fused
 Farneback iteration kernel.  `--impl reference` times the reference's own CPU path (cv2's Farneback +
 the NumPy restatement of the reference's FoE/phi/mask code in oracle/) on the host cores.
+`--workload all` measures C2 (the headline) and adds one line per other configuration under `extra`.
 """
 from __future__ import annotations
 
@@ -27,19 +29,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+SAMPLE = dict(pyr_scale=0.5, levels=5, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+REFPRM = dict(pyr_scale=0.4, levels=1, winsize=12, iterations=10, poly_n=8, poly_sigma=1.2, flags=0)
 WORKLOADS = {
-    # name: (W, H, farneback params, pairs per step, label)
-    'c2': (1920, 1080, dict(pyr_scale=0.5, levels=5, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0), 64,
-           'C2: synthetic AirSim-like 1920x1080 sequence, Farneback (0.5,5,15,3,5,1.2,0) 6 pyramid images'),
-    'c2ref': (1920, 1080, dict(pyr_scale=0.4, levels=1, winsize=12, iterations=10, poly_n=8, poly_sigma=1.2, flags=0), 32,
-              "C2': 1920x1080 with the reference's own parameters (0.4,1,12,10,8,1.2,0)"),
-    'c1': (640, 480, dict(pyr_scale=0.4, levels=1, winsize=12, iterations=10, poly_n=8, poly_sigma=1.2, flags=0), 1,
-           'C1: one 640x480 pair, reference parameters'),
-    'c3': (640, 480, dict(pyr_scale=0.5, levels=5, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0), 64,
-           'C3: 640x480, 64 pairs per launch'),
-    'c4': (3840, 2160, dict(pyr_scale=0.5, levels=7, winsize=15, iterations=10, poly_n=5, poly_sigma=1.2, flags=0), 8,
-           'C4: 3840x2160, 7 pyramid images, winsize 15, 10 iterations'),
+    # name: (W, H, farneback params, pairs per step, label, sequence options)
+    'c2': (1920, 1080, SAMPLE, 64,
+           'C2: synthetic AirSim-like 1920x1080 sequence, Farneback (0.5,5,15,3,5,1.2,0) 6 pyramid images', {}),
+    'c2rot': (1920, 1080, SAMPLE, 64,
+              'C2 with IMU rotation omega=(0.002,-0.001,0.0005) rad/frame (derotation not a no-op)',
+              dict(with_rotation=True)),
+    'c2dense': (1920, 1080, SAMPLE, 64,
+                'C2 frames under a sideways translation: no FoE consensus, ~100 % of the pixels in both masks '
+                '(dense residual / components stress)', dict(motion='translate')),
+    'c2ref': (1920, 1080, REFPRM, 32, "C2': 1920x1080 with the reference's own parameters (0.4,1,12,10,8,1.2,0)", {}),
+    'c1': (640, 480, REFPRM, 1, 'C1: one 640x480 pair, reference parameters', {}),
+    'c3': (640, 480, SAMPLE, 64, 'C3: 640x480, 64 pairs per launch', {}),
+    'c4': (3840, 2160, dict(SAMPLE, levels=7, iterations=10), 8,
+           'C4: 3840x2160, 7 pyramid images, winsize 15, 10 iterations', {}),
 }
+EXTRA_ORDER = ['c2rot', 'c2dense', 'c2ref', 'c1', 'c3', 'c4']
 N_BATCHES = 4          # distinct resident batches cycled through (working set per step >> L2 anyway)
 
 
@@ -105,10 +113,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def build_workload(name: str, rank: int = 0, pairs: int = 0):
     from mav_detection_b200 import synth
-    W, H, params, B, label = WORKLOADS[name]
+    W, H, params, B, label, opts = WORKLOADS[name]
     B = pairs or B
     n_frames = N_BATCHES * B + 1
-    seq = synth.make_sequence(W, H, n_frames, seq=rank, with_rotation=False)
+    seq = synth.make_sequence(W, H, n_frames, seq=rank, **opts)
     rs = np.random.RandomState(1000 + rank)   # legacy generator = the stream np.random.randint draws from
     samples = np.empty((N_BATCHES * B, 4000), np.int32)
     for i in range(N_BATCHES * B):
@@ -117,9 +125,36 @@ def build_workload(name: str, rank: int = 0, pairs: int = 0):
     return dict(name=name, W=W, H=H, params=params, B=B, label=label, seq=seq, samples=samples)
 
 
-def algorithmic_bytes_iter(W, H, B):
-    """Fused iteration, finest level: M 20 + R0 20 + R1 20 -> flow 8 + M' 20 = 88 B/px."""
-    return 88.0 * W * H * B
+def level_sizes(W, H, params):
+    """Pyramid image sizes, finest first."""
+    k, s = 0, 1.0
+    while k < params['levels']:
+        s *= params['pyr_scale']
+        if W * s < 32 or H * s < 32:
+            break
+        k += 1
+    out = []
+    for li in range(k + 1):
+        sc = params['pyr_scale'] ** li
+        out.append((int(np.rint(W * sc)), int(np.rint(H * sc))))
+    return out
+
+
+def algorithmic_bytes(W, H, params, B, n_frames):
+    """SURVEY §8(d) stage-graph compulsory bytes per launch group of each profiled kernel class, for B pairs."""
+    lv = level_sizes(W, H, params)
+    px = [w * h for w, h in lv]
+    n0, it = px[0], params['iterations']
+    return {
+        'pyramid': n_frames * sum(n0 + 4 * p for p in px[1:]) if len(px) > 1 else 0,
+        'polyexp': n_frames * (n0 * (1 + 20) + sum(24 * p for p in px[1:])),
+        'matrices': B * (sum(68 * p for p in px[:-1]) + 60 * px[-1] + sum(8 * p for p in px[1:])),
+        'iter_full': B * 88.0 * n0 * max(it - 1, 0),
+        'iter_full_last': B * 28.0 * n0,
+        'iter_coarse': B * sum((88.0 * (it - 1) + 28.0) * p for p in px[1:]),
+        'residual': B * 12.0 * n0,          # flow 8 + sky/seg 2 -> two masks 2
+        'ccl': B * 5.0 * n0,
+    }
 
 
 def cpu_one_pair(args):
@@ -176,12 +211,16 @@ def cpu_workers() -> int:
     return max(1, min(os.cpu_count() or 1, 32))
 
 
+def metric_name(W):
+    return '1080p frame-pairs/sec (flow+FoE+mask)' if W == 1920 else 'frame-pairs/sec (flow+FoE+mask)'
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     import cv2
-    wl = build_workload(args.workload, 0, args.pairs)
+    wl = build_workload('c2' if args.workload == 'all' else args.workload, 0, args.pairs)
     workers = cpu_workers()
     per_step = workers
     ref = CpuReference(wl, workers)
@@ -194,7 +233,7 @@ def run_reference(args):
     v = float(np.sum([per_step for _ in vals]) / np.sum([x[3] for x in vals]))
     line = {
         'impl': 'reference',
-        'metric': '1080p frame-pairs/sec (flow+FoE+mask)' if wl['W'] == 1920 else 'frame-pairs/sec (flow+FoE+mask)',
+        'metric': metric_name(wl['W']),
         'value': v, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * float(np.mean([x[3] for x in vals])), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -210,22 +249,24 @@ def run_reference(args):
     print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
-def run_b200(args):
+# ------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------
+def measure(name, args, steps, world, rank, local, headline):
+    """One workload on this rank's GPU.  Returns the fields of the JSON line (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from mav_detection_b200 import engine
+    from mav_detection_b200._lib import HOST_SLOTS
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    wl = build_workload(args.workload, rank, args.pairs)
+    wl = build_workload(name, rank, args.pairs)
     W, H, B, params = wl['W'], wl['H'], wl['B'], wl['params']
     seq = wl['seq']
     eng = engine.Engine(W, H, params, max_pairs=B, device=local)
+    if args.tune:
+        eng.set_tuning(**engine.parse_tuning(args.tune))
     dev = torch.device('cuda', local)
+    stream = torch.cuda.Stream(device=dev)
 
     # resident inputs (device arm) and pinned host inputs (e2e arm)
     frames_d = torch.from_numpy(seq.frames).to(dev)
@@ -258,101 +299,151 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for s in range(args.warmup):
-        step(s)
-    sync_all()
-    eng.profile_enable(True)
-    launches0 = eng.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for s in range(args.steps):
-        step(args.warmup + s)
-    if world > 1:
-        torch.cuda.current_stream(dev).wait_stream(side)
-    e1.record()
-    sync_all()
-    elapsed_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = eng.launch_count() - launches0
-    prof = eng.profile_read()
-    eng.profile_enable(False)
+    warm = max(args.warmup, N_BATCHES + 1)     # every resident batch once: its launch sequence is captured then
+    with torch.cuda.stream(stream):
+        for s in range(warm):
+            step(s)
+        sync_all()
+        # (1) the timed region: K steps as the caller sees them (graph replay when tuning.use_graph)
+        launches0 = eng.launch_count()
+        sampler = ClockSampler(local)
+        if rank == 0 and headline:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for s in range(steps):
+            step(warm + s)
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(side)
+        e1.record()
+        sync_all()
+        elapsed_ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if (rank == 0 and headline) else None
+        launches = eng.launch_count() - launches0
+        # (2) per-kernel-class device times: the same steps again with CUDA events around every launch group
+        # (profiling launches kernel by kernel, so it is kept out of the timed region above)
+        psteps = max(2, min(steps, 8))
+        eng.profile_enable(True)
+        for s in range(psteps):
+            step(warm + s)
+        sync_all()
+        prof = eng.profile_read()
+        eng.profile_enable(False)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    value = world * B * steps / (elapsed_ms * 1e-3)
 
     # ---- e2e: host buffers through the C-ABI host call, copies inside the timed region ----
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
         t.numpy()[...] = a
         return t.numpy()
+    npx = W * H
+    pb = eng.packed_mask_bytes
     frames_h = pinned(seq.frames)
     seg_h = pinned(seq.segmentation)
+    segbits_h = pinned(eng.pack_mask_host(seq.segmentation))
     samples_h = pinned(wl['samples'])
-    from mav_detection_b200._lib import HOST_SLOTS
     fixed_h = [pinned(np.zeros((B, H, W), np.uint8)) for _ in range(HOST_SLOTS)]
+    fixedbits_h = [pinned(np.zeros((B, pb), np.uint8)) for _ in range(HOST_SLOTS)]
     rec_h = [pinned(np.zeros((B,), engine.RECORD_DTYPE).view(np.uint8)).view(engine.RECORD_DTYPE)
              for _ in range(HOST_SLOTS)]
 
-    def step_host(s):
-        # the public host call, pipelined: batch s's host->device copies overlap batch s-1's kernels and
-        # batch s-2's device->host copies (mavd_submit_host / mavd_wait_host, HOST_SLOTS staging sets)
-        b = s % N_BATCHES
-        f0 = b * B
-        slot = s % HOST_SLOTS
-        eng.wait_host(slot)
-        eng.submit_host(slot, frames_h[f0:f0 + B + 1], imus[b], samples_h[f0:f0 + B], seg=seg_h[f0 + 1:f0 + B + 1],
-                        fixed_out=fixed_h[slot], records=rec_h[slot])
-
-    def drain_host():
-        for slot in range(HOST_SLOTS):
+    def host_pass(packed: bool, copy_only: bool, n_steps: int) -> float:
+        """pairs/s of this rank's pipelined host calls: batch s's host->device copies overlap batch s-1's kernels
+        and batch s-2's device->host copies (mavd_submit_host_ex / mavd_wait_host, HOST_SLOTS staging sets)."""
+        def one(s):
+            b = s % N_BATCHES
+            f0 = b * B
+            slot = s % HOST_SLOTS
             eng.wait_host(slot)
-    for s in range(min(args.warmup, 3)):
-        step_host(s)
-    drain_host()
-    sync_all()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        step_host(args.warmup + s)
-    drain_host()                       # every step's records and masks have landed in host memory
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * B * args.steps / e2e_s
-    npx = W * H
-    h2d = (B + 1) * npx + B * npx + B * 4000 * 4
-    d2h = B * engine.RECORD_DTYPE.itemsize + B * npx
+            if packed:
+                eng.submit_host(slot, frames_h[f0:f0 + B + 1], imus[b], samples_h[f0:f0 + B],
+                                seg=segbits_h[f0 + 1:f0 + B + 1], fixed_out=fixedbits_h[slot], records=rec_h[slot],
+                                seg_packed=True, fixed_packed=True, copy_only=copy_only)
+            else:
+                eng.submit_host(slot, frames_h[f0:f0 + B + 1], imus[b], samples_h[f0:f0 + B],
+                                seg=seg_h[f0 + 1:f0 + B + 1], fixed_out=fixed_h[slot], records=rec_h[slot],
+                                copy_only=copy_only)
 
+        def drain():
+            for slot in range(HOST_SLOTS):
+                eng.wait_host(slot)
+        with torch.cuda.stream(stream):
+            for s in range(3):
+                one(s)
+            drain()
+            sync_all()
+            t0 = time.perf_counter()
+            for s in range(n_steps):
+                one(3 + s)
+            drain()                       # every step's records and masks have landed in host memory
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * B * n_steps / dt
+
+    e2e_value = host_pass(True, False, steps)
+    h2d = (B + 1) * npx + B * pb + B * 4000 * 4
+    d2h = B * engine.RECORD_DTYPE.itemsize + B * pb
+    e2e_detail = None
+    if headline:
+        short = max(4, steps // 2)
+        e2e_detail = {
+            'packed_masks': e2e_value,
+            'byte_masks': host_pass(False, False, short),
+            'copy_only_packed_masks': host_pass(True, True, short),
+            'copy_only_byte_masks': host_pass(False, True, short),
+            'bytes_per_step_byte_masks': {'h2d': int((B + 1) * npx + B * npx + B * 16000),
+                                          'd2h': int(B * engine.RECORD_DTYPE.itemsize + B * npx)},
+            'note': 'copy_only_* = the same host calls with the compute skipped (MAVD_HOST_COPY_ONLY): the host-feed '
+                    'ceiling of this box at this N; byte_masks = segmentation in / estimate_fixed out as uint8 images',
+        }
+
+    line = None
     if rank == 0:
         peak, peak_src = hbm_peak()
+        alg = algorithmic_bytes(W, H, params, B, B + 1)
+        per_class = {}
+        for k, (ms, n) in prof.items():
+            if n <= 0:
+                continue
+            ms_step = ms / psteps
+            ent = {'ms_per_step': round(ms_step, 4)}
+            if alg.get(k) and k not in ('pyramid', 'polyexp'):      # those two overlap the side stream: wall time, not kernel time
+                ent['algorithmic_gb_per_step'] = round(alg[k] / 1e9, 3)
+                ent['frac_of_hbm_peak'] = round(alg[k] / (ms_step * 1e-3) / 1e9 / peak, 3)
+            per_class[k] = ent
         it_ms, it_n = prof['iter_full']
         roof = None
         if it_n > 0:
             dur_s = it_ms * 1e-3 / it_n
-            achieved = algorithmic_bytes_iter(W, H, B) / dur_s / 1e9
-            traffic = None
+            ab = 88.0 * W * H * B
+            achieved = ab / dur_s / 1e9
+            traffic, traffic_src = None, None
             try:
                 with open(os.path.join(ROOT, 'profiles', 'iter_kernel_traffic.json')) as f:
-                    per_pair = json.load(f).get(args.workload + '_per_pair')
+                    tj = json.load(f)
+                per_pair = tj.get(name + '_per_pair') or (tj.get('c2_per_pair') if name.startswith('c2') and
+                                                          params == SAMPLE else None)
                 traffic = per_pair * B if per_pair else None      # bytes per launch, like `achieved`
+                traffic_src = tj.get('source')
             except Exception:
                 pass
-            roof = {'bound': 'hbm', 'kernel': 'iter_box_tma_kernel<m, not-last> (fused Farneback iteration), finest level', 'achieved': achieved,
-                    'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak,
-                    'traffic': traffic, 'us_per_launch': dur_s * 1e6, 'us_per_pair': dur_s * 1e6 / B,
-                    'algorithmic_bytes_per_launch': algorithmic_bytes_iter(W, H, B), 'launches_timed': it_n}
-        total_ms = sum(v[0] for v in prof.values())
-        shares = {k: round(v[0] / total_ms, 4) for k, v in prof.items() if v[1] > 0} if total_ms > 0 else {}
+            roof = {'bound': 'hbm', 'kernel': 'iter_box_tma_kernel<m, not-last> (fused Farneback iteration), finest level',
+                    'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': traffic, 'traffic_source': traffic_src,
+                    'frac_by_traffic': (traffic / dur_s / 1e9 / peak) if traffic else None,
+                    'us_per_launch': dur_s * 1e6, 'us_per_pair': dur_s * 1e6 / B,
+                    'algorithmic_bytes_per_launch': ab, 'launches_timed': it_n}
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if world == 1 and headline and not args.no_cpu:
             workers = cpu_workers()
             ref = CpuReference(wl, workers)
             ref.step(workers)                                  # warm-up: page in cv2, first touch
@@ -363,27 +454,74 @@ def run_b200(args):
                    'sample': '%d processes, one pair of this workload at a time (cv2 %s Farneback + oracle/detect_np); '
                              'per pair: flow %.0f ms, FoE/phi/masks %.0f ms; host has %d logical CPUs'
                              % (workers, cv2.__version__, flow_ms, post_ms, os.cpu_count() or 0)}
+        whole_alg = sum(alg.values())
         line = {
-            'metric': '1080p frame-pairs/sec (flow+FoE+mask)' if W == 1920 else 'frame-pairs/sec (flow+FoE+mask)',
-            'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'metric': metric_name(W),
+            'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': steps, 'warmup': warm,
+            'ms_per_step': elapsed_ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': wl['label'], 'pairs_per_step': B, 'frames_resident': int(seq.frames.shape[0]),
                        'l2_policy': 'inputs larger than L2: each step streams a %.1f GB working set'
                                     % (eng.workspace_bytes / 1e9),
                        'sharding': 'each rank runs its own sequence; records all_gathered over NCCL per step'
-                                   if world > 1 else 'single GPU'},
+                                   if world > 1 else 'single GPU',
+                       'tuning': eng.get_tuning()},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                    'call': 'mavd_submit_host/mavd_wait_host (C ABI, pinned host buffers, %d batches in flight)' % HOST_SLOTS},
+                    'call': 'mavd_submit_host_ex/mavd_wait_host (C ABI, pinned host buffers, %d batches in flight; '
+                            'segmentation in and estimate_fixed out at 1 bit per pixel)' % HOST_SLOTS},
+            'e2e_detail': e2e_detail,
             'gpu_launches': int(launches),
             'roofline': roof,
-            'kernel_time_shares': shares,
-            'kernel_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1] > 0},
+            'whole_path_frac_of_hbm_peak': round(whole_alg / (elapsed_ms / steps * 1e-3) / 1e9 / peak, 3),
+            'kernel_classes': per_class,
             'cpu_baseline': cpu,
         }
-        print(json.dumps(line), file=JSON_OUT, flush=True)
     eng.close()
+    del frames_d, seg_d, samples_d, fixed_d, records_d
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    parity = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        # multi-GPU parity before any timing: a sharded sequence must reproduce the single-GPU records
+        from mav_detection_b200 import sharded
+        ok, parity = sharded.parity_check(local)
+        if not ok:
+            if rank == 0:
+                print('bench.py: ' + parity, file=sys.stderr, flush=True)
+            dist.destroy_process_group()
+            sys.exit(3)
+    main_name = 'c2' if args.workload == 'all' else args.workload
+    line = measure(main_name, args, args.steps, world, rank, local, True)
+    if rank == 0 and parity:
+        line['config']['sharded_parity'] = parity
+    if args.workload == 'all':
+        extra = {}
+        for name in EXTRA_ORDER:
+            steps = max(4, min(args.steps, 20 if WORKLOADS[name][0] <= 1920 else 6))
+            if name == 'c1':
+                steps = max(steps, 200)
+            sub = measure(name, args, steps, world, rank, local, False)
+            if rank == 0:
+                extra[name] = {k: sub[k] for k in ('value', 'unit', 'ms_per_step', 'steps', 'e2e', 'gpu_launches', 'roofline',
+                                                   'whole_path_frac_of_hbm_peak', 'kernel_classes')}
+                extra[name]['workload'] = sub['config']['workload']
+                extra[name]['pairs_per_step'] = sub['config']['pairs_per_step']
+        if rank == 0:
+            line['extra'] = extra
+    if rank == 0:
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -394,9 +532,11 @@ def main():
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS) + ['all'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--pairs', type=int, default=0, help='frame pairs per step (default: the workload\'s)')
+    ap.add_argument('--tune', default=os.environ.get('MAVD_TUNE', ''),
+                    help='mavd_tuning fields, e.g. pair_group=8,use_graph=0 (A/B runs; results never depend on them)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     # stdout carries the JSON line and nothing else: keep a private handle on the real stdout for it and point file

@@ -10,7 +10,13 @@
  *  - every function returns an int status (MAVD_OK == 0); nothing throws across this boundary;
  *    mavd_last_error() returns a thread-local message for the last non-zero status
  *  - pointers prefixed d_ are DEVICE pointers, h_ are HOST pointers
- *  - all device entry points are stream-ordered and never retain caller pointers past the call
+ *  - all device entry points are stream-ordered and never retain caller pointers past the call (small host
+ *    arrays such as the imu are copied into library-owned pinned staging before the call returns)
+ *  - a handle owns ONE set of scratch buffers: drive it from one stream at a time (calls on the same stream, or
+ *    calls separated by a synchronisation); use one handle per concurrent stream
+ *  - entry points that take a handle switch to the handle's device for the duration of the call and restore the
+ *    caller's current device before returning; the handle-less entry points run on the CURRENT device, which
+ *    must be the one `stream` and the buffers belong to
  *  - frames are dense row-major (H, W) uint8; flow is dense (H, W, 2) float32, x displacement first
  *    (the layout cv2.calcOpticalFlowFarneback / Dataset.get_flow_uv return)
  *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
@@ -26,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MAVD_ABI_VERSION 1
+#define MAVD_ABI_VERSION 2
 
 enum {
     MAVD_OK = 0,
@@ -86,6 +92,45 @@ typedef struct mavd_detect_params {
     double fixed_angle;         /* 15.0 */
 } mavd_detect_params;
 
+/* Launch-shape choices that never change results (defaults = the measured best on B200).  Set once after
+ * mavd_create with mavd_set_tuning while the handle is idle; tools/gpu_ab.sh A/Bs them through bench.py --tune. */
+typedef struct mavd_tuning {
+    int32_t overlap;      /* 0 = every launch on the caller's stream, 1 = coarse levels on a side stream,
+                             2 = pyramid + coarse levels on the side stream (default) */
+    int32_t pair_group;   /* pairs interleaved per tile in the fused iteration's CTA order (default 4) */
+    int32_t r1_staged;    /* fused iteration: second frame's expansion staged in shared memory by TMA (default 1) */
+    int32_t iter_fuse;    /* not-last iterations: horizontal sums + solve in registers (default 1) */
+    int32_t last_fused;   /* last iteration: the same (default 1) */
+    int32_t mat_coord;    /* level-entry matrices: 0 = recompute resize coordinates (float32 when exact), 1 = read
+                             the host tables, 2 = always recompute in float64 (default 0) */
+    int32_t mat_r0_first; /* level-entry matrices: first frame's loads before the coarse-flow loads (default 1) */
+    int32_t mat_txlog;    /* level-entry matrices: log2 of the block width, 4..8 (default 6: 64 x 4 pixels) */
+    int32_t pyr_staged;   /* pyramid: horizontal pass of the coarse levels through shared memory (default 1) */
+    int32_t use_graph;    /* replay the per-batch launch sequence from a CUDA graph keyed by (n_pairs, pair_stride,
+                             outputs requested) instead of launching kernel by kernel (default 1) */
+    int32_t polyexp_tma;  /* level-0 expansion: u8 tile staged by one TMA box (default 1) */
+    int32_t reserved[5];
+} mavd_tuning;
+
+/* Optional per-frame inputs of the detection stages.  All pointers are DEVICE pointers for the d_ entry points and
+ * HOST pointers for the _host entry points; every member may be NULL.
+ * sky / seg: (H, W) uint8 per frame, stride in bytes between frames (0 = one image shared by all frames; H*W = one per
+ * frame), or 1 bit per pixel when the MAVD_HOST_*_PACKED flag of the host call says so.
+ * gt_flow: (n, H, W, 2) float32 ground-truth flow, Dataset.get_gt_of (src/processor.py:309-310): derotated like the
+ * estimated flow and summed over segmentation > 127 into stats.gt_flow_sum (drone_flow_avg_gt, processor.py:344). */
+typedef struct mavd_aux_inputs {
+    const uint8_t* sky; int64_t sky_stride;
+    const uint8_t* seg; int64_t seg_stride;
+    const float* gt_flow;
+} mavd_aux_inputs;
+
+/* flags of mavd_submit_host_ex / mavd_detect_host_ex */
+#define MAVD_HOST_BGR 1           /* h_frames are (H, W, 3) BGR frames, converted to gray on the device */
+#define MAVD_HOST_SEG_PACKED 2    /* aux.seg is 1 bit per pixel (bit set = 255), mavd_packed_mask_bytes per frame */
+#define MAVD_HOST_SKY_PACKED 4    /* aux.sky is 1 bit per pixel (bit set = sky) */
+#define MAVD_HOST_FIXED_PACKED 8  /* h_fixed_out receives 1 bit per pixel, mavd_packed_mask_bytes per frame */
+#define MAVD_HOST_COPY_ONLY 16    /* move the bytes (and pack / unpack) but skip the compute: the host-feed ceiling */
+
 /* Integer reductions behind FrameResult (src/frame_result.py:4-17, src/processor.py:343-362). */
 typedef struct mavd_frame_stats {
     double max_phi;          /* FocusOfExpansion.max_flow (focus_of_expansion.py:179) */
@@ -97,6 +142,8 @@ typedef struct mavd_frame_stats {
     int64_t tp_fixed, fp_fixed; /* against 255*estimate_fixed                 (processor.py:350) */
     int32_t seg_bbox[4];     /* get_simple_bounding_box(segmentation): x0,y0,x1,y1 or -1 (im_helpers.py:55-84) */
     double seg_flow_sum[2];  /* sum of derotated flow over segmentation > 127 (processor.py:343) */
+    double gt_flow_sum[2];   /* the same sum for the derotated GROUND-TRUTH flow (processor.py:309-310,344); 0 when no
+                                ground-truth flow was given */
 } mavd_frame_stats;
 
 typedef struct mavd_frame_record {
@@ -118,6 +165,9 @@ void mavd_default_detect_params(mavd_detect_params* out);
 int mavd_create(const mavd_config* cfg, mavd_handle* out);
 int mavd_destroy(mavd_handle h);
 int mavd_workspace_bytes(mavd_handle h, size_t* out);
+void mavd_default_tuning(mavd_tuning* out);
+int mavd_set_tuning(mavd_handle h, const mavd_tuning* t); /* the handle must be idle; invalidates captured graphs */
+int mavd_get_tuning(mavd_handle h, mavd_tuning* out);
 /* Pyramid geometry actually used: n_images = capped levels + 1; arrays sized >= 16, finest first. */
 int mavd_level_info(mavd_handle h, int32_t* n_images, int32_t* widths, int32_t* heights);
 
@@ -258,6 +308,37 @@ int mavd_detect_host(mavd_handle h, const float* h_flow, int32_t n, const mavd_i
                      const mavd_detect_params* prm, const int32_t* h_samples, const uint8_t* h_sky,
                      int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride, uint8_t* h_fixed_out,
                      mavd_frame_record* h_records, void* stream);
+
+/* ---- the same calls with every optional per-frame input in one struct (ground-truth flow included) ----
+ * mavd_detect / mavd_process / mavd_submit_host / mavd_detect_host forward to these.  One device call per batch also
+ * for datasets that carry a ground-truth flow (SimData: src/processor.py:309-310,344,359). */
+int mavd_detect_ex(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,
+                   const int32_t* d_samples, const mavd_aux_inputs* d_aux, uint8_t* d_total_out, uint8_t* d_fixed_out,
+                   mavd_frame_record* d_records, void* stream);
+int mavd_process_ex(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride, const mavd_imu* h_imu,
+                    const mavd_detect_params* prm, const int32_t* d_samples, const mavd_aux_inputs* d_aux,
+                    float* d_flow_out, uint8_t* d_total_out, uint8_t* d_fixed_out, mavd_frame_record* d_records,
+                    void* stream);
+/* flags: MAVD_HOST_* above.  With MAVD_HOST_SEG_PACKED / MAVD_HOST_SKY_PACKED the segmentation / sky masks cross the
+ * bus at 1 bit per pixel and are expanded on the device on the copy-in stream; with MAVD_HOST_FIXED_PACKED the
+ * estimate_fixed masks are packed on the copy-out stream and return at 1 bit per pixel (numpy.packbits(mask.ravel(),
+ * bitorder='little') per frame, padded to mavd_packed_mask_bytes).  Sample indices are range-checked on the host. */
+int mavd_submit_host_ex(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32_t n_pairs, int32_t pair_stride,
+                        const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
+                        const mavd_aux_inputs* h_aux, int32_t flags, float* h_flow_out, uint8_t* h_fixed_out,
+                        mavd_frame_record* h_records, void* stream);
+int mavd_detect_host_ex(mavd_handle h, const float* h_flow, int32_t n, const mavd_imu* h_imu,
+                        const mavd_detect_params* prm, const int32_t* h_samples, const mavd_aux_inputs* h_aux,
+                        int32_t flags, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream);
+
+/* ---- 1-bit-per-pixel masks on the wire (ground-truth segmentation in, estimate_fixed out) ----
+ * Bytes one packed (H, W) mask occupies: ceil(H*W / 8) rounded up to a multiple of 4.  Bit k of byte j is pixel
+ * 8*j + k of the flattened frame (numpy bitorder='little'). */
+int64_t mavd_packed_mask_bytes(int32_t width, int32_t height);
+/* d_mask (n, H*W) uint8, any non-zero byte -> bit set; d_bits (n, mavd_packed_mask_bytes) */
+int mavd_pack_mask(const uint8_t* d_mask, int32_t n, int64_t n_pixels, uint8_t* d_bits, void* stream);
+/* the inverse: set bits become `value` (255 for a segmentation image, 1 for a 0/1 mask), clear bits 0 */
+int mavd_unpack_mask(const uint8_t* d_bits, int32_t n, int64_t n_pixels, uint8_t value, uint8_t* d_mask, void* stream);
 
 /* ---- optional per-kernel-class device timing (CUDA events on the launching stream) ---- */
 enum {

@@ -9,6 +9,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libmavd.so')
 
+ABI_VERSION = 2
 MAVD_OK, MAVD_ERR_INVALID, MAVD_ERR_CUDA, MAVD_ERR_UNSUPPORTED, MAVD_ERR_NOMEM = 0, 1, 2, 3, 4
 N_SAMPLE_PAIRS = 1000
 SAMPLES_PER_FRAME = 4 * N_SAMPLE_PAIRS
@@ -42,13 +43,29 @@ class FrameStats(C.Structure):
     _fields_ = [('max_phi', C.c_double), ('n_total', C.c_int64), ('n_fixed', C.c_int64),
                 ('positives', C.c_int64), ('negatives', C.c_int64), ('tp_total', C.c_int64),
                 ('fp_total', C.c_int64), ('tp_fixed', C.c_int64), ('fp_fixed', C.c_int64),
-                ('seg_bbox', C.c_int32 * 4), ('seg_flow_sum', C.c_double * 2)]
+                ('seg_bbox', C.c_int32 * 4), ('seg_flow_sum', C.c_double * 2), ('gt_flow_sum', C.c_double * 2)]
 
 
 class FrameRecord(C.Structure):
     _fields_ = [('foe', C.c_double * 2), ('n_intersections', C.c_int32), ('n_labels', C.c_int32),
                 ('stats', FrameStats), ('boxes', (C.c_int32 * 5) * MAX_BOXES)]
 
+
+class Tuning(C.Structure):
+    """Launch-shape choices (include/mavd.h: mavd_tuning); results never depend on them."""
+    _fields_ = [('overlap', C.c_int32), ('pair_group', C.c_int32), ('r1_staged', C.c_int32), ('iter_fuse', C.c_int32),
+                ('last_fused', C.c_int32), ('mat_coord', C.c_int32), ('mat_r0_first', C.c_int32),
+                ('mat_txlog', C.c_int32), ('pyr_staged', C.c_int32), ('use_graph', C.c_int32),
+                ('polyexp_tma', C.c_int32), ('reserved', C.c_int32 * 5)]
+
+
+class AuxInputs(C.Structure):
+    """Optional per-frame inputs of the detection stages (include/mavd.h: mavd_aux_inputs)."""
+    _fields_ = [('sky', C.c_void_p), ('sky_stride', C.c_int64), ('seg', C.c_void_p), ('seg_stride', C.c_int64),
+                ('gt_flow', C.c_void_p)]
+
+
+HOST_BGR, HOST_SEG_PACKED, HOST_SKY_PACKED, HOST_FIXED_PACKED, HOST_COPY_ONLY = 1, 2, 4, 8, 16
 
 PROF_CLASSES = 12
 PROF_NAMES = ['pyramid', 'polyexp', 'matrices', 'iter_full', 'iter_full_last', 'iter_coarse', 'foe', 'residual',
@@ -68,6 +85,9 @@ SIGNATURES = {
     'mavd_create': (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     'mavd_destroy': (C.c_int, [_P]),
     'mavd_workspace_bytes': (C.c_int, [_P, C.POINTER(C.c_size_t)]),
+    'mavd_default_tuning': (None, [C.POINTER(Tuning)]),
+    'mavd_set_tuning': (C.c_int, [_P, C.POINTER(Tuning)]),
+    'mavd_get_tuning': (C.c_int, [_P, C.POINTER(Tuning)]),
     'mavd_level_info': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'mavd_bgr2gray': (C.c_int, [_P, _P, C.c_int64, _P]),
     'mavd_farneback': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
@@ -94,6 +114,17 @@ SIGNATURES = {
     'mavd_wait_host': (C.c_int, [_P, C.c_int32]),
     'mavd_detect_host': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P, _P, C.c_int64, _P,
                                    C.c_int64, _P, _P, _P]),
+    'mavd_detect_ex': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P, C.POINTER(AuxInputs),
+                                 _P, _P, _P, _P]),
+    'mavd_process_ex': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
+                                  C.POINTER(AuxInputs), _P, _P, _P, _P, _P]),
+    'mavd_submit_host_ex': (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams),
+                                      _P, C.POINTER(AuxInputs), C.c_int32, _P, _P, _P, _P]),
+    'mavd_detect_host_ex': (C.c_int, [_P, _P, C.c_int32, C.POINTER(Imu), C.POINTER(DetectParams), _P,
+                                      C.POINTER(AuxInputs), C.c_int32, _P, _P, _P]),
+    'mavd_packed_mask_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
+    'mavd_pack_mask': (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
+    'mavd_unpack_mask': (C.c_int, [_P, C.c_int32, C.c_int64, C.c_uint8, _P, _P]),
     'mavd_magnitude': (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     'mavd_simple_bbox': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'mavd_tpr_fpr_counts': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
@@ -126,7 +157,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    assert lib.mavd_abi_version() == 1
+    assert lib.mavd_abi_version() == ABI_VERSION
     _lib = lib
     return lib
 

@@ -196,6 +196,32 @@ struct mavd_handle_full : mavd_handle_s {
     Arena arena;
 };
 
+static void drop_graphs(mavd_handle h);
+
+// streams, events, graphs and pinned staging of a handle (everything but the device arena)
+static void release_host_side(mavd_handle_full* H) {
+    drop_graphs(H);
+    for (auto& S : H->slot) {
+        if (S.ev_in) cudaEventDestroy(S.ev_in);
+        if (S.ev_done) cudaEventDestroy(S.ev_done);
+        if (S.ev_out) cudaEventDestroy(S.ev_out);
+    }
+    if (H->s_aux) cudaStreamDestroy(H->s_aux);
+    if (H->ev_fork) cudaEventDestroy(H->ev_fork);
+    if (H->ev_join) cudaEventDestroy(H->ev_join);
+    if (H->ev_pyr) cudaEventDestroy(H->ev_pyr);
+    if (H->s_in) cudaStreamDestroy(H->s_in);
+    if (H->s_out) cudaStreamDestroy(H->s_out);
+    if (H->s_main) cudaStreamDestroy(H->s_main);
+    if (H->ev_main_in) cudaEventDestroy(H->ev_main_in);
+    if (H->ev_main_out) cudaEventDestroy(H->ev_main_out);
+    for (cudaEvent_t e : H->imu_ev)
+        if (e) cudaEventDestroy(e);
+    if (H->h_imu_ring) cudaFreeHost(H->h_imu_ring);
+    for (auto& r : H->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : H->prof.pool) cudaEventDestroy(e);
+}
+
 #define TRY(x)                       \
     do {                             \
         int rc__ = (x);              \
@@ -246,10 +272,11 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
     MAVD_CUDA(cudaGetDeviceCount(&ndev));
     MAVD_REQUIRE(cfg->device >= 0 && cfg->device < ndev, MAVD_ERR_CUDA, "CUDA device %d not available (%d devices)",
                  cfg->device, ndev);
-    MAVD_CUDA(cudaSetDevice(cfg->device));
+    DeviceGuard dg(cfg->device);
     mavd_handle_full* H = new (std::nothrow) mavd_handle_full();
     MAVD_REQUIRE(H != nullptr, MAVD_ERR_NOMEM, "out of host memory");
     H->cfg = *cfg;
+    mavd_default_tuning(&H->tune);
     const mavd_farneback_params& fp = cfg->farneback;
     const int W = cfg->width, Hh = cfg->height, B = cfg->max_pairs;
     const int F = 2 * B;  // worst case: independent pairs
@@ -258,6 +285,7 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
     int rc = MAVD_OK;
     auto fail = [&](int code) {
         for (void* p : A.ptrs) cudaFree(p);
+        release_host_side(H);
         delete H;
         return code;
     };
@@ -400,8 +428,21 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
             cudaGetLastError();
             H->s_aux = nullptr;   // the path still works, just without the overlap
         }
-        const char* env = getenv("MAVD_OVERLAP");
-        if (env && env[0] >= '0' && env[0] <= '2') H->overlap_mode = env[0] - '0';
+        if (cudaStreamCreateWithFlags(&H->s_main, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&H->ev_main_in, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&H->ev_main_out, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            H->s_main = nullptr;  // default-stream calls then launch directly (no graph replay)
+        }
+    }
+    {
+        cudaError_t e = cudaMallocHost((void**)&H->h_imu_ring, sizeof(mavd_imu) * mavd_handle_s::kImuRing * (size_t)B);
+        for (int k = 0; e == cudaSuccess && k < mavd_handle_s::kImuRing; ++k)
+            e = cudaEventCreateWithFlags(&H->imu_ev[k], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            set_error("imu staging: %s", cudaGetErrorString(e));
+            return fail(e == cudaErrorMemoryAllocation ? MAVD_ERR_NOMEM : MAVD_ERR_CUDA);
+        }
     }
     H->bytes = A.bytes;
     cudaError_t e = cudaDeviceSynchronize();
@@ -417,29 +458,51 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
 int mavd_destroy(mavd_handle h) {
     if (!h) return MAVD_OK;
     mavd_handle_full* H = static_cast<mavd_handle_full*>(h);
-    cudaSetDevice(H->cfg.device);
+    DeviceGuard dg(H->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : H->arena.ptrs) cudaFree(p);
-    for (auto& S : H->slot) {
-        if (S.ev_in) cudaEventDestroy(S.ev_in);
-        if (S.ev_done) cudaEventDestroy(S.ev_done);
-        if (S.ev_out) cudaEventDestroy(S.ev_out);
-    }
-    if (H->s_aux) cudaStreamDestroy(H->s_aux);
-    if (H->ev_fork) cudaEventDestroy(H->ev_fork);
-    if (H->ev_join) cudaEventDestroy(H->ev_join);
-    if (H->ev_pyr) cudaEventDestroy(H->ev_pyr);
-    if (H->s_in) cudaStreamDestroy(H->s_in);
-    if (H->s_out) cudaStreamDestroy(H->s_out);
-    for (auto& r : H->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-    for (cudaEvent_t e : H->prof.pool) cudaEventDestroy(e);
+    release_host_side(H);
     delete H;
+    return MAVD_OK;
+}
+
+void mavd_default_tuning(mavd_tuning* t) {
+    if (!t) return;
+    memset(t, 0, sizeof(*t));
+    t->overlap = 2;
+    t->pair_group = 4;
+    t->r1_staged = 1;
+    t->iter_fuse = 1;
+    t->last_fused = 1;
+    t->mat_coord = 0;
+    t->mat_r0_first = 1;
+    t->mat_txlog = 6;
+    t->pyr_staged = 1;
+    t->use_graph = 1;
+    t->polyexp_tma = 1;
+}
+
+int mavd_set_tuning(mavd_handle h, const mavd_tuning* t) {
+    MAVD_REQUIRE(h && t, MAVD_ERR_INVALID, "set_tuning: NULL argument");
+    MAVD_REQUIRE(t->overlap >= 0 && t->overlap <= 2 && t->pair_group >= 1 && t->mat_coord >= 0 && t->mat_coord <= 2 &&
+                     t->mat_txlog >= 4 && t->mat_txlog <= 8 && t->iter_fuse >= 0 && t->iter_fuse <= 2,
+                 MAVD_ERR_INVALID, "set_tuning: value out of range");
+    DeviceGuard dg(h->cfg.device);
+    MAVD_CUDA(cudaDeviceSynchronize());
+    drop_graphs(h);
+    h->tune = *t;
+    return MAVD_OK;
+}
+
+int mavd_get_tuning(mavd_handle h, mavd_tuning* out) {
+    MAVD_REQUIRE(h && out, MAVD_ERR_INVALID, "get_tuning: NULL argument");
+    *out = h->tune;
     return MAVD_OK;
 }
 
 int mavd_profile_enable(mavd_handle h, int32_t on) {
     MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "profile: handle is NULL");
-    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     MAVD_CUDA(cudaDeviceSynchronize());
     for (auto& r : h->prof.recs) { h->prof.pool.push_back(r.a); h->prof.pool.push_back(r.b); }
     h->prof.recs.clear();
@@ -450,7 +513,7 @@ int mavd_profile_enable(mavd_handle h, int32_t on) {
 int mavd_profile_read(mavd_handle h, mavd_profile* out) {
     MAVD_REQUIRE(h && out, MAVD_ERR_INVALID, "profile: NULL argument");
     memset(out, 0, sizeof(*out));
-    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     for (auto& r : h->prof.recs) {
         MAVD_CUDA(cudaEventSynchronize(r.b));
         float ms = 0.f;
@@ -465,7 +528,7 @@ int mavd_profile_read(mavd_handle h, mavd_profile* out) {
 
 int mavd_profile_timeline(mavd_handle h, double* out, int32_t max_records, int32_t* n_out) {
     MAVD_REQUIRE(h && out && n_out, MAVD_ERR_INVALID, "profile_timeline: NULL argument");
-    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     int n = 0;
     if (!h->prof.recs.empty()) {
         cudaEvent_t base = h->prof.recs[0].a;
@@ -485,6 +548,9 @@ int mavd_profile_timeline(mavd_handle h, double* out, int32_t max_records, int32
 
 int mavd_debug_force_generic_iteration(mavd_handle h, int32_t on) {
     MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "handle is NULL");
+    DeviceGuard dg(h->cfg.device);
+    MAVD_CUDA(cudaDeviceSynchronize());
+    drop_graphs(h);                    // the flag changes the launch sequence
     h->force_generic_iter = on != 0;
     return MAVD_OK;
 }
@@ -515,21 +581,20 @@ static int check_batch(mavd_handle h, int n, const char* what) {
     MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "%s: handle is NULL", what);
     MAVD_REQUIRE(n >= 0 && n <= h->cfg.max_pairs, MAVD_ERR_INVALID, "%s: batch %d exceeds max_pairs %d", what, n,
                  h->cfg.max_pairs);
-    MAVD_CUDA(cudaSetDevice(h->cfg.device));
     return MAVD_OK;
 }
 
-int mavd_farneback(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride, float* d_flow,
-                   void* stream) {
-    TRY(check_batch(h, n_pairs, "farneback"));
-    MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
-    if (n_pairs == 0) return MAVD_OK;
-    MAVD_REQUIRE(d_frames && d_flow, MAVD_ERR_INVALID, "farneback: NULL buffer");
-    return farneback_run(h, d_frames, n_pairs, pair_stride, d_flow, (cudaStream_t)stream);
+// taps read "the last mavd_farneback call": recorded here, outside the (possibly replayed) launch sequence
+static void note_farneback_call(mavd_handle h, const uint8_t* d_frames, int n_pairs, int pair_stride, float* d_flow) {
+    h->last_pairs = n_pairs;
+    h->last_stride = pair_stride;
+    h->last_flow0 = d_flow;
+    h->last_frames = d_frames;
 }
 
 int mavd_farneback_tap(mavd_handle h, int32_t kind, int32_t level, int32_t index, float* d_out, void* stream) {
     MAVD_REQUIRE(h && d_out, MAVD_ERR_INVALID, "tap: NULL argument");
+    DeviceGuard dg(h->cfg.device);
     MAVD_REQUIRE(index >= 0 && index < h->max_frames, MAVD_ERR_INVALID, "tap: index out of range");
     return farneback_tap(h, kind, level, index, d_out, (cudaStream_t)stream);
 }
@@ -547,11 +612,20 @@ static int upload_imu(mavd_handle h, const mavd_imu* h_imu, int n, cudaStream_t 
     }
     if (n64) *n64 = a;
     if (n32) *n32 = b;
-    MAVD_CUDA(cudaMemcpyAsync(h->d_imu, h_imu, sizeof(mavd_imu) * n, cudaMemcpyHostToDevice, s));
+    // the caller's array is not retained: it is copied into the next pinned ring slot, and the asynchronous upload
+    // reads that slot (a slot is rewritten only after the upload that used it has completed)
+    const int k = h->imu_next;
+    h->imu_next = (k + 1) % mavd_handle_s::kImuRing;
+    MAVD_CUDA(cudaEventSynchronize(h->imu_ev[k]));
+    mavd_imu* stage = h->h_imu_ring + (size_t)k * h->cfg.max_pairs;
+    memcpy(stage, h_imu, sizeof(mavd_imu) * n);
+    MAVD_CUDA(cudaMemcpyAsync(h->d_imu, stage, sizeof(mavd_imu) * n, cudaMemcpyHostToDevice, s));
+    MAVD_CUDA(cudaEventRecord(h->imu_ev[k], s));
     return MAVD_OK;
 }
 
 int mavd_derotate(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, double* d_out, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n, "derotate"));
     if (n == 0) return MAVD_OK;
     MAVD_REQUIRE(d_flow && d_out, MAVD_ERR_INVALID, "derotate: NULL buffer");
@@ -560,6 +634,7 @@ int mavd_derotate(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu*
 }
 
 int mavd_derotate_f64(mavd_handle h, const double* d_flow, int32_t n, const mavd_imu* h_imu, double* d_out, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n, "derotate_f64"));
     if (n == 0) return MAVD_OK;
     MAVD_REQUIRE(d_flow && d_out, MAVD_ERR_INVALID, "derotate_f64: NULL buffer");
@@ -569,6 +644,7 @@ int mavd_derotate_f64(mavd_handle h, const double* d_flow, int32_t n, const mavd
 
 int mavd_foe(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,
              const int32_t* d_samples, double* d_foe, int32_t* d_n_intersections, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n, "foe"));
     if (n == 0) return MAVD_OK;
     MAVD_REQUIRE(d_flow && d_samples && d_foe, MAVD_ERR_INVALID, "foe: NULL buffer");
@@ -581,6 +657,7 @@ int mavd_foe(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_im
 
 int mavd_foe_dense(mavd_handle h, const void* d_flow, int32_t flow_is_f64, int32_t n, const mavd_detect_params* prm,
                    const int32_t* d_samples, double* d_foe, int32_t* d_n_intersections, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n, "foe_dense"));
     if (n == 0) return MAVD_OK;
     MAVD_REQUIRE(d_flow && d_samples && d_foe, MAVD_ERR_INVALID, "foe_dense: NULL buffer");
@@ -594,12 +671,13 @@ int mavd_ransac(mavd_handle h, const double* d_estimates, int32_t k, double rans
                 void* stream) {
     MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "ransac: handle is NULL");
     MAVD_REQUIRE(k >= 0 && d_foe && (k == 0 || d_estimates), MAVD_ERR_INVALID, "ransac: bad arguments");
-    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     return ransac_run(d_estimates, k, ransac_threshold, d_foe, (cudaStream_t)stream);
 }
 
 int mavd_get_phi(mavd_handle h, const void* d_flow, int32_t flow_is_f64, int32_t n, const double* d_foe, void* d_phi,
                  double* d_max_phi, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n, "get_phi"));
     if (n == 0) return MAVD_OK;
     MAVD_REQUIRE(d_flow && d_foe && d_phi, MAVD_ERR_INVALID, "get_phi: NULL buffer");
@@ -613,6 +691,9 @@ int mavd_get_phi(mavd_handle h, const void* d_flow, int32_t flow_is_f64, int32_t
 
 int mavd_debug_force_exact_residual(mavd_handle h, int32_t on) {
     MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "handle is NULL");
+    DeviceGuard dg(h->cfg.device);
+    MAVD_CUDA(cudaDeviceSynchronize());
+    drop_graphs(h);
     h->force_exact_residual = on != 0;
     return MAVD_OK;
 }
@@ -621,6 +702,7 @@ int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mav
                         const mavd_detect_params* prm, const double* d_foe, const uint8_t* d_sky, int64_t sky_stride,
                         const uint8_t* d_seg, int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed,
                         mavd_frame_stats* d_stats, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n, "residual_masks"));
     if (n == 0) return MAVD_OK;
     MAVD_REQUIRE(d_flow && d_foe, MAVD_ERR_INVALID, "residual_masks: NULL buffer");
@@ -634,6 +716,7 @@ int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mav
 
 int mavd_ccl(mavd_handle h, const uint8_t* d_mask, int32_t n, int32_t* d_labels, int32_t* d_boxes, int32_t max_boxes,
              int32_t* d_n_labels, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n, "ccl"));
     if (n == 0) return MAVD_OK;
     MAVD_REQUIRE(d_mask && d_n_labels, MAVD_ERR_INVALID, "ccl: NULL buffer");
@@ -673,18 +756,19 @@ __global__ void records_fill_kernel(mavd_frame_record* rec, const double* foe, c
     rec[f].n_intersections = ninter[f];
 }
 
+static const mavd_aux_inputs kNoAux = {nullptr, 0, nullptr, 0, nullptr};
+
 static int detect_run(mavd_handle h, const float* flow, int n, const mavd_detect_params& p, int n64, int n32,
-                      const int32_t* d_samples, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
-                      int64_t seg_stride, uint8_t* d_total_out, uint8_t* fixed, mavd_frame_record* d_records,
-                      cudaStream_t s) {
+                      const int32_t* d_samples, const mavd_aux_inputs& aux, uint8_t* d_total_out, uint8_t* fixed,
+                      mavd_frame_record* d_records, cudaStream_t s) {
     TRY(foe_run(h, flow, 0, n, h->d_imu, p, d_samples, h->d_foe, h->d_ninter, s));
     char* stats0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, stats);
     // the residual kernel lists the 128-pixel units of the fixed mask that hold foreground; the labelling passes then
     // visit only those (detection masks are almost empty)
     TRY(ccl_list_reset(h, n, s));
-    TRY(residual_run(h, flow, 0, n, h->d_imu, p, h->d_foe, d_sky, sky_stride, d_seg, seg_stride, nullptr, d_total_out,
-                     fixed, reinterpret_cast<mavd_frame_stats*>(stats0), sizeof(mavd_frame_record), n64 > 0, n32 > 0, s,
-                     true));
+    TRY(residual_run(h, flow, 0, n, h->d_imu, p, h->d_foe, aux.sky, aux.sky_stride, aux.seg, aux.seg_stride, nullptr,
+                     d_total_out, fixed, reinterpret_cast<mavd_frame_stats*>(stats0), sizeof(mavd_frame_record), n64 > 0,
+                     n32 > 0, s, true, aux.gt_flow));
     int32_t* boxes0 = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, boxes));
     char* nl0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, n_labels);
     TRY(ccl_run(h, fixed, n, nullptr, boxes0, sizeof(mavd_frame_record) / sizeof(int32_t), MAVD_MAX_BOXES,
@@ -694,78 +778,307 @@ static int detect_run(mavd_handle h, const float* flow, int n, const mavd_detect
     return MAVD_OK;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Captured launch sequences.  One batch is ~50 launches on two streams; at small frame sizes (C1: one 640x480 pair)
+// the launches, not the kernels, are the cost.  The sequence for a given argument tuple is captured once with stream
+// capture (the side stream joins the capture through its fork / join events) and replayed as ONE graph launch.
+// Everything that shapes the sequence is part of the key: buffers, batch geometry, detection parameters, which
+// residual modes run.  The imu upload stays outside the graph (its contents change every call, the device buffer does
+// not).  With profiling on, on a stream that is already being captured, or when capture fails, the launches go out
+// directly — same kernels, same arguments.
+// ------------------------------------------------------------------------------------------------
+static constexpr size_t kMaxGraphs = 16;
+
+struct KeyBuilder {
+    std::vector<uint64_t> k;
+    KeyBuilder& operator()(const void* p) { k.push_back((uint64_t)(uintptr_t)p); return *this; }
+    KeyBuilder& operator()(int64_t v) { k.push_back((uint64_t)v); return *this; }
+    KeyBuilder& operator()(const mavd_detect_params& p) {
+        const size_t n = sizeof(p) / sizeof(uint64_t);
+        uint64_t w[sizeof(mavd_detect_params) / sizeof(uint64_t)];
+        memcpy(w, &p, sizeof(p));
+        k.insert(k.end(), w, w + n);
+        return *this;
+    }
+    KeyBuilder& operator()(const mavd_aux_inputs& a) {
+        return (*this)(a.sky)(a.sky_stride)(a.seg)(a.seg_stride)((const void*)a.gt_flow);
+    }
+};
+
+static void drop_graphs(mavd_handle h) {
+    for (auto& g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
+template <typename F>
+static int run_graphed(mavd_handle h, std::vector<uint64_t>&& key, cudaStream_t s, F&& body) {
+    if (!h->tune.use_graph || h->prof.on || s == nullptr) return body(s);
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return body(s);
+    }
+    for (auto& g : h->graphs) {
+        if (g.key != key) continue;
+        g.last_use = ++h->graph_clock;
+        if (!g.exec) return body(s);        // this sequence could not be captured: direct launches
+        MAVD_CUDA(cudaGraphLaunch(g.exec, s));
+        g_launches.fetch_add(g.launches, std::memory_order_relaxed);
+        return MAVD_OK;
+    }
+    mavd_handle_s::GraphEntry ent;
+    ent.key = std::move(key);
+    ent.last_use = ++h->graph_clock;
+    const int64_t l0 = g_launches.load();
+    int rc = MAVD_OK;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        rc = body(s);
+        const cudaError_t e = cudaStreamEndCapture(s, &graph);
+        const int64_t nl = g_launches.load() - l0;
+        g_launches.fetch_sub(nl, std::memory_order_relaxed);        // captured, not run
+        if (rc == MAVD_OK && e == cudaSuccess && graph &&
+            cudaGraphInstantiate(&ent.exec, graph, 0) == cudaSuccess) {
+            ent.launches = nl;
+        } else {
+            ent.exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc != MAVD_OK) return rc;       // a real error (bad argument, failed launch configuration): report it
+    } else {
+        cudaGetLastError();
+    }
+    if (h->graphs.size() >= kMaxGraphs) {
+        size_t lru = 0;
+        for (size_t i = 1; i < h->graphs.size(); ++i)
+            if (h->graphs[i].last_use < h->graphs[lru].last_use) lru = i;
+        if (h->graphs[lru].exec) cudaGraphExecDestroy(h->graphs[lru].exec);
+        h->graphs.erase(h->graphs.begin() + lru);
+    }
+    h->graphs.push_back(ent);
+    if (!ent.exec) return body(s);
+    MAVD_CUDA(cudaGraphLaunch(ent.exec, s));
+    g_launches.fetch_add(ent.launches, std::memory_order_relaxed);
+    return MAVD_OK;
+}
+
+// Work submitted on the legacy default stream (which cannot be captured) runs on the handle's own stream, ordered
+// after / before the default stream by two events: same semantics for the caller.
+struct StreamScope {
+    mavd_handle h;
+    cudaStream_t user, s;
+    bool redirected = false;
+    StreamScope(mavd_handle h_, void* stream) : h(h_), user((cudaStream_t)stream), s((cudaStream_t)stream) {
+        if (user != nullptr || !h->tune.use_graph || h->prof.on || !h->s_main) return;
+        if (cudaEventRecord(h->ev_main_in, user) != cudaSuccess ||
+            cudaStreamWaitEvent(h->s_main, h->ev_main_in, 0) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        s = h->s_main;
+        redirected = true;
+    }
+    ~StreamScope() {
+        if (!redirected) return;
+        if (cudaEventRecord(h->ev_main_out, s) != cudaSuccess || cudaStreamWaitEvent(user, h->ev_main_out, 0) != cudaSuccess)
+            cudaGetLastError();
+    }
+};
+
+extern "C" {
+
+int mavd_farneback(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride, float* d_flow,
+                   void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
+    TRY(check_batch(h, n_pairs, "farneback"));
+    MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
+    if (n_pairs == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_frames && d_flow, MAVD_ERR_INVALID, "farneback: NULL buffer");
+    StreamScope ss(h, stream);
+    note_farneback_call(h, d_frames, n_pairs, pair_stride, d_flow);
+    return run_graphed(h, std::move(KeyBuilder()(int64_t(1))(d_frames)(int64_t(n_pairs))(int64_t(pair_stride))(d_flow).k),
+                       ss.s, [&](cudaStream_t s) { return farneback_run(h, d_frames, n_pairs, pair_stride, d_flow, s); });
+}
+
+int mavd_detect_ex(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,
+                   const int32_t* d_samples, const mavd_aux_inputs* d_aux, uint8_t* d_total_out, uint8_t* d_fixed_out,
+                   mavd_frame_record* d_records, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
+    TRY(check_batch(h, n, "detect"));
+    if (n == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_flow && d_samples && d_records, MAVD_ERR_INVALID, "detect: NULL buffer");
+    StreamScope ss(h, stream);
+    mavd_detect_params p;
+    if (prm) p = *prm; else mavd_default_detect_params(&p);
+    const mavd_aux_inputs aux = d_aux ? *d_aux : kNoAux;
+    int n64 = 0, n32 = 0;
+    TRY(upload_imu(h, h_imu, n, ss.s, &n64, &n32));
+    uint8_t* fixed = d_fixed_out ? d_fixed_out : h->d_fixed;
+    return run_graphed(h, std::move(KeyBuilder()(int64_t(2))(d_flow)(int64_t(n))(p)(int64_t(n64))(int64_t(n32))(d_samples)(aux)
+                                        (d_total_out)(fixed)(d_records).k),
+                       ss.s, [&](cudaStream_t s) {
+                           return detect_run(h, d_flow, n, p, n64, n32, d_samples, aux, d_total_out, fixed, d_records, s);
+                       });
+}
+
 int mavd_detect(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,
                 const int32_t* d_samples, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
                 int64_t seg_stride, uint8_t* d_total_out, uint8_t* d_fixed_out, mavd_frame_record* d_records,
                 void* stream) {
-    TRY(check_batch(h, n, "detect"));
-    if (n == 0) return MAVD_OK;
-    MAVD_REQUIRE(d_flow && d_samples && d_records, MAVD_ERR_INVALID, "detect: NULL buffer");
-    cudaStream_t s = (cudaStream_t)stream;
+    const mavd_aux_inputs aux = {d_sky, sky_stride, d_seg, seg_stride, nullptr};
+    return mavd_detect_ex(h, d_flow, n, h_imu, prm, d_samples, &aux, d_total_out, d_fixed_out, d_records, stream);
+}
+
+int mavd_process_ex(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride, const mavd_imu* h_imu,
+                    const mavd_detect_params* prm, const int32_t* d_samples, const mavd_aux_inputs* d_aux,
+                    float* d_flow_out, uint8_t* d_total_out, uint8_t* d_fixed_out, mavd_frame_record* d_records,
+                    void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
+    TRY(check_batch(h, n_pairs, "process"));
+    MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
+    if (n_pairs == 0) return MAVD_OK;
+    MAVD_REQUIRE(d_frames && d_samples && d_records, MAVD_ERR_INVALID, "process: NULL buffer");
+    StreamScope ss(h, stream);
     mavd_detect_params p;
     if (prm) p = *prm; else mavd_default_detect_params(&p);
+    const mavd_aux_inputs aux = d_aux ? *d_aux : kNoAux;
+    float* flow = d_flow_out ? d_flow_out : h->d_flow;
+    uint8_t* fixed = d_fixed_out ? d_fixed_out : h->d_fixed;
     int n64 = 0, n32 = 0;
-    TRY(upload_imu(h, h_imu, n, s, &n64, &n32));
-    return detect_run(h, d_flow, n, p, n64, n32, d_samples, d_sky, sky_stride, d_seg, seg_stride, d_total_out,
-                      d_fixed_out ? d_fixed_out : h->d_fixed, d_records, s);
+    TRY(upload_imu(h, h_imu, n_pairs, ss.s, &n64, &n32));
+    note_farneback_call(h, d_frames, n_pairs, pair_stride, flow);
+    return run_graphed(h, std::move(KeyBuilder()(int64_t(3))(d_frames)(int64_t(n_pairs))(int64_t(pair_stride))(p)(int64_t(n64))
+                                        (int64_t(n32))(d_samples)(aux)(flow)(d_total_out)(fixed)(d_records).k),
+                       ss.s, [&](cudaStream_t s) {
+                           TRY(farneback_run(h, d_frames, n_pairs, pair_stride, flow, s));
+                           return detect_run(h, flow, n_pairs, p, n64, n32, d_samples, aux, d_total_out, fixed, d_records, s);
+                       });
 }
 
 int mavd_process(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int32_t pair_stride, const mavd_imu* h_imu,
                  const mavd_detect_params* prm, const int32_t* d_samples, const uint8_t* d_sky, int64_t sky_stride,
                  const uint8_t* d_seg, int64_t seg_stride, float* d_flow_out, uint8_t* d_total_out,
                  uint8_t* d_fixed_out, mavd_frame_record* d_records, void* stream) {
-    TRY(check_batch(h, n_pairs, "process"));
-    MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
-    if (n_pairs == 0) return MAVD_OK;
-    MAVD_REQUIRE(d_frames && d_samples && d_records, MAVD_ERR_INVALID, "process: NULL buffer");
-    cudaStream_t s = (cudaStream_t)stream;
-    mavd_detect_params p;
-    if (prm) p = *prm; else mavd_default_detect_params(&p);
-    float* flow = d_flow_out ? d_flow_out : h->d_flow;
-    int n64 = 0, n32 = 0;
-    TRY(upload_imu(h, h_imu, n_pairs, s, &n64, &n32));
-    TRY(farneback_run(h, d_frames, n_pairs, pair_stride, flow, s));
-    return detect_run(h, flow, n_pairs, p, n64, n32, d_samples, d_sky, sky_stride, d_seg, seg_stride, d_total_out,
-                      d_fixed_out ? d_fixed_out : h->d_fixed, d_records, s);
+    const mavd_aux_inputs aux = {d_sky, sky_stride, d_seg, seg_stride, nullptr};
+    return mavd_process_ex(h, d_frames, n_pairs, pair_stride, h_imu, prm, d_samples, &aux, d_flow_out, d_total_out,
+                           d_fixed_out, d_records, stream);
 }
 
-static int ensure_slot(mavd_handle h, int slot, bool want_flow_out, bool want_flow_in) {
+// ------------------------------------------------------------------------------------------------
+// Host-buffer calls: three-stage pipeline over MAVD_HOST_SLOTS staging sets (copy-in stream, the caller's compute
+// stream, copy-out stream).
+// ------------------------------------------------------------------------------------------------
+static int ensure_slot(mavd_handle h, int slot, bool want_flow_out, bool want_flow_in, bool want_bits_in, bool want_bits_out,
+                       bool want_gt) {
     mavd_handle_full* H = static_cast<mavd_handle_full*>(h);
     mavd_handle_s::HostSlot& S = H->slot[slot];
     const size_t npx = (size_t)h->cfg.width * h->cfg.height;
+    const size_t pb = (size_t)packed_mask_bytes((int64_t)npx);
     const int B = h->cfg.max_pairs;
     if (!S.d_frames) TRY(alloc_slot(H->arena, S, h->max_frames, B, npx));
     if (want_flow_out && !S.d_flow) TRY(H->arena.alloc(&S.d_flow, B * npx * 2));
     if (want_flow_in && !S.d_flow_in) TRY(H->arena.alloc(&S.d_flow_in, B * npx * 2));
+    if (want_bits_in && !S.d_bits_in) TRY(H->arena.alloc(&S.d_bits_in, 2 * B * pb));
+    if (want_bits_out && !S.d_bits_out) TRY(H->arena.alloc(&S.d_bits_out, B * pb));
+    if (want_gt && !S.d_gt_flow) TRY(H->arena.alloc(&S.d_gt_flow, B * npx * 2));
     if (!H->s_in) MAVD_CUDA(cudaStreamCreateWithFlags(&H->s_in, cudaStreamNonBlocking));
     if (!H->s_out) MAVD_CUDA(cudaStreamCreateWithFlags(&H->s_out, cudaStreamNonBlocking));
     H->bytes = H->arena.bytes;
     return MAVD_OK;
 }
 
-static int submit_host_impl(mavd_handle h, int32_t slot, const uint8_t* h_frames, int bgr, int32_t n_pairs,
-                            int32_t pair_stride, const mavd_imu* h_imu, const mavd_detect_params* prm,
-                            const int32_t* h_samples, const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg,
-                            int64_t seg_stride, float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records,
-                            void* stream) {
+// np.random.randint(0, H, 2000) rows then np.random.randint(0, W, 2000) columns per frame (focus_of_expansion.py:69-71)
+static int check_samples(const int32_t* h_samples, int n, int W, int Hh) {
+    for (int f = 0; f < n; ++f) {
+        const int32_t* sm = h_samples + (size_t)f * MAVD_SAMPLES_PER_FRAME;
+        unsigned bad = 0;
+        for (int i = 0; i < 2 * MAVD_N_SAMPLE_PAIRS; ++i) bad |= (unsigned)((unsigned)sm[i] >= (unsigned)Hh);
+        for (int i = 2 * MAVD_N_SAMPLE_PAIRS; i < 4 * MAVD_N_SAMPLE_PAIRS; ++i) bad |= (unsigned)((unsigned)sm[i] >= (unsigned)W);
+        MAVD_REQUIRE(!bad, MAVD_ERR_INVALID, "samples of frame %d out of range for a %dx%d frame (rows first, then columns)",
+                     f, W, Hh);
+    }
+    return MAVD_OK;
+}
+
+// copy the optional per-frame host inputs of a batch into the slot's device buffers on the copy-in stream
+static int stage_aux(mavd_handle h, mavd_handle_s::HostSlot& S, const mavd_aux_inputs& ha, int flags, int n,
+                     cudaStream_t s_in, mavd_aux_inputs* da) {
+    const size_t npx = (size_t)h->cfg.width * h->cfg.height;
+    const size_t pb = (size_t)packed_mask_bytes((int64_t)npx);
+    *da = kNoAux;
+    if (ha.sky) {
+        const int cnt = ha.sky_stride ? n : 1;
+        if (flags & MAVD_HOST_SKY_PACKED) {
+            uint8_t* bits = S.d_bits_in;
+            MAVD_CUDA(cudaMemcpyAsync(bits, ha.sky, pb * cnt, cudaMemcpyHostToDevice, s_in));
+            TRY(unpack_mask_run(bits, cnt, (int64_t)npx, 1, S.d_sky, s_in));
+        } else {
+            MAVD_CUDA(cudaMemcpyAsync(S.d_sky, ha.sky, npx * cnt, cudaMemcpyHostToDevice, s_in));
+        }
+        da->sky = S.d_sky;
+        da->sky_stride = ha.sky_stride ? (int64_t)npx : 0;
+    }
+    if (ha.seg) {
+        const int cnt = ha.seg_stride ? n : 1;
+        if (flags & MAVD_HOST_SEG_PACKED) {
+            uint8_t* bits = S.d_bits_in + (size_t)h->cfg.max_pairs * pb;
+            MAVD_CUDA(cudaMemcpyAsync(bits, ha.seg, pb * cnt, cudaMemcpyHostToDevice, s_in));
+            TRY(unpack_mask_run(bits, cnt, (int64_t)npx, 255, S.d_seg, s_in));
+        } else {
+            MAVD_CUDA(cudaMemcpyAsync(S.d_seg, ha.seg, npx * cnt, cudaMemcpyHostToDevice, s_in));
+        }
+        da->seg = S.d_seg;
+        da->seg_stride = ha.seg_stride ? (int64_t)npx : 0;
+    }
+    if (ha.gt_flow) {
+        MAVD_CUDA(cudaMemcpyAsync(S.d_gt_flow, ha.gt_flow, sizeof(float) * 2 * npx * n, cudaMemcpyHostToDevice, s_in));
+        da->gt_flow = S.d_gt_flow;
+    }
+    return MAVD_OK;
+}
+
+static int check_aux_strides(mavd_handle h, const mavd_aux_inputs& a, int flags) {
+    const int64_t npx = (int64_t)h->cfg.width * h->cfg.height, pb = packed_mask_bytes(npx);
+    const int64_t sky_full = (flags & MAVD_HOST_SKY_PACKED) ? pb : npx, seg_full = (flags & MAVD_HOST_SEG_PACKED) ? pb : npx;
+    MAVD_REQUIRE(a.sky_stride == 0 || a.sky_stride == sky_full, MAVD_ERR_INVALID, "sky_stride must be 0 or %lld",
+                 (long long)sky_full);
+    MAVD_REQUIRE(a.seg_stride == 0 || a.seg_stride == seg_full, MAVD_ERR_INVALID, "seg_stride must be 0 or %lld",
+                 (long long)seg_full);
+    return MAVD_OK;
+}
+
+int mavd_submit_host_ex(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32_t n_pairs, int32_t pair_stride,
+                        const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
+                        const mavd_aux_inputs* h_aux, int32_t flags, float* h_flow_out, uint8_t* h_fixed_out,
+                        mavd_frame_record* h_records, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n_pairs, "submit_host"));
     MAVD_REQUIRE(slot >= 0 && slot < MAVD_HOST_SLOTS, MAVD_ERR_INVALID, "slot %d out of range", slot);
     MAVD_REQUIRE(pair_stride == 1 || pair_stride == 2, MAVD_ERR_INVALID, "pair_stride must be 1 or 2");
     MAVD_REQUIRE(n_pairs >= 1, MAVD_ERR_INVALID, "submit_host: empty batch");
     MAVD_REQUIRE(h_frames && h_samples && h_records, MAVD_ERR_INVALID, "submit_host: NULL buffer");
+    const mavd_aux_inputs ha = h_aux ? *h_aux : kNoAux;
+    TRY(check_aux_strides(h, ha, flags));
+    TRY(check_samples(h_samples, n_pairs, h->cfg.width, h->cfg.height));
     const size_t npx = (size_t)h->cfg.width * h->cfg.height;
-    MAVD_REQUIRE(sky_stride == 0 || sky_stride == (int64_t)npx, MAVD_ERR_INVALID, "sky_stride must be 0 or H*W");
-    MAVD_REQUIRE(seg_stride == 0 || seg_stride == (int64_t)npx, MAVD_ERR_INVALID, "seg_stride must be 0 or H*W");
-    TRY(ensure_slot(h, slot, h_flow_out != nullptr, false));
+    const size_t pb = (size_t)packed_mask_bytes((int64_t)npx);
+    const bool bgr = (flags & MAVD_HOST_BGR) != 0, fixed_packed = (flags & MAVD_HOST_FIXED_PACKED) != 0;
+    TRY(ensure_slot(h, slot, h_flow_out != nullptr, false, (flags & (MAVD_HOST_SEG_PACKED | MAVD_HOST_SKY_PACKED)) != 0,
+                    fixed_packed && h_fixed_out, ha.gt_flow != nullptr));
     mavd_handle_s::HostSlot& S = h->slot[slot];
     MAVD_REQUIRE(!S.busy, MAVD_ERR_INVALID, "slot %d is still in flight: call mavd_wait_host first", slot);
-    cudaStream_t s = (cudaStream_t)stream;
     const int n_frames = pair_stride == 1 ? n_pairs + 1 : 2 * n_pairs;
     if (bgr && !S.d_bgr) {
         mavd_handle_full* H = static_cast<mavd_handle_full*>(h);
         TRY(H->arena.alloc(&S.d_bgr, (size_t)h->max_frames * npx * 3));
         H->bytes = H->arena.bytes;
     }
+    StreamScope ss(h, stream);
+    cudaStream_t s = ss.s;
     // copy-in stream (BGR frames are converted to gray there too, so the compute stream sees gray frames only)
     if (bgr) {
         MAVD_CUDA(cudaMemcpyAsync(S.d_bgr, h_frames, 3 * npx * n_frames, cudaMemcpyHostToDevice, h->s_in));
@@ -775,20 +1088,25 @@ static int submit_host_impl(mavd_handle h, int32_t slot, const uint8_t* h_frames
     }
     MAVD_CUDA(cudaMemcpyAsync(S.d_samples, h_samples, sizeof(int32_t) * MAVD_SAMPLES_PER_FRAME * n_pairs,
                               cudaMemcpyHostToDevice, h->s_in));
-    if (h_sky) MAVD_CUDA(cudaMemcpyAsync(S.d_sky, h_sky, sky_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, h->s_in));
-    if (h_seg) MAVD_CUDA(cudaMemcpyAsync(S.d_seg, h_seg, seg_stride ? npx * n_pairs : npx, cudaMemcpyHostToDevice, h->s_in));
+    mavd_aux_inputs da;
+    TRY(stage_aux(h, S, ha, flags, n_pairs, h->s_in, &da));
     MAVD_CUDA(cudaEventRecord(S.ev_in, h->s_in));
     // compute stream (the caller's).  (Running the detection stages of a batch on a second stream, concurrently with
     // the next batch's Farneback, was measured: no gain, the GPU is already full and the work is only re-ordered.)
     MAVD_CUDA(cudaStreamWaitEvent(s, S.ev_in, 0));
-    TRY(mavd_process(h, S.d_frames, n_pairs, pair_stride, h_imu, prm, S.d_samples, h_sky ? S.d_sky : nullptr, sky_stride,
-                     h_seg ? S.d_seg : nullptr, seg_stride, h_flow_out ? S.d_flow : nullptr, nullptr, S.d_fixed,
-                     S.d_records, s));
+    if (!(flags & MAVD_HOST_COPY_ONLY))
+        TRY(mavd_process_ex(h, S.d_frames, n_pairs, pair_stride, h_imu, prm, S.d_samples, &da,
+                            h_flow_out ? S.d_flow : nullptr, nullptr, S.d_fixed, S.d_records, s));
     MAVD_CUDA(cudaEventRecord(S.ev_done, s));
     // copy-out stream
     MAVD_CUDA(cudaStreamWaitEvent(h->s_out, S.ev_done, 0));
     MAVD_CUDA(cudaMemcpyAsync(h_records, S.d_records, sizeof(mavd_frame_record) * n_pairs, cudaMemcpyDeviceToHost, h->s_out));
-    if (h_fixed_out) MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, S.d_fixed, npx * n_pairs, cudaMemcpyDeviceToHost, h->s_out));
+    if (h_fixed_out && fixed_packed) {
+        TRY(pack_mask_run(S.d_fixed, n_pairs, (int64_t)npx, S.d_bits_out, h->s_out));
+        MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, S.d_bits_out, pb * n_pairs, cudaMemcpyDeviceToHost, h->s_out));
+    } else if (h_fixed_out) {
+        MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, S.d_fixed, npx * n_pairs, cudaMemcpyDeviceToHost, h->s_out));
+    }
     if (h_flow_out)
         MAVD_CUDA(cudaMemcpyAsync(h_flow_out, S.d_flow, sizeof(float) * 2 * npx * n_pairs, cudaMemcpyDeviceToHost, h->s_out));
     MAVD_CUDA(cudaEventRecord(S.ev_out, h->s_out));
@@ -801,16 +1119,18 @@ int mavd_submit_host(mavd_handle h, int32_t slot, const uint8_t* h_frames, int32
                      const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
                      const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
                      float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
-    return submit_host_impl(h, slot, h_frames, 0, n_pairs, pair_stride, h_imu, prm, h_samples, h_sky, sky_stride, h_seg,
-                            seg_stride, h_flow_out, h_fixed_out, h_records, stream);
+    const mavd_aux_inputs aux = {h_sky, sky_stride, h_seg, seg_stride, nullptr};
+    return mavd_submit_host_ex(h, slot, h_frames, n_pairs, pair_stride, h_imu, prm, h_samples, &aux, 0, h_flow_out,
+                               h_fixed_out, h_records, stream);
 }
 
 int mavd_submit_host_bgr(mavd_handle h, int32_t slot, const uint8_t* h_bgr_frames, int32_t n_pairs, int32_t pair_stride,
                          const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
                          const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
                          float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
-    return submit_host_impl(h, slot, h_bgr_frames, 1, n_pairs, pair_stride, h_imu, prm, h_samples, h_sky, sky_stride,
-                            h_seg, seg_stride, h_flow_out, h_fixed_out, h_records, stream);
+    const mavd_aux_inputs aux = {h_sky, sky_stride, h_seg, seg_stride, nullptr};
+    return mavd_submit_host_ex(h, slot, h_bgr_frames, n_pairs, pair_stride, h_imu, prm, h_samples, &aux, MAVD_HOST_BGR,
+                               h_flow_out, h_fixed_out, h_records, stream);
 }
 
 int mavd_wait_host(mavd_handle h, int32_t slot) {
@@ -818,7 +1138,7 @@ int mavd_wait_host(mavd_handle h, int32_t slot) {
     MAVD_REQUIRE(slot >= 0 && slot < MAVD_HOST_SLOTS, MAVD_ERR_INVALID, "slot %d out of range", slot);
     mavd_handle_s::HostSlot& S = h->slot[slot];
     if (!S.busy) return MAVD_OK;
-    MAVD_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     S.busy = false;
     MAVD_CUDA(cudaEventSynchronize(S.ev_out));
     return MAVD_OK;
@@ -828,6 +1148,7 @@ int mavd_process_host(mavd_handle h, const uint8_t* h_frames, int32_t n_pairs, i
                       const mavd_imu* h_imu, const mavd_detect_params* prm, const int32_t* h_samples,
                       const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg, int64_t seg_stride,
                       float* h_flow_out, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n_pairs, "process_host"));
     if (n_pairs == 0) return MAVD_OK;
     TRY(mavd_wait_host(h, 0));
@@ -836,29 +1157,69 @@ int mavd_process_host(mavd_handle h, const uint8_t* h_frames, int32_t n_pairs, i
     return mavd_wait_host(h, 0);
 }
 
-int mavd_detect_host(mavd_handle h, const float* h_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,
-                     const int32_t* h_samples, const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg,
-                     int64_t seg_stride, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+int mavd_detect_host_ex(mavd_handle h, const float* h_flow, int32_t n, const mavd_imu* h_imu,
+                        const mavd_detect_params* prm, const int32_t* h_samples, const mavd_aux_inputs* h_aux,
+                        int32_t flags, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+    DeviceGuard dg(h ? h->cfg.device : -1);
     TRY(check_batch(h, n, "detect_host"));
     if (n == 0) return MAVD_OK;
     MAVD_REQUIRE(h_flow && h_samples && h_records, MAVD_ERR_INVALID, "detect_host: NULL buffer");
+    MAVD_REQUIRE((flags & MAVD_HOST_BGR) == 0, MAVD_ERR_INVALID, "detect_host: MAVD_HOST_BGR has no meaning here");
+    const mavd_aux_inputs ha = h_aux ? *h_aux : kNoAux;
+    TRY(check_aux_strides(h, ha, flags));
+    TRY(check_samples(h_samples, n, h->cfg.width, h->cfg.height));
     const size_t npx = (size_t)h->cfg.width * h->cfg.height;
-    MAVD_REQUIRE(sky_stride == 0 || sky_stride == (int64_t)npx, MAVD_ERR_INVALID, "sky_stride must be 0 or H*W");
-    MAVD_REQUIRE(seg_stride == 0 || seg_stride == (int64_t)npx, MAVD_ERR_INVALID, "seg_stride must be 0 or H*W");
+    const size_t pb = (size_t)packed_mask_bytes((int64_t)npx);
+    const bool fixed_packed = (flags & MAVD_HOST_FIXED_PACKED) != 0;
     TRY(mavd_wait_host(h, 0));
-    TRY(ensure_slot(h, 0, false, true));
+    TRY(ensure_slot(h, 0, false, true, (flags & (MAVD_HOST_SEG_PACKED | MAVD_HOST_SKY_PACKED)) != 0,
+                    fixed_packed && h_fixed_out, ha.gt_flow != nullptr));
     mavd_handle_s::HostSlot& S = h->slot[0];
-    cudaStream_t s = (cudaStream_t)stream;
+    StreamScope ss(h, stream);
+    cudaStream_t s = ss.s;
     MAVD_CUDA(cudaMemcpyAsync(S.d_flow_in, h_flow, sizeof(float) * 2 * npx * n, cudaMemcpyHostToDevice, s));
     MAVD_CUDA(cudaMemcpyAsync(S.d_samples, h_samples, sizeof(int32_t) * MAVD_SAMPLES_PER_FRAME * n, cudaMemcpyHostToDevice, s));
-    if (h_sky) MAVD_CUDA(cudaMemcpyAsync(S.d_sky, h_sky, sky_stride ? npx * n : npx, cudaMemcpyHostToDevice, s));
-    if (h_seg) MAVD_CUDA(cudaMemcpyAsync(S.d_seg, h_seg, seg_stride ? npx * n : npx, cudaMemcpyHostToDevice, s));
-    TRY(mavd_detect(h, S.d_flow_in, n, h_imu, prm, S.d_samples, h_sky ? S.d_sky : nullptr, sky_stride,
-                    h_seg ? S.d_seg : nullptr, seg_stride, nullptr, S.d_fixed, S.d_records, s));
+    mavd_aux_inputs da;
+    TRY(stage_aux(h, S, ha, flags, n, s, &da));
+    if (!(flags & MAVD_HOST_COPY_ONLY))
+        TRY(mavd_detect_ex(h, S.d_flow_in, n, h_imu, prm, S.d_samples, &da, nullptr, S.d_fixed, S.d_records, s));
     MAVD_CUDA(cudaMemcpyAsync(h_records, S.d_records, sizeof(mavd_frame_record) * n, cudaMemcpyDeviceToHost, s));
-    if (h_fixed_out) MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, S.d_fixed, npx * n, cudaMemcpyDeviceToHost, s));
+    if (h_fixed_out && fixed_packed) {
+        TRY(pack_mask_run(S.d_fixed, n, (int64_t)npx, S.d_bits_out, s));
+        MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, S.d_bits_out, pb * n, cudaMemcpyDeviceToHost, s));
+    } else if (h_fixed_out) {
+        MAVD_CUDA(cudaMemcpyAsync(h_fixed_out, S.d_fixed, npx * n, cudaMemcpyDeviceToHost, s));
+    }
     MAVD_CUDA(cudaStreamSynchronize(s));
     return MAVD_OK;
+}
+
+int mavd_detect_host(mavd_handle h, const float* h_flow, int32_t n, const mavd_imu* h_imu, const mavd_detect_params* prm,
+                     const int32_t* h_samples, const uint8_t* h_sky, int64_t sky_stride, const uint8_t* h_seg,
+                     int64_t seg_stride, uint8_t* h_fixed_out, mavd_frame_record* h_records, void* stream) {
+    const mavd_aux_inputs aux = {h_sky, sky_stride, h_seg, seg_stride, nullptr};
+    return mavd_detect_host_ex(h, h_flow, n, h_imu, prm, h_samples, &aux, 0, h_fixed_out, h_records, stream);
+}
+
+int64_t mavd_packed_mask_bytes(int32_t width, int32_t height) {
+    if (width <= 0 || height <= 0) return 0;
+    return packed_mask_bytes((int64_t)width * height);
+}
+
+int mavd_pack_mask(const uint8_t* d_mask, int32_t n, int64_t n_pixels, uint8_t* d_bits, void* stream) {
+    MAVD_REQUIRE(n >= 0 && n <= 65535 && n_pixels >= 1 && (n == 0 || (d_mask && d_bits)), MAVD_ERR_INVALID,
+                 "pack_mask: bad arguments");
+    MAVD_REQUIRE((reinterpret_cast<uintptr_t>(d_bits) & 3) == 0, MAVD_ERR_INVALID, "pack_mask: d_bits must be 4-byte aligned");
+    if (n == 0) return MAVD_OK;
+    return pack_mask_run(d_mask, n, n_pixels, d_bits, (cudaStream_t)stream);
+}
+
+int mavd_unpack_mask(const uint8_t* d_bits, int32_t n, int64_t n_pixels, uint8_t value, uint8_t* d_mask, void* stream) {
+    MAVD_REQUIRE(n >= 0 && n <= 65535 && n_pixels >= 1 && (n == 0 || (d_mask && d_bits)), MAVD_ERR_INVALID,
+                 "unpack_mask: bad arguments");
+    MAVD_REQUIRE((reinterpret_cast<uintptr_t>(d_bits) & 3) == 0, MAVD_ERR_INVALID, "unpack_mask: d_bits must be 4-byte aligned");
+    if (n == 0) return MAVD_OK;
+    return unpack_mask_run(d_bits, n, n_pixels, value, d_mask, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -44,6 +44,37 @@ extern std::atomic<int64_t> g_launches;
         }                                                                                       \
     } while (0)
 
+// Switches to a handle's device for the lifetime of the guard and restores the caller's current device afterwards
+// (every handle-taking entry point of the C ABI holds one).
+struct DeviceGuard {
+    int prev = -1, cur = -1;
+    explicit DeviceGuard(int dev) {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        cur = dev;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != cur) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: opt in once per (kernel, device).
+template <auto Kernel>
+static inline cudaError_t ensure_dynamic_smem(size_t bytes) {
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = dev < 64 ? (1ull << dev) : 0ull;
+    if (bit && (done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+    e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && bit) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
@@ -152,6 +183,10 @@ struct mavd_handle_s {
         float* d_flow_in = nullptr;     // [max_pairs][H][W][2], mavd_detect_host only (allocated on first use)
         mavd_frame_record* d_records = nullptr;
         uint8_t* d_fixed = nullptr;     // [max_pairs][H][W] estimate_fixed masks of the batch
+        uint8_t* d_bits_in = nullptr;   // [2][max_pairs][packed bytes]: segmentation / sky as they cross the bus at
+                                        // 1 bit per pixel (allocated on first use)
+        uint8_t* d_bits_out = nullptr;  // [max_pairs][packed bytes]: estimate_fixed packed for the way back
+        float* d_gt_flow = nullptr;     // [max_pairs][H][W][2] ground-truth flow (allocated on first use)
         float* d_flow = nullptr;        // [max_pairs][H][W][2] flow of the batch (allocated on first request)
         cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
         bool busy = false;
@@ -159,9 +194,26 @@ struct mavd_handle_s {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaStream_t s_aux = nullptr;     // high-priority side stream for the coarse pyramid levels (farneback_run)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pyr = nullptr;
-    int overlap_mode = 2;             // MAVD_OVERLAP: 0 = every launch on the caller's stream, 1 = coarse levels on the
-                                      // side stream, 2 = pyramid + coarse levels on the side stream
+    mavd_tuning tune;                 // launch-shape choices (mavd_set_tuning); results never depend on them
     mavd::Profiler prof;
+    // imu staging: callers' imu arrays are copied into a ring of pinned slots before the asynchronous upload, so the
+    // call never retains the caller's pointer; an event per slot keeps a slot from being rewritten while its copy
+    // is still pending
+    static constexpr int kImuRing = 8;
+    mavd_imu* h_imu_ring = nullptr;   // pinned, [kImuRing][max_pairs]
+    cudaEvent_t imu_ev[kImuRing] = {};
+    int imu_next = 0;
+    // captured launch sequences (api.cu: run_graphed), least recently used entry replaced first
+    struct GraphEntry {
+        std::vector<uint64_t> key;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+        uint64_t last_use = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    uint64_t graph_clock = 0;
+    cudaStream_t s_main = nullptr;    // work submitted on the legacy default stream runs here between two events
+    cudaEvent_t ev_main_in = nullptr, ev_main_out = nullptr;
     bool force_generic_iter = false;  // tests: run the non-TMA iteration kernel
     // last call bookkeeping for taps
     int last_pairs = 0, last_stride = 1;
@@ -185,7 +237,11 @@ int gather_max_phi_run(const mavd_frame_stats* d_stats, int n, double* d_out, cu
 int residual_run(mavd_handle h, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu, const mavd_detect_params& prm,
                  const double* d_foe, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
                  int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
-                 size_t stats_stride_bytes, int run_f64, int run_f32, cudaStream_t s, bool list_fixed_units = false);
+                 size_t stats_stride_bytes, int run_f64, int run_f32, cudaStream_t s, bool list_fixed_units = false,
+                 const float* d_gt_flow = nullptr);
+int pack_mask_run(const uint8_t* d_mask, int n, int64_t npx, uint8_t* d_bits, cudaStream_t s);
+int unpack_mask_run(const uint8_t* d_bits, int n, int64_t npx, uint8_t value, uint8_t* d_mask, cudaStream_t s);
+static inline int64_t packed_mask_bytes(int64_t npx) { return ((npx + 7) / 8 + 3) / 4 * 4; }
 // The labelling passes walk a list of occupied 128-pixel units of the mask.  residual_run(list_fixed_units) appends the
 // units of the fixed mask while it writes it (after ccl_list_reset), so that ccl_run(list_ready) never streams the mask.
 int ccl_list_reset(mavd_handle h, int n, cudaStream_t s);

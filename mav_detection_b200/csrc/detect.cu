@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(1024) foe_kernel(const void* __restrict__ flow
     bool valid = false;
     double ex = 0.0, ey = 0.0;
     if (i < kNP) {
-        const int y1 = sm[i], y2 = sm[i + kNP], x1 = sm[2 * kNP + i], x2 = sm[3 * kNP + i];
+        // indices are the caller's np.random.randint draws; a stale or wrong-resolution table must not read out of bounds
+        const int y1 = min(max(sm[i], 0), h - 1), y2 = min(max(sm[i + kNP], 0), h - 1);
+        const int x1 = min(max(sm[2 * kNP + i], 0), w - 1), x2 = min(max(sm[3 * kNP + i], 0), w - 1);
         float2 a = make_float2(0.f, 0.f), b = a;
         double f1x, f1y, f2x, f2y;
         bool keep;
@@ -359,6 +361,7 @@ struct ResidualArgs {
     const uint8_t* sky; int64_t sky_stride;
     const uint8_t* seg; int64_t seg_stride;
     const int* seg_max;
+    const float2* gt_flow;   // nullable: ground-truth flow, summed (derotated) over segmentation > 127
     void* phi_out;
     uint8_t* total_out;
     uint8_t* fixed_out;
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
 
     int c_tot = 0, c_fix = 0, c_pos = 0, c_tpt = 0, c_fpt = 0, c_tpf = 0, c_fpf = 0, n_px = 0;
     int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;
-    double sfx = 0.0, sfy = 0.0, maxphi = 0.0;
+    double sfx = 0.0, sfy = 0.0, gfx = 0.0, gfy = 0.0, maxphi = 0.0;
 
 #pragma unroll 1
     for (int it = 0; it < RES_ITEMS; ++it) {
@@ -654,6 +657,19 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
                         if ((hi >> (8 * k)) & 0x80u) {
                             if (MODE == 1 || (FAST && MODE == 0 && !dr.on)) { sfx += (double)vfx[k]; sfy += (double)vfy[k]; }
                             else { sfx += vx[k]; sfy += vy[k]; }
+                            if (MODE != 2 && A.gt_flow) {
+                                // Detector.derotate on the ground-truth flow (processor.py:309-310), only where it is
+                                // summed (processor.py:344): a few hundred pixels per frame
+                                const float2 g = __ldg(A.gt_flow + fbase + i0 + k);
+                                double g0 = (double)g.x, g1 = (double)g.y;
+                                if (MODE == 0 && dr.on) {
+                                    double r0, r1;
+                                    derot_tab(dr, __ldg(A.xn + x0 + k), yn, r0, r1);
+                                    g0 = __dsub_rn(g0, r0);
+                                    g1 = __dsub_rn(g1, r1);
+                                }
+                                gfx += g0; gfy += g1;
+                            }
                         }
                 }
             }
@@ -671,10 +687,13 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
     // ---- block reduction: warp redux -> shared atomics -> one set of global atomics per block ----
     __shared__ int s_cnt[8];
     __shared__ int s_bb[4];
-    __shared__ double s_sum[2];
+    __shared__ double s_sum[4];
     __shared__ unsigned long long s_max;
     if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
-    if (threadIdx.x == 8) { s_bb[0] = s_bb[1] = 0x7fffffff; s_bb[2] = s_bb[3] = -1; s_sum[0] = s_sum[1] = 0.0; s_max = 0ull; }
+    if (threadIdx.x == 8) {
+        s_bb[0] = s_bb[1] = 0x7fffffff; s_bb[2] = s_bb[3] = -1;
+        s_sum[0] = s_sum[1] = s_sum[2] = s_sum[3] = 0.0; s_max = 0ull;
+    }
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -696,12 +715,14 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
         c_tpf = __reduce_add_sync(FULL, c_tpf); c_fpf = __reduce_add_sync(FULL, c_fpf);
         bx0 = __reduce_min_sync(FULL, bx0); by0 = __reduce_min_sync(FULL, by0);
         bx1 = __reduce_max_sync(FULL, bx1); by1 = __reduce_max_sync(FULL, by1);
-        const bool any_sum = __any_sync(FULL, sfx != 0.0 || sfy != 0.0);
+        const bool any_sum = __any_sync(FULL, sfx != 0.0 || sfy != 0.0 || gfx != 0.0 || gfy != 0.0);
         if (any_sum) {
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) {
                 sfx += __shfl_xor_sync(FULL, sfx, s);
                 sfy += __shfl_xor_sync(FULL, sfy, s);
+                gfx += __shfl_xor_sync(FULL, gfx, s);
+                gfy += __shfl_xor_sync(FULL, gfy, s);
             }
         }
         if (lane == 0) {
@@ -712,7 +733,11 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
             if (c_tpf) atomicAdd(&s_cnt[6], c_tpf);
             if (c_fpf) atomicAdd(&s_cnt[7], c_fpf);
             if (bx1 >= 0) { atomicMin(&s_bb[0], bx0); atomicMin(&s_bb[1], by0); atomicMax(&s_bb[2], bx1); atomicMax(&s_bb[3], by1); }
-            if (any_sum) { atomicAdd(&s_sum[0], sfx); atomicAdd(&s_sum[1], sfy); }
+            if (any_sum) {
+                atomicAdd(&s_sum[0], sfx); atomicAdd(&s_sum[1], sfy);
+                if (gfx != 0.0) atomicAdd(&s_sum[2], gfx);
+                if (gfy != 0.0) atomicAdd(&s_sum[3], gfy);
+            }
         }
     }
     __syncthreads();
@@ -736,6 +761,8 @@ __global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, 
             }
             if (s_sum[0] != 0.0) atomicAdd(&st->seg_flow_sum[0], s_sum[0]);
             if (s_sum[1] != 0.0) atomicAdd(&st->seg_flow_sum[1], s_sum[1]);
+            if (s_sum[2] != 0.0) atomicAdd(&st->gt_flow_sum[0], s_sum[2]);
+            if (s_sum[3] != 0.0) atomicAdd(&st->gt_flow_sum[1], s_sum[3]);
         }
     }
 }
@@ -781,7 +808,7 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
                  const mavd_detect_params& p, const double* d_foe, const uint8_t* d_sky, int64_t sky_stride,
                  const uint8_t* d_seg, int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed,
                  mavd_frame_stats* d_stats, size_t stats_stride, int run_f64, int run_f32, cudaStream_t s,
-                 bool list_fixed_units) {
+                 bool list_fixed_units, const float* d_gt_flow) {
     ProfScope ps(&H->prof, MAVD_PROF_RESIDUAL, s);
     const int w = H->cfg.width, h = H->cfg.height;
     const int64_t npx = (int64_t)w * h;
@@ -804,6 +831,7 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
     A.flow = d_flow; A.imu = flow_kind == 0 ? d_imu : nullptr; A.foe = d_foe; A.xn = H->d_xn; A.yn = H->d_yn; A.w = w; A.h = h;
     A.prm = ResidualPrm{p.dyn_offset, p.dyn_base, p.dyn_gain, p.dyn_min_mag, p.fixed_min_mag, p.fixed_angle};
     A.sky = d_sky; A.sky_stride = sky_stride; A.seg = d_seg; A.seg_stride = seg_stride; A.seg_max = seg_max;
+    A.gt_flow = (d_seg && d_stats) ? reinterpret_cast<const float2*>(d_gt_flow) : nullptr;
     A.phi_out = d_phi; A.total_out = d_total; A.fixed_out = d_fixed;
     A.stats_base = (char*)d_stats; A.stats_stride = stats_stride;
     // i / w by multiplication: M = floor(2^32 / w) + 1 is exact for i * (M * w - 2^32) < 2^32
@@ -929,6 +957,73 @@ __global__ void __launch_bounds__(256) tpr_fpr_kernel(const uint8_t* __restrict_
 int tpr_fpr_run(const uint8_t* d_gt, const int64_t* d_img, int64_t n, int64_t* d_counts4, cudaStream_t s) {
     MAVD_CUDA(cudaMemsetAsync(d_counts4, 0, 4 * sizeof(int64_t), s));
     tpr_fpr_kernel<<<148 * 4, 256, 0, s>>>(d_gt, d_img, n, reinterpret_cast<unsigned long long*>(d_counts4));
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1-bit-per-pixel masks for the host<->device wire (include/mavd.h: mavd_pack_mask / mavd_unpack_mask).  The ground-truth
+// segmentation going in and estimate_fixed coming out carry one bit of information per pixel; as byte masks they were
+// two thirds of the bytes a batch moves over PCIe.  Thread = one 32-bit word = 32 pixels of the flattened frame, bit b
+// of word j is pixel 32 j + b (numpy.packbits(..., bitorder='little')).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_mask_kernel(const uint8_t* __restrict__ mask, int64_t npx, int64_t words,
+                                                       uint32_t* __restrict__ bits) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= words) return;
+    const uint8_t* m = mask + (size_t)blockIdx.y * npx + 32 * j;
+    uint32_t out = 0;
+    if (32 * j + 32 <= npx && (reinterpret_cast<uintptr_t>(m) & 15) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(m)), b = __ldg(reinterpret_cast<const uint4*>(m) + 1);
+        const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            // one bit per non-zero byte, gathered into a nibble: the 0x01010101-masked word times 0x01020408 lands byte
+            // k's bit at position 24 + k (no two partial products share a bit, so nothing carries)
+            const uint32_t nz = __vcmpne4(wv[q], 0u) & 0x01010101u;
+            out |= (((nz * 0x01020408u) >> 24) & 15u) << (4 * q);
+        }
+    } else {
+        for (int b = 0; b < 32; ++b)
+            if (32 * j + b < npx && m[b]) out |= 1u << b;
+    }
+    bits[(size_t)blockIdx.y * words + j] = out;
+}
+
+__global__ void __launch_bounds__(256) unpack_mask_kernel(const uint32_t* __restrict__ bits, int64_t npx, int64_t words,
+                                                         uint32_t value, uint8_t* __restrict__ mask) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= words) return;
+    const uint32_t v = __ldg(bits + (size_t)blockIdx.y * words + j);
+    uint8_t* m = mask + (size_t)blockIdx.y * npx + 32 * j;
+    if (32 * j + 32 <= npx && (reinterpret_cast<uintptr_t>(m) & 15) == 0) {
+        uint32_t wv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t nib = (v >> (4 * q)) & 15u;
+            // spread the nibble's bits into the low bit of four bytes, then scale to `value`
+            const uint32_t sp = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+            wv[q] = sp * value;
+        }
+        reinterpret_cast<uint4*>(m)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        reinterpret_cast<uint4*>(m)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+    } else {
+        for (int b = 0; b < 32; ++b)
+            if (32 * j + b < npx) m[b] = (v >> b) & 1u ? (uint8_t)value : (uint8_t)0;
+    }
+}
+
+int pack_mask_run(const uint8_t* d_mask, int n, int64_t npx, uint8_t* d_bits, cudaStream_t s) {
+    const int64_t words = packed_mask_bytes(npx) / 4;
+    pack_mask_kernel<<<dim3((unsigned)((words + 255) / 256), n), 256, 0, s>>>(d_mask, npx, words, (uint32_t*)d_bits);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+int unpack_mask_run(const uint8_t* d_bits, int n, int64_t npx, uint8_t value, uint8_t* d_mask, cudaStream_t s) {
+    const int64_t words = packed_mask_bytes(npx) / 4;
+    unpack_mask_kernel<<<dim3((unsigned)((words + 255) / 256), n), 256, 0, s>>>((const uint32_t*)d_bits, npx, words, value,
+                                                                               d_mask);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }

@@ -1259,12 +1259,7 @@ __global__ void tap_flow_kernel(const float2* __restrict__ src, int w, int h, in
 // ------------------------------------------------------------------------------------------------
 template <bool GAUSS, bool LAST>
 static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        MAVD_CUDA(cudaFuncSetAttribute(iter_kernel<GAUSS, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024));
-        configured = true;
-    }
+    MAVD_CUDA((ensure_dynamic_smem<iter_kernel<GAUSS, LAST>>(200 * 1024)));
     iter_kernel<GAUSS, LAST><<<grid, 256, smem, s>>>(a);
     MAVD_LAUNCHED();
     return MAVD_OK;
@@ -1274,25 +1269,20 @@ template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0>
 static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const CUtensorMap& mapRbox, const IterArgs& a,
                            dim3 grid, cudaStream_t s) {
     constexpr size_t smem = sizeof(float) * 5 * (IT_TY + 2 * M_) * (IT_TX + 16);
-    static bool configured = false;
-    if (!configured) {
-        MAVD_CUDA(cudaFuncSetAttribute(iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    MAVD_CUDA((ensure_dynamic_smem<iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE>>(smem)));
     iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE><<<grid, NT, smem, s>>>(map, mapR, mapRbox, a);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
 
 template <bool LAST>
-static int launch_iter_tma_m(int m, const CUtensorMap& map, const CUtensorMap& mapR, const CUtensorMap& mapRbox,
-                             const IterArgs& a, dim3 grid, cudaStream_t s) {
-    // R1 staged in shared memory by a second TMA load: 4.36 vs 4.56 ms per 64-pair step (MAVD_R1S=0 switches it off)
-    static const bool r1s = !(getenv("MAVD_R1S") && getenv("MAVD_R1S")[0] == '0');
+static int launch_iter_tma_m(int m, const mavd_tuning& tune, const CUtensorMap& map, const CUtensorMap& mapR,
+                             const CUtensorMap& mapRbox, const IterArgs& a, dim3 grid, cudaStream_t s) {
+    // R1 staged in shared memory by a second TMA load: 4.36 vs 4.56 ms per 64-pair step (tuning.r1_staged)
+    const bool r1s = tune.r1_staged != 0;
     // horizontal sums + solve in registers for the not-last iterations too, flow vectors handed to the update phase
-    // through shared memory: iter_full 4.27 vs 4.39 ms per 64-pair step (MAVD_ITER_FUSE=0 switches it off)
-    static const int fuse = getenv("MAVD_ITER_FUSE") ? atoi(getenv("MAVD_ITER_FUSE")) : 1;
+    // through shared memory: iter_full 4.27 vs 4.39 ms per 64-pair step (tuning.iter_fuse)
+    const int fuse = tune.iter_fuse;
     if (r1s && !LAST && fuse == 2 && m >= 6) {      // experimental: hand-over through the dead box rows
         switch (m) {
             case 6: return launch_iter_tma<6, false, 256, true, 2>(map, mapR, mapRbox, a, grid, s);
@@ -1342,7 +1332,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         const int Wp = round_up(W, 4);
         PyrDesc d;
         d.n = hi - lo + 1;
-        static const bool pyr_staged_env = !(getenv("MAVD_PYR_STAGED") && getenv("MAVD_PYR_STAGED")[0] == '0');
+        const bool pyr_staged_env = H->tune.pyr_staged != 0;
         int rows = 0, hx_max = 1;
         for (int li = lo; li <= hi; ++li) {
             const Level& L = H->lv[li];
@@ -1377,8 +1367,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
     // consecutive pairs share an R plane (R1 of pair p is R0 of pair p+1): interleaving the pairs of a tile in
     // groups of 4 in the CTA order lets the second reader hit L2 (4502 vs 4441 pairs/s ungrouped, 4338 with the
     // whole 64-pair batch interleaved: too many concurrent HBM regions)
-    static const int group_env = getenv("MAVD_PAIR_GROUP") ? atoi(getenv("MAVD_PAIR_GROUP")) : 4;
-    const int pair_group = max(1, min(group_env, n_pairs));
+    const int pair_group = max(1, min(H->tune.pair_group, n_pairs));
 
     // polynomial expansion of one level for all frames (level 0 reads the u8 frames and blurs on the fly)
     auto expand_level = [&](int li, cudaStream_t st) -> int {
@@ -1411,14 +1400,12 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             dim3 g(ceil_div(L.w, 64), ceil_div(L.h, 4), n_pairs);
             const bool top = (li == H->n_levels - 1);
             const Level* C = top ? nullptr : &H->lv[li + 1];
-            static const bool tables = getenv("MAVD_MAT_TABLES") && getenv("MAVD_MAT_TABLES")[0] == '1';
-            static const bool no_pow2 = getenv("MAVD_MAT_POW2") && getenv("MAVD_MAT_POW2")[0] == '0';
+            const bool tables = H->tune.mat_coord == 1, no_pow2 = H->tune.mat_coord == 2;
             const double xscale = top ? 1.0 : 1.0 / ((double)L.w / C->w), yscale = top ? 1.0 : 1.0 / ((double)L.h / C->h);
             auto is_pow2 = [](double v) { int e; return v > 0.0 && frexp(v, &e) == 0.5 && e > -20 && e <= 1; };
             const int coord = tables ? MI_COORD_TABLES
                                      : (!no_pow2 && is_pow2(xscale) && is_pow2(yscale)) ? MI_COORD_POW2 : MI_COORD_F64;
-            static const int r0_first = getenv("MAVD_MAT_R0FIRST") ? atoi(getenv("MAVD_MAT_R0FIRST")) : 1;
-            static const int txlog = getenv("MAVD_MAT_TXLOG") ? atoi(getenv("MAVD_MAT_TXLOG")) : 6;
+            const int r0_first = H->tune.mat_r0_first, txlog = H->tune.mat_txlog;
             const dim3 g3(g.z, ceil_div(L.w, 1 << txlog), ceil_div(L.h, 256 >> txlog));       // pair index fastest
 #define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, (size_t)pair_stride * 5 * L.plane,                                     \
                 top ? nullptr : (const float2*)C->flow, top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch,             \
@@ -1454,16 +1441,15 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             a.n_pairs = n_pairs;
             a.tiles_x = g.x;
             a.group = pair_group;
-            static const bool last_fused_env = !(getenv("MAVD_LAST_FUSED") && getenv("MAVD_LAST_FUSED")[0] == '0');
-            a.last_fused = (last && last_fused_env) ? 1 : 0;
+            a.last_fused = (last && H->tune.last_fused != 0) ? 1 : 0;
             const dim3 g1(g.x * g.y * g.z);
             const int RW = IT_TX + 2 * hx, RH = IT_TY + 2 * m;
             const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
             ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), st);
             int rc;
             if (!gauss && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter)
-                rc = last ? launch_iter_tma_m<true>(m, L.tmapM[cur], L.tmapR, L.tmapRbox, a, g1, st)
-                          : launch_iter_tma_m<false>(m, L.tmapM[cur], L.tmapR, L.tmapRbox, a, g1, st);
+                rc = last ? launch_iter_tma_m<true>(m, H->tune, L.tmapM[cur], L.tmapR, L.tmapRbox, a, g1, st)
+                          : launch_iter_tma_m<false>(m, H->tune, L.tmapM[cur], L.tmapR, L.tmapRbox, a, g1, st);
             else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, st) : launch_iter<true, false>(a, g, smem, st);
             else       rc = last ? launch_iter<false, true>(a, g, smem, st) : launch_iter<false, false>(a, g, smem, st);
             if (rc != MAVD_OK) return rc;
@@ -1477,9 +1463,9 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
     // expansions of levels 1 and 0 are large and depend only on the frames / pyramid.  Run the coarse chain on a
     // high-priority side stream while the caller's stream does the two big expansions, and join before level 1's
     // matrices need the level-2 flow.  Stream order as seen by the caller is unchanged.
-    const bool fork = H->n_levels >= 3 && H->s_aux != nullptr && H->overlap_mode != 0;
+    const bool fork = H->n_levels >= 3 && H->s_aux != nullptr && H->tune.overlap != 0;
     const int top_level = H->n_levels - 1;
-    if (fork && H->overlap_mode == 2) {
+    if (fork && H->tune.overlap == 2) {
         // the pyramid too goes to the side stream: level 0's expansion reads only the u8 frames
         MAVD_CUDA(cudaEventRecord(H->ev_fork, s));
         MAVD_CUDA(cudaStreamWaitEvent(H->s_aux, H->ev_fork, 0));

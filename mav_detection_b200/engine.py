@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import Config, DetectParams, FarnebackParams, FrameRecord, FrameStats, Imu, check
+from ._lib import AuxInputs, Config, DetectParams, FarnebackParams, FrameRecord, FrameStats, Imu, Tuning, check
 
 # cv2.calcOpticalFlowFarneback arguments used by the reference (src/farneback.py:78-80)
 REFERENCE_PARAMS = dict(pyr_scale=0.4, levels=1, winsize=12, iterations=10, poly_n=8, poly_sigma=1.2, flags=0)
@@ -31,6 +31,18 @@ def make_imu(n: int, ang: Optional[np.ndarray] = None, dt=None, derotate=None) -
         d = True if derotate is None else (derotate if isinstance(derotate, (bool, int)) else derotate[i])
         arr[i].derotate = 1 if d else 0
     return arr
+
+
+def parse_tuning(text: str) -> Dict[str, int]:
+    """'pair_group=8,use_graph=0' -> {'pair_group': 8, 'use_graph': 0} (bench.py --tune, tools/gpu_ab.sh)."""
+    out: Dict[str, int] = {}
+    names = {f[0] for f in Tuning._fields_} - {'reserved'}
+    for item in filter(None, (t.strip() for t in text.split(','))):
+        k, _, v = item.partition('=')
+        if k not in names:
+            raise ValueError('unknown tuning field %r (known: %s)' % (k, ', '.join(sorted(names))))
+        out[k] = int(v)
+    return out
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -94,6 +106,108 @@ class Engine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    # -- launch-shape tuning (never changes results) --------------------------------------------
+    def get_tuning(self) -> Dict[str, int]:
+        t = Tuning()
+        check(self.lib.mavd_get_tuning(self._h, C.byref(t)))
+        return {f[0]: int(getattr(t, f[0])) for f in Tuning._fields_ if f[0] != 'reserved'}
+
+    def set_tuning(self, **fields: int) -> None:
+        """Set mavd_tuning fields by name; the handle must be idle (the call synchronises the device)."""
+        t = Tuning()
+        check(self.lib.mavd_get_tuning(self._h, C.byref(t)))
+        for k, v in fields.items():
+            if k == 'reserved' or not hasattr(t, k):
+                raise ValueError('unknown tuning field %r' % k)
+            setattr(t, k, int(v))
+        check(self.lib.mavd_set_tuning(self._h, C.byref(t)))
+
+    def _check_samples(self, samples: torch.Tensor, n: int) -> None:
+        if not isinstance(samples, torch.Tensor) or samples.dtype != torch.int32 or not samples.is_cuda or \
+                samples.device != self.device or not samples.is_contiguous() or \
+                tuple(samples.shape) != (n, _lib.SAMPLES_PER_FRAME):
+            raise ValueError('samples must be a contiguous int32 tensor (%d, %d) on %s: [ry(2000) | rx(2000)] per frame'
+                             % (n, _lib.SAMPLES_PER_FRAME, self.device))
+
+    def _aux(self, sky, seg, gt_flow, n: int, host: bool = False, sky_packed: bool = False,
+             seg_packed: bool = False) -> AuxInputs:
+        """mavd_aux_inputs from optional sky / seg masks ((H, W) shared or (n, H, W) per frame; packed: (bytes,) or
+        (n, bytes)) and an optional (n, H, W, 2) float32 ground-truth flow; device tensors or host arrays."""
+        npx = self.width * self.height
+        pb = self.packed_mask_bytes
+
+        def one(t, packed, name):
+            if t is None:
+                return None, 0
+            if host:
+                if t.dtype not in (np.uint8, np.bool_) or not t.flags['C_CONTIGUOUS']:
+                    raise ValueError('%s must be a C-contiguous uint8/bool array' % name)
+                dim, size, ptr = t.ndim, t.size, t.ctypes.data
+            else:
+                if t.dtype not in (torch.uint8, torch.bool) or not t.is_cuda or not t.is_contiguous():
+                    raise ValueError('%s must be a contiguous CUDA uint8/bool tensor' % name)
+                dim, size, ptr = t.dim(), t.numel(), t.data_ptr()
+            per, shared_dim = (pb, 1) if packed else (npx, 2)
+            if dim == shared_dim and size == per:
+                return ptr, 0
+            if dim == shared_dim + 1 and size == per * n:
+                return ptr, per
+            raise ValueError('%s has %d elements: expected %d (shared) or %d x %d (per frame)' % (name, size, per, n, per))
+        a = AuxInputs()
+        a.sky, a.sky_stride = one(sky, sky_packed, 'sky')
+        a.seg, a.seg_stride = one(seg, seg_packed, 'seg')
+        if gt_flow is not None:
+            if host:
+                ok = gt_flow.dtype == np.float32 and gt_flow.flags['C_CONTIGUOUS'] and \
+                    tuple(gt_flow.shape) == (n, self.height, self.width, 2)
+                a.gt_flow = gt_flow.ctypes.data if ok else None
+            else:
+                ok = gt_flow.dtype == torch.float32 and gt_flow.is_cuda and gt_flow.is_contiguous() and \
+                    tuple(gt_flow.shape) == (n, self.height, self.width, 2)
+                a.gt_flow = gt_flow.data_ptr() if ok else None
+            if not ok:
+                raise ValueError('gt_flow must be contiguous float32 (%d, %d, %d, 2)' % (n, self.height, self.width))
+        return a
+
+    @property
+    def packed_mask_bytes(self) -> int:
+        """Bytes one (H, W) mask occupies at 1 bit per pixel on the host<->device wire."""
+        return int(self.lib.mavd_packed_mask_bytes(self.width, self.height))
+
+    def pack_mask_host(self, mask: np.ndarray) -> np.ndarray:
+        """(..., H, W) uint8/bool host mask -> (..., packed_mask_bytes) uint8, the layout MAVD_HOST_*_PACKED expects
+        (numpy.packbits(bitorder='little') of the flattened frame, zero padded)."""
+        lead = mask.shape[:-2]
+        bits = np.packbits(np.ascontiguousarray(mask).reshape(lead + (-1,)) != 0, axis=-1, bitorder='little')
+        out = np.zeros(lead + (self.packed_mask_bytes,), np.uint8)
+        out[..., :bits.shape[-1]] = bits
+        return out
+
+    def unpack_mask_host(self, bits: np.ndarray) -> np.ndarray:
+        """The inverse: (..., packed_mask_bytes) uint8 -> (..., H, W) uint8 0/1."""
+        lead = bits.shape[:-1]
+        flat = np.unpackbits(bits, axis=-1, bitorder='little')[..., :self.width * self.height]
+        return flat.reshape(lead + (self.height, self.width))
+
+    def pack_mask(self, mask: torch.Tensor) -> torch.Tensor:
+        """(n, H, W) CUDA uint8 mask -> (n, packed_mask_bytes) uint8 (mavd_pack_mask)."""
+        mask = mask.contiguous()
+        n = mask.shape[0]
+        out = torch.empty((n, self.packed_mask_bytes), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.mavd_pack_mask(mask.data_ptr(), n, self.width * self.height, out.data_ptr(), self._stream()))
+        return out
+
+    def unpack_mask(self, bits: torch.Tensor, value: int = 1) -> torch.Tensor:
+        """(n, packed_mask_bytes) CUDA uint8 -> (n, H, W) uint8 with set bits = value (mavd_unpack_mask)."""
+        bits = bits.contiguous()
+        n = bits.shape[0]
+        out = torch.empty((n, self.height, self.width), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.mavd_unpack_mask(bits.data_ptr(), n, self.width * self.height, int(value), out.data_ptr(),
+                                            self._stream()))
+        return out
+
     def _check_frames(self, frames: torch.Tensor, n_pairs: int, pair_stride: int) -> None:
         need = n_pairs + 1 if pair_stride == 1 else 2 * n_pairs
         if frames.dtype != torch.uint8 or not frames.is_cuda or not frames.is_contiguous():
@@ -111,8 +225,11 @@ class Engine:
         if bgr.dtype != torch.uint8 or not bgr.is_cuda or bgr.shape[-1] != 3:
             raise ValueError('bgr must be a CUDA uint8 tensor (..., 3)')
         bgr = bgr.contiguous()
+        if bgr.device != self.device:
+            raise ValueError('bgr lives on %s, the engine on %s' % (bgr.device, self.device))
         out = torch.empty(bgr.shape[:-1], dtype=torch.uint8, device=bgr.device)
-        check(self.lib.mavd_bgr2gray(bgr.data_ptr(), out.data_ptr(), out.numel(), self._stream()))
+        with torch.cuda.device(self.device):        # handle-less entry point: runs on the current device
+            check(self.lib.mavd_bgr2gray(bgr.data_ptr(), out.data_ptr(), out.numel(), self._stream()))
         return out
 
     # -- stage 1 -----------------------------------------------------------------------------
@@ -244,100 +361,96 @@ class Engine:
     def process(self, frames: torch.Tensor, imu, samples: torch.Tensor, n_pairs: Optional[int] = None,
                 pair_stride: int = 1, sky: Optional[torch.Tensor] = None, seg: Optional[torch.Tensor] = None,
                 flow_out: Optional[torch.Tensor] = None, total_out: Optional[torch.Tensor] = None,
-                fixed_out: Optional[torch.Tensor] = None, records: Optional[torch.Tensor] = None) -> torch.Tensor:
+                fixed_out: Optional[torch.Tensor] = None, records: Optional[torch.Tensor] = None,
+                gt_flow: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Farneback -> derotate -> FoE -> phi/masks -> components, device buffers in and out.
         Returns the (n_pairs, sizeof(mavd_frame_record)) uint8 CUDA tensor of records."""
         if n_pairs is None:
             n_pairs = frames.shape[0] - 1 if pair_stride == 1 else frames.shape[0] // 2
         self._check_frames(frames, n_pairs, pair_stride)
-        npx = self.width * self.height
+        self._check_samples(samples, n_pairs)
         if records is None:
             records = torch.empty((n_pairs, RECORD_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
-        sky_stride = 0 if (sky is None or sky.dim() == 2) else npx
-        seg_stride = 0 if (seg is None or seg.dim() == 2) else npx
-        check(self.lib.mavd_process(self._h, frames.data_ptr(), n_pairs, pair_stride, imu,
-                                    C.byref(self.detect_params), samples.data_ptr(), _ptr(sky), sky_stride,
-                                    _ptr(seg), seg_stride, _ptr(flow_out), _ptr(total_out), _ptr(fixed_out),
-                                    records.data_ptr(), self._stream()))
+        aux = self._aux(sky, seg, gt_flow, n_pairs)
+        check(self.lib.mavd_process_ex(self._h, frames.data_ptr(), n_pairs, pair_stride, imu,
+                                       C.byref(self.detect_params), samples.data_ptr(), C.byref(aux),
+                                       _ptr(flow_out), _ptr(total_out), _ptr(fixed_out), records.data_ptr(),
+                                       self._stream()))
         return records
 
     def detect(self, flow: torch.Tensor, imu, samples: torch.Tensor, sky: Optional[torch.Tensor] = None,
                seg: Optional[torch.Tensor] = None, total_out: Optional[torch.Tensor] = None,
-               fixed_out: Optional[torch.Tensor] = None, records: Optional[torch.Tensor] = None) -> torch.Tensor:
+               fixed_out: Optional[torch.Tensor] = None, records: Optional[torch.Tensor] = None,
+               gt_flow: Optional[torch.Tensor] = None) -> torch.Tensor:
         """derotate -> FoE -> phi/masks -> components from a given float32 flow (the Dataset.get_flow_uv seam)."""
         n = flow.shape[0]
         if flow.dtype != torch.float32 or not flow.is_cuda or not flow.is_contiguous() or \
                 tuple(flow.shape[1:]) != (self.height, self.width, 2):
             raise ValueError('flow must be a contiguous CUDA float32 tensor (n, %d, %d, 2)' % (self.height, self.width))
-        npx = self.width * self.height
+        self._check_samples(samples, n)
         if records is None:
             records = torch.empty((n, RECORD_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
-        sky_stride = 0 if (sky is None or sky.dim() == 2) else npx
-        seg_stride = 0 if (seg is None or seg.dim() == 2) else npx
-        check(self.lib.mavd_detect(self._h, flow.data_ptr(), n, imu, C.byref(self.detect_params), samples.data_ptr(),
-                                   _ptr(sky), sky_stride, _ptr(seg), seg_stride, _ptr(total_out), _ptr(fixed_out),
-                                   records.data_ptr(), self._stream()))
+        aux = self._aux(sky, seg, gt_flow, n)
+        check(self.lib.mavd_detect_ex(self._h, flow.data_ptr(), n, imu, C.byref(self.detect_params), samples.data_ptr(),
+                                      C.byref(aux), _ptr(total_out), _ptr(fixed_out), records.data_ptr(),
+                                      self._stream()))
         return records
 
-    def _host_args(self, frames, samples, n_pairs, pair_stride, sky, seg, flow_out, fixed_out, records):
+    def _host_args(self, frames, samples, n_pairs, pair_stride, flow_out, fixed_out, records, fixed_packed=False):
         if n_pairs is None:
             n_pairs = frames.shape[0] - 1 if pair_stride == 1 else frames.shape[0] // 2
-        npx = self.width * self.height
         if records is None:
             records = np.empty((n_pairs,), dtype=RECORD_DTYPE)
-        for name, a in (('frames', frames), ('samples', samples), ('sky', sky), ('seg', seg),
-                        ('flow_out', flow_out), ('fixed_out', fixed_out)):
+        for name, a in (('frames', frames), ('samples', samples), ('flow_out', flow_out), ('fixed_out', fixed_out)):
             if a is not None and not a.flags['C_CONTIGUOUS']:
                 raise ValueError('%s must be C-contiguous' % name)
-        if samples.dtype != np.int32:
-            raise ValueError('samples must be int32')
+        if samples.dtype != np.int32 or samples.size < n_pairs * _lib.SAMPLES_PER_FRAME:
+            raise ValueError('samples must be int32 (n, %d)' % _lib.SAMPLES_PER_FRAME)
         need = n_pairs + 1 if pair_stride == 1 else 2 * n_pairs
         if frames is not None and (frames.dtype != np.uint8 or frames.shape[0] < need or
                                    tuple(frames.shape[1:]) not in ((self.height, self.width),
                                                                    (self.height, self.width, 3))):
             raise ValueError('frames must be uint8 (>=%d, %d, %d) gray or (>=%d, %d, %d, 3) BGR'
                              % (need, self.height, self.width, need, self.height, self.width))
-        sky_stride = 0 if (sky is None or sky.ndim == 2) else npx
-        seg_stride = 0 if (seg is None or seg.ndim == 2) else npx
-        return n_pairs, records, sky_stride, seg_stride
+        if fixed_out is not None:
+            want = n_pairs * (self.packed_mask_bytes if fixed_packed else self.width * self.height)
+            if fixed_out.dtype != np.uint8 or fixed_out.size < want:
+                raise ValueError('fixed_out must be uint8 with at least %d elements' % want)
+        return n_pairs, records
 
     def process_host(self, frames: np.ndarray, imu, samples: np.ndarray, n_pairs: Optional[int] = None,
                      pair_stride: int = 1, sky: Optional[np.ndarray] = None, seg: Optional[np.ndarray] = None,
                      flow_out: Optional[np.ndarray] = None, fixed_out: Optional[np.ndarray] = None,
-                     records: Optional[np.ndarray] = None) -> np.ndarray:
+                     records: Optional[np.ndarray] = None, **kw) -> np.ndarray:
         """The end-to-end call: HOST buffers in, HOST records (and optional masks / flow) out.  Frames may be gray
-        (F, H, W) or BGR (F, H, W, 3)."""
-        if frames.ndim == 4:
-            self.wait_host(0)
-            records = self.submit_host(0, frames, imu, samples, n_pairs, pair_stride, sky, seg, flow_out, fixed_out,
-                                       records)
-            self.wait_host(0)
-            return records
-        n_pairs, records, sky_stride, seg_stride = self._host_args(frames, samples, n_pairs, pair_stride, sky, seg,
-                                                                   flow_out, fixed_out, records)
-        with torch.cuda.device(self.device):
-            check(self.lib.mavd_process_host(self._h, _hp(frames), n_pairs, pair_stride, imu,
-                                             C.byref(self.detect_params), _hp(samples), _hp(sky), sky_stride,
-                                             _hp(seg), seg_stride, _hp(flow_out), _hp(fixed_out),
-                                             records.ctypes.data, self._stream()))
+        (F, H, W) or BGR (F, H, W, 3).  Keyword options as in submit_host."""
+        self.wait_host(0)
+        records = self.submit_host(0, frames, imu, samples, n_pairs, pair_stride, sky, seg, flow_out, fixed_out,
+                                   records, **kw)
+        self.wait_host(0)
         return records
 
     def submit_host(self, slot: int, frames: np.ndarray, imu, samples: np.ndarray, n_pairs: Optional[int] = None,
                     pair_stride: int = 1, sky: Optional[np.ndarray] = None, seg: Optional[np.ndarray] = None,
                     flow_out: Optional[np.ndarray] = None, fixed_out: Optional[np.ndarray] = None,
-                    records: Optional[np.ndarray] = None) -> np.ndarray:
+                    records: Optional[np.ndarray] = None, gt_flow: Optional[np.ndarray] = None,
+                    seg_packed: bool = False, sky_packed: bool = False, fixed_packed: bool = False,
+                    copy_only: bool = False) -> np.ndarray:
         """Asynchronous process_host: returns at once; the outputs are valid after wait_host(slot).  Keeping
-        up to _lib.HOST_SLOTS batches in flight overlaps the host<->device copies with the compute."""
-        n_pairs, records, sky_stride, seg_stride = self._host_args(frames, samples, n_pairs, pair_stride, sky, seg,
-                                                                   flow_out, fixed_out, records)
-        submit = self.lib.mavd_submit_host_bgr if frames.ndim == 4 else self.lib.mavd_submit_host
-        with torch.cuda.device(self.device):
-            check(submit(self._h, slot, _hp(frames), n_pairs, pair_stride, imu,
-                         C.byref(self.detect_params), _hp(samples), _hp(sky), sky_stride,
-                         _hp(seg), seg_stride, _hp(flow_out), _hp(fixed_out),
-                         records.ctypes.data, self._stream()))
+        up to _lib.HOST_SLOTS batches in flight overlaps the host<->device copies with the compute.
+        seg_packed / sky_packed: the masks are given at 1 bit per pixel (pack_mask_host); fixed_packed: fixed_out
+        receives (n, packed_mask_bytes) bits; copy_only: move the bytes but skip the compute (host-feed ceiling)."""
+        n_pairs, records = self._host_args(frames, samples, n_pairs, pair_stride, flow_out, fixed_out, records,
+                                           fixed_packed)
+        aux = self._aux(sky, seg, gt_flow, n_pairs, host=True, sky_packed=sky_packed, seg_packed=seg_packed)
+        flags = (_lib.HOST_BGR if frames.ndim == 4 else 0) | (_lib.HOST_SEG_PACKED if seg_packed else 0) | \
+            (_lib.HOST_SKY_PACKED if sky_packed else 0) | (_lib.HOST_FIXED_PACKED if fixed_packed else 0) | \
+            (_lib.HOST_COPY_ONLY if copy_only else 0)
+        check(self.lib.mavd_submit_host_ex(self._h, slot, _hp(frames), n_pairs, pair_stride, imu,
+                                           C.byref(self.detect_params), _hp(samples), C.byref(aux), flags,
+                                           _hp(flow_out), _hp(fixed_out), records.ctypes.data, self._stream()))
         # keep the host buffers alive until the wait
-        self._inflight[slot] = (frames, imu, samples, sky, seg, flow_out, fixed_out, records)
+        self._inflight[slot] = (frames, imu, samples, sky, seg, gt_flow, flow_out, fixed_out, records)
         return records
 
     def wait_host(self, slot: int) -> None:
@@ -346,18 +459,20 @@ class Engine:
 
     def detect_host(self, flow: np.ndarray, imu, samples: np.ndarray, sky: Optional[np.ndarray] = None,
                     seg: Optional[np.ndarray] = None, fixed_out: Optional[np.ndarray] = None,
-                    records: Optional[np.ndarray] = None) -> np.ndarray:
+                    records: Optional[np.ndarray] = None, gt_flow: Optional[np.ndarray] = None,
+                    seg_packed: bool = False, sky_packed: bool = False, fixed_packed: bool = False) -> np.ndarray:
         """Detection from a HOST float32 flow (n, H, W, 2): what Processor.run_detection does with
         Dataset.get_flow_uv (processor.py:305-362)."""
         if flow.dtype != np.float32 or tuple(flow.shape[1:]) != (self.height, self.width, 2) or \
                 not flow.flags['C_CONTIGUOUS']:
             raise ValueError('flow must be C-contiguous float32 (n, %d, %d, 2)' % (self.height, self.width))
-        n, records, sky_stride, seg_stride = self._host_args(None, samples, flow.shape[0], 1, sky, seg, None, fixed_out,
-                                                             records)
-        with torch.cuda.device(self.device):
-            check(self.lib.mavd_detect_host(self._h, flow.ctypes.data, n, imu, C.byref(self.detect_params),
-                                            _hp(samples), _hp(sky), sky_stride, _hp(seg), seg_stride, _hp(fixed_out),
-                                            records.ctypes.data, self._stream()))
+        n, records = self._host_args(None, samples, flow.shape[0], 1, None, fixed_out, records, fixed_packed)
+        aux = self._aux(sky, seg, gt_flow, n, host=True, sky_packed=sky_packed, seg_packed=seg_packed)
+        flags = (_lib.HOST_SEG_PACKED if seg_packed else 0) | (_lib.HOST_SKY_PACKED if sky_packed else 0) | \
+            (_lib.HOST_FIXED_PACKED if fixed_packed else 0)
+        check(self.lib.mavd_detect_host_ex(self._h, flow.ctypes.data, n, imu, C.byref(self.detect_params),
+                                           _hp(samples), C.byref(aux), flags, _hp(fixed_out), records.ctypes.data,
+                                           self._stream()))
         return records
 
     @staticmethod

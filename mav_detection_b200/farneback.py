@@ -62,8 +62,9 @@ class Farneback:
         self._prevgray_d = gray
         h, w = gray.shape
         bgr = torch.empty((h, w, 3), dtype=torch.uint8, device=eng.device)
-        check(eng.lib.mavd_flow_vis(self.flow.data_ptr(), h * w, bgr.data_ptr(), self._scratch.data_ptr(),
-                                    torch.cuda.current_stream(eng.device).cuda_stream))
+        with torch.cuda.device(eng.device):      # handle-less entry point: runs on the current device
+            check(eng.lib.mavd_flow_vis(self.flow.data_ptr(), h * w, bgr.data_ptr(), self._scratch.data_ptr(),
+                                        torch.cuda.current_stream(eng.device).cuda_stream))
         nonzero_values = int(self._scratch[2].item()) & 0xffffffff
         invalid_frame = nonzero_values < 1
         result = bgr.cpu().numpy()

@@ -33,6 +33,11 @@ def _ratio(a: int, b: int) -> float:
         return float(np.float64(a) / np.float64(b))
 
 
+def eng_records_dtype() -> np.dtype:
+    from .engine import RECORD_DTYPE
+    return RECORD_DTYPE
+
+
 def to_gray(frame: np.ndarray) -> np.ndarray:
     """Validates a frame: (H, W) gray or (H, W, 3) BGR uint8.  No conversion happens on the host: BGR frames are
     converted on the device (mavd_bgr2gray)."""
@@ -70,6 +75,7 @@ class Processor:
         self.is_exiting = False
         self.focus_of_expansion = FocusOfExpansion(self.detector.lucas_kanade, engine=engine)
         self._pending_frame: Optional[np.ndarray] = None
+        self._staging: Dict[Any, Any] = {}
 
     # ------------------------------------------------------------------------------------------------
     def is_active(self) -> bool:
@@ -94,15 +100,30 @@ class Processor:
             raise ValueError('Could not load frame.')
         return to_gray(np.ascontiguousarray(frame))
 
-    def _host_inputs(self, indices: List[int]):
-        """Per-frame host inputs in frame order: IMU, FoE sample indices, sky and segmentation masks."""
+    def _pinned(self, slot: int, name: str, shape, dtype) -> np.ndarray:
+        """A pinned host array owned by staging slot `slot`, reused from batch to batch: asynchronous copies from / to
+        pageable memory are staged synchronously by the driver, which would serialise the three-stage pipeline."""
+        import torch
+        key = (slot, name)
+        dtype = np.dtype(dtype)
+        need = int(np.prod(shape)) * dtype.itemsize
+        buf = self._staging.get(key)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty((max(need, 1),), dtype=torch.uint8, pin_memory=True)
+            self._staging[key] = buf
+        return buf.numpy()[:need].view(dtype).reshape(shape)
+
+    def _host_inputs(self, indices: List[int], slot: int):
+        """Per-frame host inputs in frame order, in the slot's pinned staging: IMU, FoE sample indices, sky and
+        segmentation masks and, when the dataset has one, the ground-truth flow (processor.py:309)."""
         from . import engine as engine_mod
         width, height = self.dataset.capture_size
         n = len(indices)
         ang, dt, rot = np.zeros((n, 3)), np.ones(n), []
-        samples = np.empty((n, 4 * 1000), np.int32)
-        sky = np.zeros((n, height, width), np.uint8)
-        seg = np.zeros((n, height, width), np.uint8)
+        samples = self._pinned(slot, 'samples', (n, 4 * 1000), np.int32)
+        sky = self._pinned(slot, 'sky', (n, height, width), np.uint8)
+        seg = self._pinned(slot, 'seg', (n, height, width), np.uint8)
+        gt = None
         for k, i in enumerate(indices):
             a, d, on = self.detector.imu_for(i - self.frame_step_size, i)
             ang[k], dt[k] = a, d
@@ -111,9 +132,17 @@ class Processor:
             sky[k] = np.asarray(self.dataset.get_sky_segmentation(i)).astype(np.uint8)
             s = np.asarray(self.dataset.get_segmentation(i))
             seg[k] = s[..., 0] if s.ndim == 3 else s
-        return engine_mod.make_imu(n, ang, dt, derotate=rot), samples, sky, seg
+            g = self.dataset.get_gt_of(i) if hasattr(self.dataset, 'get_gt_of') else None
+            if g is not None:
+                if gt is None:
+                    gt = self._pinned(slot, 'gt_flow', (n, height, width, 2), np.float32)
+                    gt[:k] = 0.0
+                gt[k] = g
+            elif gt is not None:
+                gt[k] = 0.0
+        return engine_mod.make_imu(n, ang, dt, derotate=rot), samples, sky, seg, gt
 
-    def _frame_result(self, i: int, rec: np.void, sky_k: np.ndarray) -> FrameResult:
+    def _frame_result(self, i: int, rec: np.void, sky_k: np.ndarray, has_gt: bool = False) -> FrameResult:
         """processor.py:327-329,343-362 from the device record of frame i."""
         st = rec['stats']
         fr = FrameResult()
@@ -134,30 +163,16 @@ class Processor:
             fr.sky_tpr, fr.sky_fpr = self.dataset.validate_sky_segment(sky_k.astype(bool), depth)
         fr.drone_size_pixels = int(st['positives'])
         fr.time = self.dataset.get_time(i)
-        fr.drone_flow_pixels = self._drone_flow_gt(i, rec)
+        fr.drone_flow_pixels = self._drone_flow_gt(i, rec, has_gt)
         return fr
 
-    def _drone_flow_gt(self, i: int, rec: np.void) -> Tuple[float, float]:
-        """np.average(gt_flow_uv_derotated[segmentation > 127]) (processor.py:344,359).  The ground-truth
-        flow goes through the same device reduction as the estimated flow; without a ground-truth flow the
-        estimated flow's average over the segmentation is reported."""
+    def _drone_flow_gt(self, i: int, rec: np.void, has_gt: bool) -> Tuple[float, float]:
+        """np.average(gt_flow_uv_derotated[segmentation > 127]) (processor.py:344,359).  The ground-truth flow of the
+        whole batch went to the device with the batch (mavd_aux_inputs.gt_flow) and was derotated and summed there;
+        without a ground-truth flow the estimated flow's average over the segmentation is reported."""
         st = rec['stats']
         pos = int(st['positives'])
-        gt = self.dataset.get_gt_of(i) if hasattr(self.dataset, 'get_gt_of') else None
-        if gt is None:
-            s = st['seg_flow_sum']
-        else:
-            import torch
-            from . import engine as engine_mod
-            eng = self.engine
-            a, d, on = self.detector.imu_for(i - self.frame_step_size, i)
-            imu = engine_mod.make_imu(1, a[None], d, derotate=on)
-            seg = np.asarray(self.dataset.get_segmentation(i))
-            seg = np.ascontiguousarray(seg[..., 0] if seg.ndim == 3 else seg)
-            foe = torch.zeros((1, 2), dtype=torch.float64, device=eng.device)
-            flow = torch.from_numpy(np.ascontiguousarray(gt, dtype=np.float32)[None]).to(eng.device)
-            _, _, _, stats = eng.residual_masks(flow, imu, foe, seg=torch.from_numpy(seg).to(eng.device), want_phi=False)
-            s = eng.stats_to_numpy(stats)[0]['seg_flow_sum']
+        s = st['gt_flow_sum'] if has_gt else st['seg_flow_sum']
         return (_ratio(s[0], pos), _ratio(s[1], pos)) if pos else (float('nan'), float('nan'))
 
     # ------------------------------------------------------------------------------------------------
@@ -168,15 +183,15 @@ class Processor:
         eng = self.engine
         width, height = self.dataset.capture_size
         B = self.batch_frames
-        inflight: List[Tuple[int, List[int], np.ndarray, np.ndarray]] = []   # (slot, indices, records, sky)
+        inflight: List[Tuple[int, List[int], np.ndarray, np.ndarray, bool]] = []   # (slot, indices, records, sky, gt?)
         slot = 0
 
         def finish(entry) -> None:
-            s, indices, records, sky = entry
+            s, indices, records, sky, has_gt = entry
             if s >= 0:
                 eng.wait_host(s)
             for k, i in enumerate(indices):
-                fr = self._frame_result(i, records[k], sky[k])
+                fr = self._frame_result(i, records[k], sky[k], has_gt)
                 self.detection_results[i] = fr
                 self.config.results[i] = fr
                 self.write(i)
@@ -184,31 +199,34 @@ class Processor:
         while self.is_active():
             first = self.frame_index
             indices = list(range(first, min(first + B * self.frame_step_size, self.dataset.N - 1), self.frame_step_size))
+            n = len(indices)
             if self.flow_source == 'dataset':
                 for _ in indices:
                     self.dataset.get_frame()                      # keeps the capture in step (processor.py:284)
-                flows = []
-                for i in indices:
+                flows = self._pinned(0, 'flow', (n, height, width, 2), np.float32)
+                for k, i in enumerate(indices):
                     f = self.dataset.get_flow_uv(i)
                     if f is None:
                         raise ValueError('Could not load flow field.')
-                    flows.append(np.asarray(f, np.float32))
-                imu, samples, sky, seg = self._host_inputs(indices)
-                records = eng.detect_host(np.ascontiguousarray(np.stack(flows)), imu, samples, sky=sky, seg=seg)
-                finish((-1, indices, records, sky))
+                    flows[k] = f
+                imu, samples, sky, seg, gt = self._host_inputs(indices, 0)
+                records = self._pinned(0, 'records', (n,), eng_records_dtype())
+                eng.detect_host(flows, imu, samples, sky=sky, seg=seg, gt_flow=gt, records=records)
+                finish((-1, indices, records, sky, gt is not None))
             else:
                 # flow(i) = Farneback(frame i, frame i+1); consecutive batches share one frame
+                if len(inflight) == HOST_SLOTS - 1:
+                    finish(inflight.pop(0))                      # frees the staging of the slot used next
                 first_frame = self._pending_frame if self._pending_frame is not None else self._next_frame()
-                frames = np.empty((len(indices) + 1,) + first_frame.shape, np.uint8)     # gray or BGR, as delivered
+                frames = self._pinned(slot, 'frames', (n + 1,) + first_frame.shape, np.uint8)     # gray or BGR, as delivered
                 frames[0] = first_frame
-                for k in range(len(indices)):
+                for k in range(n):
                     frames[k + 1] = self._next_frame()
                 self._pending_frame = frames[-1].copy()
-                imu, samples, sky, seg = self._host_inputs(indices)
-                if len(inflight) == HOST_SLOTS - 1:
-                    finish(inflight.pop(0))
-                records = eng.submit_host(slot, frames, imu, samples, n_pairs=len(indices), sky=sky, seg=seg)
-                inflight.append((slot, indices, records, sky))
+                imu, samples, sky, seg, gt = self._host_inputs(indices, slot)
+                records = self._pinned(slot, 'records', (n,), eng_records_dtype())
+                eng.submit_host(slot, frames, imu, samples, n_pairs=n, sky=sky, seg=seg, gt_flow=gt, records=records)
+                inflight.append((slot, indices, records, sky, gt is not None))
                 slot = (slot + 1) % HOST_SLOTS
             self.frame_index = indices[-1] + self.frame_step_size
             n10 = int(self.dataset.N / 10)

@@ -83,3 +83,61 @@ def run_sharded(frames: np.ndarray, process_batch: Callable[[np.ndarray, int, np
         return local
     counts = [shard_range(n_pairs, world, r)[1] - shard_range(n_pairs, world, r)[0] for r in range(world)]
     return gather_records(local, counts, group)
+
+
+def compare_records(got: np.ndarray, ref: np.ndarray) -> List[str]:
+    """Names of the record fields that differ.  Every field must be bit-equal except the float64 flow sums, which
+    are accumulated with atomics (summation order varies from run to run): those to 1e-12 relative."""
+    if got.shape != ref.shape:
+        return ['shape %s != %s' % (got.shape, ref.shape)]
+    bad = []
+    for name in ('foe', 'n_intersections', 'n_labels', 'boxes'):
+        if not np.array_equal(got[name], ref[name]):
+            bad.append(name)
+    for name in ref['stats'].dtype.names:
+        a, b = got['stats'][name], ref['stats'][name]
+        same = np.allclose(a, b, rtol=1e-12, atol=1e-9) if name in ('seg_flow_sum', 'gt_flow_sum') else np.array_equal(a, b)
+        if not same:
+            bad.append('stats.' + name)
+    return bad
+
+
+def parity_check(device: int, width: int = 640, height: int = 480, n_frames: int = 33, batch_pairs: int = 8,
+                 seed: int = 77, group=None) -> Tuple[bool, str]:
+    """Multi-GPU parity, run by every rank of an initialised process group: a synthetic sequence's pairs are sharded
+    over the ranks (run_sharded), the records gathered, and rank 0 compares them field by field with its own
+    single-GPU run of the whole sequence.  Returns (ok, message) on every rank (the verdict is broadcast)."""
+    import torch
+    import torch.distributed as dist
+    from . import engine, synth
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    params = dict(engine.SAMPLE_PARAMS)
+    seq = synth.make_sequence(width, height, n_frames, seq=3, with_rotation=True)
+    eng = engine.Engine(width, height, params, max_pairs=batch_pairs, device=device)
+
+    def batch(frames, first_pair, samples):
+        n = frames.shape[0] - 1
+        imu = engine.make_imu(n, seq.omega[first_pair + 1:first_pair + 1 + n], seq.dt,
+                              derotate=[(first_pair + i) >= 1 for i in range(n)])
+        seg = np.ascontiguousarray(seq.segmentation[first_pair + 1:first_pair + 1 + n])
+        return eng.process_host(np.ascontiguousarray(frames), imu, np.ascontiguousarray(samples), seg=seg).copy()
+
+    got = run_sharded(seq.frames, batch, seed=seed, batch_pairs=batch_pairs, group=group)
+    ok, msg = True, ''
+    if rank == 0:
+        n_pairs = n_frames - 1
+        samples = draw_all_samples(n_pairs, height, width, seed=seed)
+        ref = np.concatenate([batch(seq.frames[b:min(b + batch_pairs, n_pairs) + 1], b,
+                                    samples[b:min(b + batch_pairs, n_pairs)]) for b in range(0, n_pairs, batch_pairs)])
+        bad = compare_records(got, ref)
+        ok = not bad
+        msg = ('%d pairs of %dx%d sharded over %d ranks == single-GPU run, field by field' % (n_pairs, width, height, world)
+               if ok else 'sharded records differ from the single-GPU run in: ' + ', '.join(bad))
+    eng.close()
+    if world > 1:
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32,
+                            device=torch.device('cuda', device) if dist.get_backend(group) == 'nccl' else 'cpu')
+        dist.broadcast(flag, src=0, group=group)
+        ok = bool(flag.item())
+    return ok, msg

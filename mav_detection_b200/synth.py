@@ -28,7 +28,10 @@ def _bicubic_upsample8(lo: np.ndarray) -> np.ndarray:
 
 
 def make_sequence(width: int, height: int, n_frames: int, seq: int = 0,
-                  expansion: float = 0.01, with_rotation: bool = False) -> SyntheticSequence:
+                  expansion: float = 0.01, with_rotation: bool = False, motion: str = 'zoom') -> SyntheticSequence:
+    """motion 'zoom': expansion about the FoE (radial flow, sparse detection masks).  motion 'translate': the camera
+    slides sideways (6 px per frame, uniform flow): the flow lines are parallel, the FoE estimate finds no consensus
+    (or a far-away one) and most pixels end up above the angle thresholds — the dense-mask stress case."""
     import cv2
     seed = 1000 + seq
     rng = np.random.default_rng(seed)
@@ -42,9 +45,15 @@ def make_sequence(width: int, height: int, n_frames: int, seq: int = 0,
     seg = np.zeros((n_frames, height, width), np.uint8)
     bx0, by0 = 0.6 * width, 0.55 * height
     for t in range(n_frames):
-        z = (1.0 + expansion) ** t
-        mx = (foe[0] + (xs - foe[0]) / z + 16).astype(np.float32)
-        my = (foe[1] + (ys - foe[1]) / z + 16).astype(np.float32)
+        if motion == 'translate':
+            ph = t % 8
+            sh = 6.0 * (ph if ph <= 4 else 8 - ph)       # triangle wave 0..24 px: stays inside the canvas margin
+            mx = (xs + 4.0 + sh).astype(np.float32)
+            my = (ys + 16.0).astype(np.float32)
+        else:
+            z = (1.0 + expansion) ** t
+            mx = (foe[0] + (xs - foe[0]) / z + 16).astype(np.float32)
+            my = (foe[1] + (ys - foe[1]) / z + 16).astype(np.float32)
         img = cv2.remap(canvas, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
         bx = int(round(bx0 + 3 * t)) % max(width - 40, 1)
         by = int(round(by0 - 2 * t)) % max(height - 24, 1)
@@ -68,7 +77,7 @@ class SyntheticDataset:
     SyntheticSequence held in memory.  Stands in for SimData in tests, the bench and the examples."""
 
     def __init__(self, seq: SyntheticSequence, sequence: str = 'synthetic', flows: np.ndarray = None,
-                 results_path: str = None, bgr: bool = False) -> None:
+                 results_path: str = None, bgr: bool = False, gt_flows: np.ndarray = None) -> None:
         self.seq = seq
         self.sequence = sequence
         self.N = int(seq.frames.shape[0])
@@ -76,6 +85,7 @@ class SyntheticDataset:
         self.resolution = np.array(self.capture_size)
         self.results_path = results_path
         self.flows = flows            # optional precomputed (N-1, H, W, 2) float32: the get_flow_uv seam
+        self.gt_flows = gt_flows      # optional (N-1, H, W, 2) float32 ground-truth flow: the get_gt_of seam
         self.bgr = bgr
         self._next = 0
 
@@ -90,7 +100,7 @@ class SyntheticDataset:
         return self.flows[i]
 
     def get_gt_of(self, i: int):
-        return None
+        return None if self.gt_flows is None else self.gt_flows[i]
 
     def get_sky_segmentation(self, i: int) -> np.ndarray:
         return self.seq.sky_mask

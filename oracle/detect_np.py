@@ -93,8 +93,14 @@ def foe_dense(flow: np.ndarray, ry: np.ndarray, rx: np.ndarray) -> Tuple[float, 
     return ransac(intersections(flow, ry, rx))
 
 
-def get_phi(flow: np.ndarray, foe: Tuple[float, float]) -> np.ndarray:
-    """focus_of_expansion.py:150-184: angle [deg] between flow and the ray from the FoE, flow's dtype."""
+def get_phi(flow: np.ndarray, foe: Tuple[float, float], cr_arccos_f32: bool = False) -> np.ndarray:
+    """focus_of_expansion.py:150-184: angle [deg] between flow and the ray from the FoE, flow's dtype.
+
+    cr_arccos_f32 (float32 flows only, i.e. frame 0): evaluate arccos correctly rounded (through float64) instead
+    of with NumPy's float32 loop.  Every other float32 operation of this function is a single IEEE operation and
+    therefore reproducible; NumPy's float32 arccos is NOT correctly rounded and depends on the CPU dispatch
+    (AVX-512 SVML here: 35 % of the arguments 1 ulp off, 0.05 % 2 ulp off, measured on 2e7 values), so the reference
+    itself is only defined up to those ulps on the float32 frame.  The CUDA path computes the correctly rounded value."""
     h, w = flow.shape[:2]
     d2 = np.zeros_like(flow)
     d2[..., 0] = np.arange(w)[None, :] - foe[0]
@@ -104,7 +110,11 @@ def get_phi(flow: np.ndarray, foe: Tuple[float, float]) -> np.ndarray:
     norm = np.maximum(np.ones_like(a) * 1e-6, a * b)
     c = (flow[..., 0] * d2[..., 0] + flow[..., 1] * d2[..., 1]) / norm
     c = np.clip(c, -1, 1)
-    ang = np.arccos(c)
+    if cr_arccos_f32 and c.dtype == np.float32:
+        with np.errstate(invalid='ignore'):
+            ang = np.arccos(c.astype(np.float64)).astype(np.float32)
+    else:
+        ang = np.arccos(c)
     ang[np.isnan(ang)] = 0
     return np.rad2deg(ang)
 
@@ -145,10 +155,10 @@ def tpr_fpr(gt: np.ndarray, mask: np.ndarray) -> Tuple[float, float]:
 
 
 def frame_pipeline(frame_index: int, flow_uv: np.ndarray, ang_diff, dt: float, sky: np.ndarray,
-                   ry: np.ndarray, rx: np.ndarray):
+                   ry: np.ndarray, rx: np.ndarray, cr_arccos_f32: bool = False):
     """processor.py:305-341 for one frame given pre-drawn sample indices."""
     fd = derotate(frame_index, flow_uv, ang_diff, dt)
     foe = foe_dense(fd, ry, rx)
-    phi = get_phi(fd, foe)
+    phi = get_phi(fd, foe, cr_arccos_f32)
     total, fixed = masks(fd, phi, sky)
     return fd, foe, phi, total, fixed

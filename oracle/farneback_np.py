@@ -339,7 +339,7 @@ def calc_optical_flow_farneback(prev: np.ndarray, nxt: np.ndarray, flow: Optiona
     """Same signature as cv2.calcOpticalFlowFarneback (/root/reference/src/farneback.py:76-80).
 
     ``tap(name, level, array)`` (optional) receives every intermediate:
-    'img0','img1','R0','R1','M0' and 'flow<i>' per iteration.
+    'img0','img1','R0','R1','M0' (level entry), and per iteration 'flow<i>' and 'M<i+1>' (the matrices rebuilt from it).
     """
     assert prev.shape == nxt.shape and prev.ndim == 2
     assert pyr_scale < 1
@@ -371,5 +371,7 @@ def calc_optical_flow_farneback(prev: np.ndarray, nxt: np.ndarray, flow: Optiona
                 tap('flow%d' % i, k, cur)
             if i < iterations - 1:
                 M = update_matrices(R[0], R[1], cur)
+                if tap:
+                    tap('M%d' % (i + 1), k, M)
         prev_flow = cur
     return prev_flow

@@ -52,7 +52,7 @@ def test_ctypes_signatures_have_the_header_arity_and_return_types():
 
 def test_abi_version_and_defaults(lib):
     from mav_detection_b200 import _lib
-    assert lib.mavd_abi_version() == 1
+    assert lib.mavd_abi_version() == _lib.ABI_VERSION == 2
     p = _lib.DetectParams()
     lib.mavd_default_detect_params(C.byref(p))
     # focus_of_expansion.py:22-23, processor.py:333-341
@@ -65,7 +65,8 @@ def test_struct_layouts():
     from mav_detection_b200 import _lib
     assert C.sizeof(_lib.Imu) == 40
     assert C.sizeof(_lib.FarnebackParams) == 40
-    assert C.sizeof(_lib.FrameStats) == 8 * 9 + 16 + 16
+    assert C.sizeof(_lib.FrameStats) == 8 * 9 + 16 + 16 + 16
+    assert C.sizeof(_lib.Tuning) == 16 * 4 and C.sizeof(_lib.AuxInputs) == 40
     assert C.sizeof(_lib.FrameRecord) == 16 + 8 + C.sizeof(_lib.FrameStats) + 32 * 5 * 4
     assert np.dtype(_lib.FrameRecord).itemsize == C.sizeof(_lib.FrameRecord)
 

@@ -47,9 +47,23 @@ def test_golden_frame(golden_dir, ci):
         assert np.abs(p - g['phi']).max() < 1e-9            # acos within a few ulp of glibc
         assert np.array_equal(total, g['total_mask']) and np.array_equal(fixed, g['estimate_fixed'])
     else:
+        # float32 frame (frame_index < 1).  Every operation of the reference is a single IEEE float32 operation except
+        # np.arccos, whose float32 loop is not correctly rounded (CPU-dispatch dependent, up to 2 ulp off).  So:
+        # (1) against the oracle with a correctly rounded arccos, phi and both masks are BIT-EXACT;
         p = phi.view(torch.float32)[0].reshape(-1)[:h * w].reshape(h, w).cpu().numpy()
-        assert np.abs(p - g['phi']).max() < 1e-4            # float32 path: NumPy's own f32 arccos
-        assert (total != g['total_mask']).sum() <= 2 and (fixed != g['estimate_fixed']).sum() <= 2
+        from oracle import detect_np as dn
+        phi_cr = dn.get_phi(g['flow'], (g['foe'][0], g['foe'][1]), cr_arccos_f32=True)
+        total_cr, fixed_cr = dn.masks(g['flow'], phi_cr, g['sky'].astype(bool))
+        assert phi_cr.dtype == np.float32 and np.array_equal(p, phi_cr)
+        assert np.array_equal(total, total_cr) and np.array_equal(fixed, fixed_cr)
+        # (2) against the golden vector (NumPy's own arccos on the CPU that made it), phi differs by at most 2 ulp
+        # and a mask pixel can flip only where NumPy's arccos is off AND phi sits within those ulps of a threshold
+        ulp = np.abs(p.view(np.int32).astype(np.int64) - g['phi'].view(np.int32).astype(np.int64))
+        flips = (total != g['total_mask']) | (fixed != g['estimate_fixed'])
+        print('float32 frame: %d of %d phi values differ from NumPy\'s arccos (max %d ulp), %d mask pixels flip'
+              % ((ulp > 0).sum(), ulp.size, ulp.max(), flips.sum()))
+        assert ulp.max() <= 2
+        assert (ulp[flips] >= 1).all() and flips.sum() <= 8
     st = eng.stats_to_numpy(stats)[0]
     assert st['n_total'] == total.sum() and st['n_fixed'] == fixed.sum()
     assert abs(st['max_phi'] - g['phi'].max()) < 1e-4
@@ -254,9 +268,17 @@ def test_fast_residual_ragged_width_and_batch():
         tr, fr = dn.masks(fd, phi, sky)
         t, f = tot[i].cpu().numpy().astype(bool), fix[i].cpu().numpy().astype(bool)
         if i == 0:
-            # float32 frame: NumPy's float32 arccos vs ours may differ in the last ulp on a handful of pixels
-            assert (t != tr).sum() <= 4 and (f != fr).sum() <= 4
-            assert abs(st[i]['max_phi'] - phi.max()) < 1e-3
+            # float32 frame: bit-exact against the oracle with a correctly rounded float32 arccos (see
+            # test_golden_frame); NumPy's own float32 arccos is up to 2 ulp off, which can flip a pixel whose phi
+            # sits within those ulps of a threshold
+            phi_cr = dn.get_phi(fd, tuple(foe[i]), cr_arccos_f32=True)
+            tc, fc = dn.masks(fd, phi_cr, sky)
+            assert np.array_equal(t, tc) and np.array_equal(f, fc)
+            assert st[i]['max_phi'] == float(phi_cr.max())
+            ulp = np.abs(phi_cr.view(np.int32).astype(np.int64) - phi.view(np.int32).astype(np.int64))
+            flips = (t != tr) | (f != fr)
+            print('float32 frame: %d mask pixels flip against NumPy\'s own arccos' % flips.sum())
+            assert ulp.max() <= 2 and (ulp[flips] >= 1).all()
         else:
             assert np.array_equal(t, tr) and np.array_equal(f, fr)
             assert st[i]['max_phi'] == -1.0
@@ -278,9 +300,14 @@ def test_reference_literal_seams_on_golden(golden_dir, ci):
     phi, mx = eng.get_phi(fl, foe)
     p = phi[0].cpu().numpy()
     assert p.dtype == g['phi'].dtype
-    tol = 1e-9 if fd.dtype == np.float64 else 1e-4
-    assert np.abs(p - g['phi']).max() < tol
-    assert abs(float(mx[0]) - float(g['phi'].max())) < tol
+    if fd.dtype == np.float64:
+        assert np.abs(p - g['phi']).max() < 1e-9 and abs(float(mx[0]) - float(g['phi'].max())) < 1e-9
+    else:
+        from oracle import detect_np as dn
+        phi_cr = dn.get_phi(fd, (g['foe'][0], g['foe'][1]), cr_arccos_f32=True)
+        assert np.array_equal(p, phi_cr) and float(mx[0]) == float(phi_cr.max())
+        ulp = np.abs(p.view(np.int32).astype(np.int64) - g['phi'].view(np.int32).astype(np.int64))
+        assert ulp.max() <= 2          # NumPy's float32 arccos is not correctly rounded
     eng.close()
 
 

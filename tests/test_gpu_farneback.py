@@ -57,6 +57,10 @@ def test_stages_match_oracle(golden_dir, name):
             R = eng.tap('R', lvl, j).cpu().numpy()
             ref = taps[('R%d' % j, lvl)]
             assert np.abs(R - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), ('R', lvl, j)
+        # the matrices after the last UpdateMatrices of the level (M0 when there is a single iteration)
+        M = eng.tap('M', lvl, 0).cpu().numpy()
+        ref = taps[('M%d' % (p['iterations'] - 1), lvl)]
+        assert np.abs(M - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), ('M', lvl, float(np.abs(M - ref).max()))
         # level 0 flow lives in the caller's output buffer (already copied out as `flow`)
         fl = flow if lvl == 0 else eng.tap('flow', lvl, 0).cpu().numpy()
         ref = taps[('flow%d' % (p['iterations'] - 1), lvl)]
