@@ -252,6 +252,19 @@ int mavd_tpr_fpr_counts(const uint8_t* d_gt, const int64_t* d_img, int64_t n, in
  * (0 = the reference's `invalid_frame`). */
 int mavd_flow_vis(const float* d_flow, int64_t n_pixels, uint8_t* d_bgr, uint32_t* d_scratch3, void* stream);
 
+/* ---- next-row f4: the image payloads Processor.run_detection writes (src/processor.py:324,364-376,385-392) ----
+ * mavd_phi_colormap: im_helpers.apply_colormap(im_helpers.to_rgb(phi, max_value)) (src/im_helpers.py:112-135,162-201):
+ * v = uint8(around(|phi| * 255 / max_value)) evaluated in phi's own dtype (float32 phi stays float32), then OpenCV's JET
+ * table.  d_gray_rgb (nullable) receives to_rgb's (n_pixels, 3) image, d_bgr (nullable) the colour-mapped one. */
+int mavd_phi_colormap(const void* d_phi, int32_t phi_is_f64, int64_t n_pixels, double max_value, uint8_t* d_gray_rgb,
+                      uint8_t* d_bgr, void* stream);
+/* mavd_mask_overlay: mask_rgb = frame with (150, 0, 150) where estimate_fixed is set; cv2.addWeighted(frame, 0.2,
+ * mask_rgb, 0.8, 0) (src/processor.py:385-392).  d_frame is (n_pixels, channels) uint8 with channels 3 (BGR, as
+ * Dataset.get_frame delivers) or 1 (gray, replicated); d_out (n_pixels, 3).  d_mask_rgb (nullable) receives
+ * im_helpers.to_rgb(255 * estimate_fixed) (src/processor.py:364). */
+int mavd_mask_overlay(const uint8_t* d_frame, int32_t channels, const uint8_t* d_mask, int64_t n_pixels, uint8_t* d_out,
+                      uint8_t* d_mask_rgb, void* stream);
+
 /* ---- stage 4 (not in the reference): 8-connected components of a mask ----
  * Labels are numbered 1..n by first appearance in a raster scan (0 = background).
  * d_boxes: n x max_boxes x 5 int32 [left, top, width, height, area]; d_n_labels: n int32 (true count).

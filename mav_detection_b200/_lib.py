@@ -129,6 +129,8 @@ SIGNATURES = {
     'mavd_simple_bbox': (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'mavd_tpr_fpr_counts': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     'mavd_flow_vis': (C.c_int, [_P, C.c_int64, _P, _P, _P]),
+    'mavd_phi_colormap': (C.c_int, [_P, C.c_int32, C.c_int64, C.c_double, _P, _P, _P]),
+    'mavd_mask_overlay': (C.c_int, [_P, C.c_int32, _P, C.c_int64, _P, _P, _P]),
     'mavd_launch_count': (C.c_int64, []),
     'mavd_debug_force_generic_iteration': (C.c_int, [_P, C.c_int32]),
     'mavd_debug_force_exact_residual': (C.c_int, [_P, C.c_int32]),

@@ -743,6 +743,22 @@ int mavd_tpr_fpr_counts(const uint8_t* d_gt, const int64_t* d_img, int64_t n, in
     return tpr_fpr_run(d_gt, d_img, n, d_counts4, (cudaStream_t)stream);
 }
 
+int mavd_phi_colormap(const void* d_phi, int32_t phi_is_f64, int64_t n_pixels, double max_value, uint8_t* d_gray_rgb,
+                      uint8_t* d_bgr, void* stream) {
+    MAVD_REQUIRE(n_pixels >= 0 && (n_pixels == 0 || d_phi) && (d_gray_rgb || d_bgr), MAVD_ERR_INVALID,
+                 "phi_colormap: bad arguments");
+    if (n_pixels == 0) return MAVD_OK;
+    return phi_colormap_run(d_phi, phi_is_f64 ? 1 : 0, n_pixels, max_value, d_gray_rgb, d_bgr, (cudaStream_t)stream);
+}
+
+int mavd_mask_overlay(const uint8_t* d_frame, int32_t channels, const uint8_t* d_mask, int64_t n_pixels, uint8_t* d_out,
+                      uint8_t* d_mask_rgb, void* stream) {
+    MAVD_REQUIRE(n_pixels >= 0 && (channels == 1 || channels == 3) && (n_pixels == 0 || (d_frame && d_mask && d_out)),
+                 MAVD_ERR_INVALID, "mask_overlay: bad arguments");
+    if (n_pixels == 0) return MAVD_OK;
+    return mask_overlay_run(d_frame, channels, d_mask, n_pixels, d_out, d_mask_rgb, (cudaStream_t)stream);
+}
+
 int mavd_flow_vis(const float* d_flow, int64_t n_pixels, uint8_t* d_bgr, uint32_t* d_scratch3, void* stream) {
     MAVD_REQUIRE(n_pixels >= 1 && d_flow && d_bgr && d_scratch3, MAVD_ERR_INVALID, "flow_vis: bad arguments");
     return flow_vis_run(d_flow, n_pixels, d_bgr, d_scratch3, (cudaStream_t)stream);

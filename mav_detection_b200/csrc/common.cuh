@@ -239,6 +239,10 @@ int residual_run(mavd_handle h, const void* d_flow, int flow_kind, int n, const 
                  int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
                  size_t stats_stride_bytes, int run_f64, int run_f32, cudaStream_t s, bool list_fixed_units = false,
                  const float* d_gt_flow = nullptr);
+int phi_colormap_run(const void* d_phi, int is_f64, int64_t n, double max_value, uint8_t* d_gray_rgb, uint8_t* d_bgr,
+                     cudaStream_t s);
+int mask_overlay_run(const uint8_t* d_frame, int channels, const uint8_t* d_mask, int64_t n, uint8_t* d_out,
+                     uint8_t* d_mask_rgb, cudaStream_t s);
 int pack_mask_run(const uint8_t* d_mask, int n, int64_t npx, uint8_t* d_bits, cudaStream_t s);
 int unpack_mask_run(const uint8_t* d_bits, int n, int64_t npx, uint8_t value, uint8_t* d_mask, cudaStream_t s);
 static inline int64_t packed_mask_bytes(int64_t npx) { return ((npx + 7) / 8 + 3) / 4 * 4; }

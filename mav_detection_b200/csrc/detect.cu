@@ -7,6 +7,8 @@
 // one rounding per operation and the masks must be bit-exact.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mavd {
@@ -1118,6 +1120,111 @@ int flow_vis_run(const float* d_flow, int64_t n, uint8_t* d_bgr, uint32_t* d_scr
     vis_minmax_kernel<<<148 * 4, 256, 0, s>>>((const float2*)d_flow, n, d_scratch3);
     MAVD_LAUNCHED();
     vis_kernel<<<148 * 8, 256, 0, s>>>((const float2*)d_flow, n, d_scratch3, d_bgr);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Visualisation payloads of Processor.run_detection (next-row f4):
+//   phi image      im_helpers.apply_colormap(im_helpers.to_rgb(phi, max_value=180)) — processor.py:324,376 with
+//                  im_helpers.py:112-135,162-201: v = uint8(around(|phi| * 255 / max)) in phi's own dtype, GRAY2RGB, then
+//                  cv2.applyColorMap(COLORMAP_JET), which for a 3-channel input takes BGR2GRAY (= v for equal
+//                  channels) and looks v up in OpenCV's 256-entry JET table (embedded below, BGR order; pinned against
+//                  cv2.applyColorMap in tests/test_oracle_vis.py)
+//   mask overlay   mask_rgb = frame; mask_rgb[estimate_fixed] = (150, 0, 150);
+//                  cv2.addWeighted(frame, 0.2, mask_rgb, 0.8, 0) — processor.py:385-392.  Unmasked pixels come out
+//                  unchanged (0.2 v + 0.8 v rounds to v), masked ones are round(0.2 v + 0.8 c): 0.2 v is never within
+//                  0.1 of a rounding tie, so the float evaluation order cannot matter.
+// ------------------------------------------------------------------------------------------------
+__constant__ uint8_t kJetLut[768] = {
+    128, 0, 0, 132, 0, 0, 136, 0, 0, 140, 0, 0, 144, 0, 0, 148, 0, 0, 152, 0, 0, 156, 0, 0,
+    160, 0, 0, 164, 0, 0, 168, 0, 0, 172, 0, 0, 176, 0, 0, 180, 0, 0, 184, 0, 0, 188, 0, 0,
+    192, 0, 0, 196, 0, 0, 200, 0, 0, 204, 0, 0, 208, 0, 0, 212, 0, 0, 216, 0, 0, 220, 0, 0,
+    224, 0, 0, 228, 0, 0, 232, 0, 0, 236, 0, 0, 240, 0, 0, 244, 0, 0, 248, 0, 0, 252, 0, 0,
+    255, 0, 0, 255, 4, 0, 255, 8, 0, 255, 12, 0, 255, 16, 0, 255, 20, 0, 255, 24, 0, 255, 28, 0,
+    255, 32, 0, 255, 36, 0, 255, 40, 0, 255, 44, 0, 255, 48, 0, 255, 52, 0, 255, 56, 0, 255, 60, 0,
+    255, 64, 0, 255, 68, 0, 255, 72, 0, 255, 76, 0, 255, 80, 0, 255, 84, 0, 255, 88, 0, 255, 92, 0,
+    255, 96, 0, 255, 100, 0, 255, 104, 0, 255, 108, 0, 255, 112, 0, 255, 116, 0, 255, 120, 0, 255, 124, 0,
+    255, 128, 0, 255, 132, 0, 255, 136, 0, 255, 140, 0, 255, 144, 0, 255, 148, 0, 255, 152, 0, 255, 156, 0,
+    255, 160, 0, 255, 164, 0, 255, 168, 0, 255, 172, 0, 255, 176, 0, 255, 180, 0, 255, 184, 0, 255, 188, 0,
+    255, 192, 0, 255, 196, 0, 255, 200, 0, 255, 204, 0, 255, 208, 0, 255, 212, 0, 255, 216, 0, 255, 220, 0,
+    255, 224, 0, 255, 228, 0, 255, 232, 0, 255, 236, 0, 255, 240, 0, 255, 244, 0, 255, 248, 0, 255, 252, 0,
+    254, 255, 2, 250, 255, 6, 246, 255, 10, 242, 255, 14, 238, 255, 18, 234, 255, 22, 230, 255, 26, 226, 255, 30,
+    222, 255, 34, 218, 255, 38, 214, 255, 42, 210, 255, 46, 206, 255, 50, 202, 255, 54, 198, 255, 58, 194, 255, 62,
+    190, 255, 66, 186, 255, 70, 182, 255, 74, 178, 255, 78, 174, 255, 82, 170, 255, 86, 166, 255, 90, 162, 255, 94,
+    158, 255, 98, 154, 255, 102, 150, 255, 106, 146, 255, 110, 142, 255, 114, 138, 255, 118, 134, 255, 122, 130, 255, 126,
+    126, 255, 130, 122, 255, 134, 118, 255, 138, 114, 255, 142, 110, 255, 146, 106, 255, 150, 102, 255, 154, 98, 255, 158,
+    94, 255, 162, 90, 255, 166, 86, 255, 170, 82, 255, 174, 78, 255, 178, 74, 255, 182, 70, 255, 186, 66, 255, 190,
+    62, 255, 194, 58, 255, 198, 54, 255, 202, 50, 255, 206, 46, 255, 210, 42, 255, 214, 38, 255, 218, 34, 255, 222,
+    30, 255, 226, 26, 255, 230, 22, 255, 234, 18, 255, 238, 14, 255, 242, 10, 255, 246, 6, 255, 250, 1, 255, 254,
+    0, 252, 255, 0, 248, 255, 0, 244, 255, 0, 240, 255, 0, 236, 255, 0, 232, 255, 0, 228, 255, 0, 224, 255,
+    0, 220, 255, 0, 216, 255, 0, 212, 255, 0, 208, 255, 0, 204, 255, 0, 200, 255, 0, 196, 255, 0, 192, 255,
+    0, 188, 255, 0, 184, 255, 0, 180, 255, 0, 176, 255, 0, 172, 255, 0, 168, 255, 0, 164, 255, 0, 160, 255,
+    0, 156, 255, 0, 152, 255, 0, 148, 255, 0, 144, 255, 0, 140, 255, 0, 136, 255, 0, 132, 255, 0, 128, 255,
+    0, 124, 255, 0, 120, 255, 0, 116, 255, 0, 112, 255, 0, 108, 255, 0, 104, 255, 0, 100, 255, 0, 96, 255,
+    0, 92, 255, 0, 88, 255, 0, 84, 255, 0, 80, 255, 0, 76, 255, 0, 72, 255, 0, 68, 255, 0, 64, 255,
+    0, 60, 255, 0, 56, 255, 0, 52, 255, 0, 48, 255, 0, 44, 255, 0, 40, 255, 0, 36, 255, 0, 32, 255,
+    0, 28, 255, 0, 24, 255, 0, 20, 255, 0, 16, 255, 0, 12, 255, 0, 8, 255, 0, 4, 255, 0, 0, 255,
+    0, 0, 252, 0, 0, 248, 0, 0, 244, 0, 0, 240, 0, 0, 236, 0, 0, 232, 0, 0, 228, 0, 0, 224,
+    0, 0, 220, 0, 0, 216, 0, 0, 212, 0, 0, 208, 0, 0, 204, 0, 0, 200, 0, 0, 196, 0, 0, 192,
+    0, 0, 188, 0, 0, 184, 0, 0, 180, 0, 0, 176, 0, 0, 172, 0, 0, 168, 0, 0, 164, 0, 0, 160,
+    0, 0, 156, 0, 0, 152, 0, 0, 148, 0, 0, 144, 0, 0, 140, 0, 0, 136, 0, 0, 132, 0, 0, 128,
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) phi_colormap_kernel(const T* __restrict__ phi, int64_t n, T max_value,
+                                                          uint8_t* __restrict__ gray_rgb, uint8_t* __restrict__ bgr) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T a = phi[i] < T(0) ? -phi[i] : phi[i];
+        unsigned v;
+        if (sizeof(T) == 8) {
+            const double t = __ddiv_rn(__dmul_rn((double)a, 255.0), (double)max_value);
+            v = (t == t) ? ((unsigned)(long long)rint(t) & 255u) : 0u;        // around() is round-half-even
+        } else {
+            const float t = __fdiv_rn(__fmul_rn((float)a, 255.f), (float)max_value);
+            v = (t == t) ? ((unsigned)(int)rintf(t) & 255u) : 0u;
+        }
+        if (gray_rgb) { gray_rgb[3 * i] = (uint8_t)v; gray_rgb[3 * i + 1] = (uint8_t)v; gray_rgb[3 * i + 2] = (uint8_t)v; }
+        if (bgr) { bgr[3 * i] = kJetLut[3 * v]; bgr[3 * i + 1] = kJetLut[3 * v + 1]; bgr[3 * i + 2] = kJetLut[3 * v + 2]; }
+    }
+}
+
+int phi_colormap_run(const void* d_phi, int is_f64, int64_t n, double max_value, uint8_t* d_gray_rgb, uint8_t* d_bgr,
+                     cudaStream_t s) {
+    if (!(max_value > 0.0)) max_value = 1.0;      // im_helpers.py:190-191
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    if (is_f64) phi_colormap_kernel<double><<<grid, 256, 0, s>>>((const double*)d_phi, n, max_value, d_gray_rgb, d_bgr);
+    else phi_colormap_kernel<float><<<grid, 256, 0, s>>>((const float*)d_phi, n, (float)max_value, d_gray_rgb, d_bgr);
+    MAVD_LAUNCHED();
+    return MAVD_OK;
+}
+
+__global__ void __launch_bounds__(256) mask_overlay_kernel(const uint8_t* __restrict__ frame, int channels,
+                                                          const uint8_t* __restrict__ mask, int64_t n, uchar3 color,
+                                                          float alpha, uint8_t* __restrict__ out,
+                                                          uint8_t* __restrict__ mask_rgb) {
+    const float beta = (float)(1.0 - (double)alpha);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint8_t px[3];
+        if (channels == 3) { px[0] = frame[3 * i]; px[1] = frame[3 * i + 1]; px[2] = frame[3 * i + 2]; }
+        else { px[0] = px[1] = px[2] = frame[i]; }
+        const bool on = mask[i] != 0;
+        const uint8_t c[3] = {color.x, color.y, color.z};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float other = on ? (float)c[k] : (float)px[k];
+            const float t = __fadd_rn(__fmul_rn((float)px[k], alpha), __fmul_rn(other, beta));
+            out[3 * i + k] = (uint8_t)min(255, max(0, (int)rintf(t)));      // cvRound + saturate_cast<uchar>
+        }
+        // im_helpers.to_rgb(255 * estimate_fixed) (processor.py:364): 0 / 255 on three equal channels
+        if (mask_rgb) { const uint8_t m = on ? 255 : 0; mask_rgb[3 * i] = m; mask_rgb[3 * i + 1] = m; mask_rgb[3 * i + 2] = m; }
+    }
+}
+
+int mask_overlay_run(const uint8_t* d_frame, int channels, const uint8_t* d_mask, int64_t n, uint8_t* d_out,
+                     uint8_t* d_mask_rgb, cudaStream_t s) {
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    mask_overlay_kernel<<<grid, 256, 0, s>>>(d_frame, channels, d_mask, n, make_uchar3(150, 0, 150), 0.2f, d_out, d_mask_rgb);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }

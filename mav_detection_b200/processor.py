@@ -50,7 +50,8 @@ class Processor:
     """Acts as detector over one sequence (the dataset-conversion half of the reference class is out of scope)."""
 
     def __init__(self, config: RunConfig, flow_source: str = 'dataset', batch_frames: int = 8,
-                 farneback_params: Optional[Dict] = None, engine: Any = None, write_results: bool = True) -> None:
+                 farneback_params: Optional[Dict] = None, engine: Any = None, write_results: bool = True,
+                 flow_cache: Any = None) -> None:
         if flow_source not in ('dataset', 'farneback'):
             raise ValueError("flow_source must be 'dataset' or 'farneback'")
         self.config = config
@@ -62,6 +63,9 @@ class Processor:
         self.flow_source = flow_source
         self.batch_frames = int(batch_frames)
         self.write_results = write_results
+        # flow_source 'farneback' + flow_cache (a flow_cache.FloCache): every computed flow field is also written as
+        # <cache dir>/<frame index:06d>.flo, the files Dataset.get_flow_uv reads (datasets/dataset.py:205-212)
+        self.flow_cache = flow_cache
         width, height = self.dataset.capture_size
         if engine is None:
             from . import engine as engine_mod
@@ -183,13 +187,16 @@ class Processor:
         eng = self.engine
         width, height = self.dataset.capture_size
         B = self.batch_frames
-        inflight: List[Tuple[int, List[int], np.ndarray, np.ndarray, bool]] = []   # (slot, indices, records, sky, gt?)
+        inflight: List[tuple] = []   # (slot, indices, records, sky, gt?, flow)
         slot = 0
 
         def finish(entry) -> None:
-            s, indices, records, sky, has_gt = entry
+            s, indices, records, sky, has_gt, flow = entry
             if s >= 0:
                 eng.wait_host(s)
+            if flow is not None:
+                for k, i in enumerate(indices):           # frame_step_size may skip indices: one file per frame
+                    self.flow_cache.put_batch(i, flow[k:k + 1])
             for k, i in enumerate(indices):
                 fr = self._frame_result(i, records[k], sky[k], has_gt)
                 self.detection_results[i] = fr
@@ -212,7 +219,7 @@ class Processor:
                 imu, samples, sky, seg, gt = self._host_inputs(indices, 0)
                 records = self._pinned(0, 'records', (n,), eng_records_dtype())
                 eng.detect_host(flows, imu, samples, sky=sky, seg=seg, gt_flow=gt, records=records)
-                finish((-1, indices, records, sky, gt is not None))
+                finish((-1, indices, records, sky, gt is not None, None))
             else:
                 # flow(i) = Farneback(frame i, frame i+1); consecutive batches share one frame
                 if len(inflight) == HOST_SLOTS - 1:
@@ -225,8 +232,11 @@ class Processor:
                 self._pending_frame = frames[-1].copy()
                 imu, samples, sky, seg, gt = self._host_inputs(indices, slot)
                 records = self._pinned(slot, 'records', (n,), eng_records_dtype())
-                eng.submit_host(slot, frames, imu, samples, n_pairs=n, sky=sky, seg=seg, gt_flow=gt, records=records)
-                inflight.append((slot, indices, records, sky, gt is not None))
+                flow = self._pinned(slot, 'flow_out', (n, height, width, 2), np.float32) if self.flow_cache is not None \
+                    else None
+                eng.submit_host(slot, frames, imu, samples, n_pairs=n, sky=sky, seg=seg, gt_flow=gt, flow_out=flow,
+                                records=records)
+                inflight.append((slot, indices, records, sky, gt is not None, flow))
                 slot = (slot + 1) % HOST_SLOTS
             self.frame_index = indices[-1] + self.frame_step_size
             n10 = int(self.dataset.N / 10)

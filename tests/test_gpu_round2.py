@@ -1,6 +1,8 @@
 """GPU: whole-path parity at the BASELINE sizes (1080p C2, one 4K pair, the dense-mask case), the 1-bit-per-pixel wire
 format, the batched ground-truth-flow reduction, graph replay vs direct launches, and several engines / devices in
 one process.  Everything goes through the C ABI (mav_detection_b200.engine is a ctypes shim)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -314,3 +316,78 @@ def test_two_engines_in_one_process():
     assert g.device == b.device
     a.close()
     b.close()
+
+
+def test_vis_kernels_match_the_reference_outputs(golden_dir):
+    """mavd_phi_colormap / mavd_mask_overlay through the reference-named im_helpers functions, against the golden vectors
+    the reference's own im_helpers / processor.py statements produced (tests/golden/make_golden_vis_flo.py)."""
+    import os
+    from mav_detection_b200 import im_helpers
+    from oracle import vis_np
+    g = np.load(os.path.join(golden_dir, 'vis_ref.npz'))
+    for name, phi in (('f64', g['phi64']), ('f32', g['phi32'])):
+        rgb = im_helpers.to_rgb(phi, max_value=180.0)
+        assert np.array_equal(rgb, g['phi_rgb_' + name]), name
+        assert np.array_equal(im_helpers.apply_colormap(rgb), g['phi_jet_' + name]), name
+        assert np.array_equal(im_helpers.apply_colormap(rgb, max_value=180.0), g['phi_jet_max_' + name]), name
+        assert np.array_equal(im_helpers.apply_colormap(phi, max_value=180.0)[1:], g['phi_jet_' + name][1:]), name
+    vis, mask_rgb = im_helpers.mask_overlay(g['frame'], g['fixed'], want_mask_rgb=True)
+    assert np.array_equal(vis, g['mask_vis']) and np.array_equal(mask_rgb, g['result_img'])
+    gray = g['frame'][..., 1].copy()
+    assert np.array_equal(im_helpers.mask_overlay(gray, g['fixed']), vis_np.mask_overlay(gray, g['fixed'])[0])
+    # every byte value through the overlay, masked and unmasked
+    v = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    frame = np.stack([v, v[::-1], v.T], -1).copy()
+    for fixed in (np.zeros((16, 16), bool), np.ones((16, 16), bool)):
+        assert np.array_equal(im_helpers.mask_overlay(frame, fixed), vis_np.mask_overlay(frame, fixed)[0])
+    # a 1080p phi field straight from the residual stage (float64) and its colour image
+    rng = np.random.default_rng(7)
+    big = rng.uniform(0, 180, (1080, 1920))
+    assert np.array_equal(im_helpers.apply_colormap(im_helpers.to_rgb(big, 180.0)),
+                          vis_np.apply_colormap_jet(vis_np.to_rgb(big, 180.0)))
+
+
+def test_flo_cache_round_trip_through_the_processor(tmp_path):
+    """flow_source='farneback' with a FloCache writes <index:06d>.flo per frame in the reference's layout; a second
+    Processor with flow_source='dataset' over CachedFlowDataset (the Dataset.get_flow_uv seam) reproduces every
+    FrameResult of the first run."""
+    import logging
+    import torch
+    from mav_detection_b200 import engine, flow_cache, synth, utils
+    from mav_detection_b200.processor import Processor
+    from mav_detection_b200.run_config import RunConfig
+    W, H, F = 320, 240, 8
+    params = dict(engine.SAMPLE_PARAMS)
+    seq = synth.make_sequence(W, H, F, seq=22, with_rotation=True)
+    cache = flow_cache.FloCache(str(tmp_path / 'output' / 'inference' / 'run.epoch-0-flow-field'))
+
+    def run(ds, source, fc):
+        RunConfig.register_dataset(RunConfig.DatasetType.SIMULATION, lambda logger, sequence: ds)
+        cfg = RunConfig(logging.getLogger('test'), 'simulation', 'synthetic', False, False, False, True, False, False,
+                        'FLOW_FOE_CLUSTERING')
+        np.random.seed(5)
+        proc = Processor(cfg, flow_source=source, batch_frames=3, farneback_params=params, write_results=False,
+                         flow_cache=fc)
+        res = proc.run_detection()
+        eng = proc.engine
+        proc.release()
+        return res, eng
+    first, eng = run(synth.SyntheticDataset(seq), 'farneback', cache)
+    cache.flush()
+    assert sorted(os.listdir(cache.directory)) == ['%06d.flo' % i for i in range(F - 1)]
+    flows = eng.farneback(torch.from_numpy(seq.frames).to(eng.device)).cpu().numpy()
+    for i in range(F - 1):
+        assert np.array_equal(utils.read_flow(flow_cache.flo_path(cache.directory, i)), flows[i]), i
+    # device batches go through the pinned double buffer
+    cache2 = flow_cache.FloCache(str(tmp_path / 'again'))
+    dev = torch.from_numpy(flows).to(eng.device)
+    cache2.put_batch(0, dev[:4])
+    cache2.put_batch(4, dev[4:])
+    for i in range(F - 1):
+        assert np.array_equal(cache2.get_flow_uv(i), flows[i]), i
+    second, _ = run(flow_cache.CachedFlowDataset(synth.SyntheticDataset(seq), cache), 'dataset', None)
+    assert sorted(second) == sorted(first)
+    for i in first:
+        a, b = first[i], second[i]
+        assert a.foe_dense == b.foe_dense and (a.tpr, a.fpr, a.tpr_fixed, a.fpr_fixed) == (b.tpr, b.fpr, b.tpr_fixed, b.fpr_fixed)
+        assert np.allclose(a.drone_flow_pixels, b.drone_flow_pixels, rtol=1e-12)
