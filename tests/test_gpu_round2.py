@@ -391,3 +391,42 @@ def test_flo_cache_round_trip_through_the_processor(tmp_path):
         a, b = first[i], second[i]
         assert a.foe_dense == b.foe_dense and (a.tpr, a.fpr, a.tpr_fixed, a.fpr_fixed) == (b.tpr, b.fpr, b.tpr_fixed, b.fpr_fixed)
         assert np.allclose(a.drone_flow_pixels, b.drone_flow_pixels, rtol=1e-12)
+
+
+@pytest.mark.parametrize('size', [(1920, 1080), (640, 480), (203, 131), (64, 48), (100, 37)])
+def test_ccl_dense_and_structured_masks(size):
+    """The run-based labelling on everything from 100 % foreground to noise: one image-sized component, checkerboards
+    (8-connected through diagonals only), stripes, 50 % noise (thousands of components, more than the 32 boxes kept),
+    widths that are / are not multiples of 4 and of the 128-pixel unit (units straddling rows, several rows per unit)."""
+    import torch
+    from mav_detection_b200 import engine
+    from oracle import ccl_np
+    W, H = size
+    rng = np.random.default_rng(W * 7 + H)
+    ys, xs = np.mgrid[0:H, 0:W]
+    masks = np.stack([
+        np.ones((H, W), np.uint8),                                   # one component
+        ((xs + ys) % 2).astype(np.uint8),                            # checkerboard
+        (xs % 3 == 0).astype(np.uint8),                              # vertical stripes
+        (ys % 2 == 0).astype(np.uint8) * (xs % 7 != 3),              # broken horizontal stripes
+        (rng.random((H, W)) < 0.5).astype(np.uint8),                 # noise
+        (rng.random((H, W)) < 0.93).astype(np.uint8),                # almost full
+        ((xs // 5 + ys // 3) % 2).astype(np.uint8) * 200,            # blocks touching at corners, value != 1
+        np.zeros((H, W), np.uint8),
+    ]).astype(np.uint8)
+    masks[7, H // 2, :] = 1
+    masks[7, :, W // 3] = 1
+    masks[7, 0, 0] = masks[7, H - 1, W - 1] = 1
+    n = masks.shape[0]
+    eng = engine.Engine(W, H, engine.SAMPLE_PARAMS, max_pairs=n)
+    for want_labels in (True, False):
+        labels, boxes, cnt = eng.ccl(torch.from_numpy(masks).cuda(), want_labels=want_labels)
+        boxes, cnt = boxes.cpu().numpy(), cnt.cpu().numpy()
+        for i in range(n):
+            ref, stats = ccl_np.label(masks[i])
+            assert cnt[i] == ref.max(), (i, cnt[i], ref.max())
+            if want_labels:
+                assert np.array_equal(labels[i].cpu().numpy(), ref), i
+            k = min(32, stats.shape[0])
+            assert np.array_equal(boxes[i, :k], stats[:k]), i
+    eng.close()
