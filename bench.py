@@ -157,6 +157,20 @@ def algorithmic_bytes(W, H, params, B, n_frames):
     }
 
 
+def survey_bytes_per_pair(W, H, params):
+    """SURVEY §8(d) stage-graph compulsory HBM bytes of one INDEPENDENT pair (both frames' pyramid and expansion counted
+    for every pair; 992.4 MB for C2): the denominator of the whole-path roofline figure quoted since round 1."""
+    px = [w * h for w, h in level_sizes(W, H, params)]
+    n0, sp, it = px[0], sum(px), params['iterations']
+    pyramid = 2 * sum(n0 + 4 * p for p in px)
+    polyexp = 2 * 24 * sp
+    flow_init = 8 * px[-1] + sum(8 * px[l + 1] + 8 * px[l] for l in range(len(px) - 1))
+    matrices = 68 * sp
+    iters = (88 * (it - 1) + 28) * sp
+    post = 16 * n0
+    return pyramid + polyexp + flow_init + matrices + iters + post
+
+
 def cpu_one_pair(args):
     """The reference's CPU path for one pair: cv2 Farneback + restated derotate/FoE/phi/masks."""
     import cv2
@@ -455,6 +469,7 @@ def measure(name, args, steps, world, rank, local, headline):
                              'per pair: flow %.0f ms, FoE/phi/masks %.0f ms; host has %d logical CPUs'
                              % (workers, cv2.__version__, flow_ms, post_ms, os.cpu_count() or 0)}
         whole_alg = sum(alg.values())
+        whole_survey = survey_bytes_per_pair(W, H, params) * B
         line = {
             'metric': metric_name(W),
             'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': steps, 'warmup': warm,
@@ -473,7 +488,10 @@ def measure(name, args, steps, world, rank, local, headline):
             'e2e_detail': e2e_detail,
             'gpu_launches': int(launches),
             'roofline': roof,
-            'whole_path_frac_of_hbm_peak': round(whole_alg / (elapsed_ms / steps * 1e-3) / 1e9 / peak, 3),
+            'whole_path_frac_of_hbm_peak': round(whole_survey / (elapsed_ms / steps * 1e-3) / 1e9 / peak, 3),
+            'whole_path_bytes': {'survey_8d_independent_pairs_mb_per_pair': round(whole_survey / B / 1e6, 1),
+                                 'sequence_mode_shared_frames_mb_per_pair': round(whole_alg / B / 1e6, 1),
+                                 'frac_sequence_mode': round(whole_alg / (elapsed_ms / steps * 1e-3) / 1e9 / peak, 3)},
             'kernel_classes': per_class,
             'cpu_baseline': cpu,
         }

@@ -485,7 +485,7 @@ void mavd_default_tuning(mavd_tuning* t) {
 int mavd_set_tuning(mavd_handle h, const mavd_tuning* t) {
     MAVD_REQUIRE(h && t, MAVD_ERR_INVALID, "set_tuning: NULL argument");
     MAVD_REQUIRE(t->overlap >= 0 && t->overlap <= 2 && t->pair_group >= 1 && t->mat_coord >= 0 && t->mat_coord <= 2 &&
-                     t->mat_txlog >= 4 && t->mat_txlog <= 8 && t->iter_fuse >= 0 && t->iter_fuse <= 2,
+                     t->mat_txlog >= 4 && t->mat_txlog <= 8 && t->iter_fuse >= 0 && t->iter_fuse <= 1,
                  MAVD_ERR_INVALID, "set_tuning: value out of range");
     DeviceGuard dg(h->cfg.device);
     MAVD_CUDA(cudaDeviceSynchronize());

@@ -929,9 +929,8 @@ __device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, 
 // FUSE (not-last iterations with R1S; default, MAVD_ITER_FUSE=0 selects the staged form): the horizontal sums and the
 // solve are done in registers as in the last iteration and the flow vectors, not the five sums, go through shared
 // memory to reach the x-fastest pixel mapping of the update phase (640 -> 256 wavefronts per tile for that hand-over,
-// one more barrier; same hsum_box, same solve expressions: identical results).  FUSE == 2 (experimental, not yet
-// measured, MAVD_ITER_FUSE=2, window half-widths >= 6): the flow vectors are written straight into the box rows below
-// the 32 rows of vertical sums (raw rows that nobody reads after the vertical pass), which saves that extra barrier.
+// one more barrier; same hsum_box, same solve expressions: identical results).  (A variant that parked the flow vectors
+// in the dead raw rows below the vertical sums to save that barrier measured 0.5 % slower and was removed.)
 template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0>
 __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                              const __grid_constant__ CUtensorMap tmapR,
@@ -1144,18 +1143,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                 gx[it] = make_float4(fx4[0], fx4[1], fx4[2], fx4[3]);
                 gy[it] = make_float4(fy4[0], fy4[1], fy4[2], fy4[3]);
             }
-            if (FUSE == 2) {
-                // (a1') rows IT_TY .. RH-1 of every plane box still hold raw M rows that are dead since the vertical
-                // pass: DR floats per plane, 4096 flow values spread over them in order, no barrier needed first
-                constexpr int DR = (RH - IT_TY) * RW;
-                static_assert(FUSE != 2 || 5 * DR >= 2 * IT_TX * IT_TY, "dead rows too small for the flow vectors");
-#pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                    const int ix = (it * 16 + rsub) * IT_TX + 4 * q4, iy = IT_TX * IT_TY + ix;
-                    *reinterpret_cast<float4*>(box + (ix / DR) * CH + IT_TY * RW + (ix % DR)) = gx[it];
-                    *reinterpret_cast<float4*>(box + (iy / DR) * CH + IT_TY * RW + (iy % DR)) = gy[it];
-                }
-            } else {
+            {
                 __syncthreads();                   // every vertical sum has been consumed: the box is free
                 // (a1) the flow vectors through shared memory: [2][32][64] floats at the start of the box
 #pragma unroll
@@ -1171,12 +1159,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         for (int j = 0; j < PPT; ++j) {
             const int idx = j * NT + tid;
             const int cx = idx & 63, r = idx >> 6;
-            if (FUSE == 2) {
-                constexpr int DR = (RH - IT_TY) * RW;
-                const int iy = IT_TX * IT_TY + idx;
-                ffx[j] = box[(idx / DR) * CH + IT_TY * RW + (idx % DR)];
-                ffy[j] = box[(iy / DR) * CH + IT_TY * RW + (iy % DR)];
-            } else if (FUSE) {
+            if (FUSE) {
                 ffx[j] = box[idx];
                 ffy[j] = box[IT_TX * IT_TY + idx];
             } else {
@@ -1283,13 +1266,6 @@ static int launch_iter_tma_m(int m, const mavd_tuning& tune, const CUtensorMap& 
     // horizontal sums + solve in registers for the not-last iterations too, flow vectors handed to the update phase
     // through shared memory: iter_full 4.27 vs 4.39 ms per 64-pair step (tuning.iter_fuse)
     const int fuse = tune.iter_fuse;
-    if (r1s && !LAST && fuse == 2 && m >= 6) {      // experimental: hand-over through the dead box rows
-        switch (m) {
-            case 6: return launch_iter_tma<6, false, 256, true, 2>(map, mapR, mapRbox, a, grid, s);
-            case 7: return launch_iter_tma<7, false, 256, true, 2>(map, mapR, mapRbox, a, grid, s);
-            default: return launch_iter_tma<8, false, 256, true, 2>(map, mapR, mapRbox, a, grid, s);
-        }
-    }
     if (r1s && !LAST && fuse != 0) {
         switch (m) {
             case 5: return launch_iter_tma<5, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
