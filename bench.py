@@ -387,13 +387,16 @@ def measure(name, args, steps, world, rank, local, headline):
             for slot in range(HOST_SLOTS):
                 eng.wait_host(slot)
         with torch.cuda.stream(stream):
-            for s in range(3):
+            # warm-up: every (staging slot, resident batch) combination once, so that each launch sequence the timed
+            # steps replay has been captured (and every lazily allocated staging buffer exists)
+            n_warm = HOST_SLOTS * N_BATCHES if not copy_only else 3
+            for s in range(n_warm):
                 one(s)
             drain()
             sync_all()
             t0 = time.perf_counter()
             for s in range(n_steps):
-                one(3 + s)
+                one(n_warm + s)
             drain()                       # every step's records and masks have landed in host memory
             torch.cuda.synchronize(dev)
             dt = time.perf_counter() - t0

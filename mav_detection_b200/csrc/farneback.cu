@@ -858,19 +858,25 @@ __device__ __forceinline__ void update_matrices_fast(int x, int y, int w, int h,
 // (bx, by); footprints that leave the box fall back to global loads.  Same operations, same order as
 // update_matrices_fast: identical results.
 
-__device__ __forceinline__ R0Px load_r0(const float* __restrict__ R0, int o, int plane) {
+__device__ __forceinline__ R0Px load_r0(const float* __restrict__ R0, unsigned o, unsigned plane) {
     R0Px r;
     r.y = __ldg(R0 + o); r.x = __ldg(R0 + (o + plane)); r.yy = __ldg(R0 + (o + 2 * plane));
     r.xx = __ldg(R0 + (o + 3 * plane)); r.xy = __ldg(R0 + (o + 4 * plane));
     return r;
 }
 
+// a global store whose address space survives the register pinning of the base pointer below (a plain store through
+// a pointer that went through an asm operand would be emitted as a generic ST)
+__device__ __forceinline__ void st_global_f32(float* p, float v) {
+    asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+
 template <int RW, int RH>
-__device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, int pitch, int plane, bool edge, float dx,
+__device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, int pitch, unsigned plane, bool edge, float dx,
                                                     float dy, const R0Px& r0, const float* __restrict__ R1,
                                                     float* __restrict__ Mout, const float* box, int bx, int by) {
     constexpr int CH = RH * RW;
-    const int o = y * pitch + x;
+    const unsigned o = (unsigned)(y * pitch + x);       // unsigned element offsets: one IMAD.WIDE.U32 per address
     const float r0y = r0.y, r0x = r0.x, r0yy = r0.yy, r0xx = r0.xx, r0xy = r0.xy;
     float fx = (float)x + dx, fy = (float)y + dy;
     const float flx = floorf(fx), fly = floorf(fy);
@@ -890,7 +896,7 @@ __device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, 
             r5 = a00 * q[3 * CH] + a01 * q[3 * CH + 1] + a10 * q[3 * CH + RW] + a11 * q[3 * CH + RW + 1];
             r6 = a00 * q[4 * CH] + a01 * q[4 * CH + 1] + a10 * q[4 * CH + RW] + a11 * q[4 * CH + RW + 1];
         } else {
-            const int q0 = y1 * pitch + x1, q1 = q0 + pitch;
+            const unsigned q0 = (unsigned)(y1 * pitch + x1), q1 = q0 + (unsigned)pitch;
             r2 = a00 * __ldg(R1 + q0) + a01 * __ldg(R1 + q0 + 1) + a10 * __ldg(R1 + q1) + a11 * __ldg(R1 + q1 + 1);
             r3 = a00 * __ldg(R1 + (q0 + plane)) + a01 * __ldg(R1 + (q0 + plane) + 1) +
                  a10 * __ldg(R1 + (q1 + plane)) + a11 * __ldg(R1 + (q1 + plane) + 1);
@@ -919,11 +925,11 @@ __device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, 
                          (y < 5 ? border_factor(y) : 1.f) * (y >= h - 5 ? border_factor(h - y - 1) : 1.f);
         r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
     }
-    Mout[o] = r4 * r4 + r6 * r6;
-    Mout[o + plane] = (r4 + r5) * r6;
-    Mout[o + 2 * plane] = r5 * r5 + r6 * r6;
-    Mout[o + 3 * plane] = r4 * r2 + r6 * r3;
-    Mout[o + 4 * plane] = r6 * r2 + r5 * r3;
+    st_global_f32(Mout + o, r4 * r4 + r6 * r6);
+    st_global_f32(Mout + (o + plane), (r4 + r5) * r6);
+    st_global_f32(Mout + (o + 2 * plane), r5 * r5 + r6 * r6);
+    st_global_f32(Mout + (o + 3 * plane), r4 * r2 + r6 * r3);
+    st_global_f32(Mout + (o + 4 * plane), r6 * r2 + r5 * r3);
 }
 
 // FUSE (not-last iterations with R1S; default, MAVD_ITER_FUSE=0 selects the staged form): the horizontal sums and the
@@ -1098,6 +1104,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
     const float* R0 = a.R + (size_t)(p * a.pair_stride) * 5 * a.plane;
     const float* R1 = R0 + 5 * a.plane;
     float* Mout = LAST ? nullptr : a.Mout + (size_t)p * 5 * a.plane;
+    // keep the pair's M' base as ONE 64-bit register pair: the compiler otherwise carries (kernel argument + 64-bit
+    // element offset) and rebuilds every store address with a 4-instruction add / shift chain instead of one
+    // IMAD.WIDE.U32 on the 32-bit element offset
+    asm volatile("" : "+l"(Mout));
     float2* fl = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
     const bool edge = (x0 < 5) || (y0 < 5) || (x0 + IT_TX > w - 5) || (y0 + IT_TY > h - 5);
     const float scale = a.scale;
@@ -1190,7 +1200,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         const bool col_ok = xp < w;
         auto r0_of = [&](int j) {
             const int y = y0 + ((j * NT + tid) >> 6);
-            return (col_ok && y < h) ? load_r0(R0, y * pitch + xp, plane) : R0Px{0.f, 0.f, 0.f, 0.f, 0.f};
+            return (col_ok && y < h) ? load_r0(R0, (unsigned)(y * pitch + xp), (unsigned)plane) : R0Px{0.f, 0.f, 0.f, 0.f, 0.f};
         };
         R0Px cur = r0_of(0);
         mbar_wait(&bar, 1);
@@ -1200,7 +1210,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
             R0Px nxt = cur;
             if (j + 1 < PPT) nxt = r0_of(j + 1);
             if (col_ok && y < h)
-                update_matrices_box<RW, RH>(xp, y, w, h, pitch, plane, edge, ffx[j], ffy[j], cur, R1, Mout, box, bx, by);
+                update_matrices_box<RW, RH>(xp, y, w, h, pitch, (unsigned)plane, edge, ffx[j], ffy[j], cur, R1, Mout, box, bx, by);
             cur = nxt;
         }
         return;

@@ -101,7 +101,7 @@ def test_whole_path_dense_masks():
     samples = _samples(n, H, W, 33)
     eng = engine.Engine(W, H, params, max_pairs=n)
     flow, fixed, rec = _run_device(eng, seq, n, samples)
-    assert fixed[1].mean() > 0.9                      # the case is what it claims to be
+    assert fixed.mean() > 0.3                         # the case is what it claims to be: large connected masks
     _check_against_chained_oracle(seq, params, flow, fixed, rec, samples, cv2_pairs=(1,))
     eng.close()
 
