@@ -124,10 +124,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// TMA descriptor of a planar buffer: rank-3 float tensor {pitch, h, planes}, box {80, box_h, box_planes}, zero fill.
-static bool make_plane_tensor_map(CUtensorMap* map, float* base, int pitch, int h, int planes, size_t plane, int box_h,
-                                  int box_planes) {
-    static EncodeTiledFn fn = nullptr;
+// TMA descriptor of a rank-3 tensor {d0, d1, d2} (d0 fastest) of 4-byte floats or bytes with byte strides s1, s2 and a
+// box {b0, b1, b2}; out-of-bounds cells are filled with zeros.  Base and strides must be multiples of 16 bytes.
+bool encode_tensor_map_3d(CUtensorMap* map, bool is_u8, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                          uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+    static std::atomic<EncodeTiledFn> fn_cache{nullptr};
+    EncodeTiledFn fn = fn_cache.load();
     if (!fn) {
         void* f = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -136,15 +138,25 @@ static bool make_plane_tensor_map(CUtensorMap* map, float* base, int pitch, int 
             return false;
         }
         fn = (EncodeTiledFn)f;
+        fn_cache.store(fn);
     }
-    cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)h, (cuuint64_t)planes};
-    cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)plane * sizeof(float)};
-    cuuint32_t box[3] = {80u, (cuuint32_t)box_h, (cuuint32_t)box_planes};
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (s1_bytes & 15) || (s2_bytes & 15)) return false;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+    cuuint32_t box[3] = {b0, b1, b2};
     cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, is_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+
+// TMA descriptor of a planar buffer: rank-3 float tensor {pitch, h, planes}, box {80, box_h, box_planes}, zero fill.
+static bool make_plane_tensor_map(CUtensorMap* map, float* base, int pitch, int h, int planes, size_t plane, int box_h,
+                                  int box_planes) {
+    return encode_tensor_map_3d(map, false, base, (uint64_t)pitch, (uint64_t)h, (uint64_t)planes,
+                                (uint64_t)pitch * sizeof(float), (uint64_t)plane * sizeof(float), 80u, (uint32_t)box_h,
+                                (uint32_t)box_planes);
 }
 
 struct Arena {
@@ -352,6 +364,8 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
             C_TRY(A.alloc(&L.tmp, (size_t)F * L.h * round_up(W, 4)));   // vertical-pass output [F][h_l][Wp]
         }
         C_TRY(A.alloc(&L.img, (size_t)F * L.plane));
+        // polynomial expansion of the float levels: one TMA box {80, 32 + 2 poly_n} of the level image per tile
+        L.has_tmap_img = li > 0 && make_plane_tensor_map(&L.tmapImg, L.img, L.pitch, L.h, F, L.plane, 32 + 2 * fp.poly_n, 1);
         C_TRY(A.alloc(&L.R, (size_t)F * 5 * L.plane));
         C_TRY(A.alloc(&L.M[0], (size_t)B * 5 * L.plane));
         C_TRY(A.alloc(&L.M[1], (size_t)B * 5 * L.plane));

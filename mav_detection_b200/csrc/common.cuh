@@ -111,6 +111,8 @@ struct Level {
     CUtensorMap tmapR;      // TMA descriptor of R: dims {pitch, h, frames*5}, box {80, 48, 10} (L2 prefetch only)
     CUtensorMap tmapRbox;   // TMA descriptor of R with the M box geometry {80, 32+2m, 5}: R1 staged in shared memory
     bool has_tmap = false;
+    CUtensorMap tmapImg;    // TMA descriptor of img: dims {pitch, h, frames}, box {80, 32+2 poly_n, 1} (polynomial expansion)
+    bool has_tmap_img = false;
 };
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline).
@@ -222,6 +224,9 @@ struct mavd_handle_s {
 };
 
 namespace mavd {
+// api.cu
+bool encode_tensor_map_3d(CUtensorMap* map, bool is_u8, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                          uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
 // farneback.cu
 int farneback_run(mavd_handle h, const uint8_t* d_frames, int n_pairs, int pair_stride, float* d_flow,
                   cudaStream_t s);

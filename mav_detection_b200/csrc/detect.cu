@@ -1409,6 +1409,57 @@ __global__ void __launch_bounds__(256) ccl_list_kernel(const uint8_t* __restrict
     }
 }
 
+// The row above a unit and the single pixels around it: U = the 128 pixels above the unit, um1 = the pixel before
+// them, u128 = the pixel after them, prevpix = the pixel before the unit itself.
+struct UnitAbove {
+    Bits128 U, Uprev, US;    // upper pixels, upper pixels shifted by one (bit t = the pixel above t - 1), upper-run starts
+    unsigned prevpix, um1, u128;
+};
+
+template <int VEC>
+__device__ __forceinline__ UnitAbove unit_above(const uint8_t* __restrict__ m, int ub, int w, int npx, const Bits128& RS) {
+    const int lane = threadIdx.x & 31;
+    UnitAbove A;
+    A.U = ccl_load_bits<VEC>(m, ub - w, npx);
+    unsigned side = 0;
+    if (lane == 0 && ub >= 1) side = m[ub - 1] != 0;
+    if (lane == 1 && ub - w - 1 >= 0) side = m[ub - w - 1] != 0;
+    if (lane == 2 && ub - w + CCL_UNIT >= 0 && ub - w + CCL_UNIT < npx) side = m[ub - w + CCL_UNIT] != 0;
+    const unsigned sides = __ballot_sync(0xffffffffu, side != 0);
+    A.prevpix = sides & 1u; A.um1 = (sides >> 1) & 1u; A.u128 = (sides >> 2) & 1u;
+    A.Uprev = shl1(A.U, A.um1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) A.US.w[j] = A.U.w[j] & (~A.Uprev.w[j] | RS.w[j]);   // a row start always starts a run
+    return A;
+}
+
+// First contact of the run [s, e] (unit-local bit positions, same row) with the row above, as a column in
+// [s - 1, e + 1] clipped to the row: -1 .. 128, or 129 when there is none.
+__device__ __forceinline__ int first_upper_contact(const UnitRuns& R, const UnitAbove& A, int s, int e, int w) {
+    if (!bit_of(R.RS, s) && ((s == 0) ? A.um1 : (unsigned)bit_of(A.U, s - 1))) return s - 1;
+    // columns s .. min(e + 1, 127) of U
+    const int hi = min(e + 1, CCL_UNIT - 1);
+    const bool e1_in_row = (e + 1 < CCL_UNIT) ? !bit_of(R.RS, e + 1) : ((R.x0 + CCL_UNIT) % w != 0);
+    int j = s >> 5;
+    unsigned wv = A.U.w[j] & (0xffffffffu << (s & 31));
+    while (true) {
+        if (wv) {
+            const int c = 32 * j + __ffs(wv) - 1;
+            if (c <= e || (c == e + 1 && c <= hi && e1_in_row)) return c;
+            break;
+        }
+        if (++j > (hi >> 5)) break;
+        wv = A.U.w[j];
+    }
+    if (e == CCL_UNIT - 1 && e1_in_row && A.u128) return CCL_UNIT;
+    return CCL_UNIT + 1;
+}
+
+// init: every set pixel points at the start of its run inside the unit; the run START itself is pre-linked without
+// an atomic: to the previous pixel when the run continues one that ends the previous unit, else to the first pixel
+// of the row above that touches the run (both have smaller indices and belong to the same component, so the forest
+// is valid).  Most runs have no further contact: the merge pass then has nothing to do for them — in particular a
+// fully set frame needs no union at all.
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w,
                                                       int npx, CclList L) {
@@ -1417,25 +1468,39 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict
     for (int q = gw; q < cnt; q += warps) {
         const int e = L.entries[q];
         const int f = e / L.n_units, u = e - f * L.n_units, ub = u * CCL_UNIT;
+        const uint8_t* m = mask + (size_t)f * npx;
         UnitRuns R;
-        R.M = ccl_load_bits<VEC>(mask + (size_t)f * npx, ub, npx);
+        R.M = ccl_load_bits<VEC>(m, ub, npx);
         R.RS = row_starts(ub, w, R.x0);
         unit_runs(R);
+        const UnitAbove A = unit_above<VEC>(m, ub, w, npx, R.RS);
         int* par = parent + (size_t)f * npx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int t = 32 * j + lane;
-            if ((R.M.w[j] >> lane) & 1u) par[ub + t] = ub + last_set_at_or_below(R.S, t);
+            if (!((R.M.w[j] >> lane) & 1u)) continue;
+            int target;
+            if ((R.S.w[j] >> lane) & 1u) {
+                if (t == 0 && A.prevpix && !(R.RS.w[0] & 1u)) {
+                    target = ub - 1;
+                } else {
+                    const int c = first_upper_contact(R, A, t, first_set_at_or_above(R.E, t), w);
+                    target = c <= CCL_UNIT ? ub - w + c : ub + t;
+                }
+            } else {
+                target = ub + last_set_at_or_below(R.S, t);
+            }
+            par[ub + t] = target;
         }
     }
 }
 
-// One union per contact between a run of this unit and a run of the row above / the previous unit.  U = the 128 pixels
-// above the unit, um1 = the pixel before them, u128 = the pixel after them.  With [s, e] a run of this row:
-//   left   s is the unit's first pixel, not a row start, and the pixel before the unit is set
-//   (B)    the upper run covers column s - 1 (it started at or before s - 1): one union at s
-//   (A)    an upper run STARTS at column t in [s, e + 1]: one union, by the lane that owns t (with pixel t if it is set,
-//          else with pixel t - 1, whose up-right neighbour it is); a start at column 128 is taken by pixel 127's owner
+// merge: one union per contact between a run of this unit and an upper run that init has not linked already.  With
+// [s, e] a run of this row, its contacts with the row above are: the upper run that covers column s - 1 (if any), and
+// every upper run that STARTS at a column t in [s, e + 1].  The first of them in column order is the one init linked;
+// a run that continues from the previous unit has that unit's contacts through the previous pixel, so its contact at
+// s - 1 is implied.  A contact at column t is handled by the lane that owns t (with pixel t if it is set, else with
+// pixel t - 1, whose up-right neighbour it is); one at column 128 by pixel 127's owner.
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w,
                                                        int npx, CclList L) {
@@ -1450,32 +1515,30 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restric
         R.M = ccl_load_bits<VEC>(m, ub, npx);
         R.RS = row_starts(ub, w, R.x0);
         unit_runs(R);
-        const Bits128 U = ccl_load_bits<VEC>(m, ub - w, npx);
-        // three single pixels: before the unit, before / after the 128 pixels above it
-        unsigned side = 0;
-        if (lane == 0 && ub >= 1) side = m[ub - 1] != 0;
-        if (lane == 1 && ub - w - 1 >= 0) side = m[ub - w - 1] != 0;
-        if (lane == 2 && ub - w + CCL_UNIT >= 0 && ub - w + CCL_UNIT < npx) side = m[ub - w + CCL_UNIT] != 0;
-        const unsigned sides = __ballot_sync(0xffffffffu, side != 0);
-        const unsigned prevpix = sides & 1u, um1 = (sides >> 1) & 1u, u128 = (sides >> 2) & 1u;
-        const Bits128 Uprev = shl1(U, um1);
-        Bits128 US;          // the upper pixel above t starts an upper run
-#pragma unroll
-        for (int j = 0; j < 4; ++j) US.w[j] = U.w[j] & (~Uprev.w[j] | R.RS.w[j]);
+        const UnitAbove A = unit_above<VEC>(m, ub, w, npx, R.RS);
+        // warp-uniform early out: no upper-run start anywhere above the unit (nor right after it) -> nothing to union
+        if (!(A.US.w[0] | A.US.w[1] | A.US.w[2] | A.US.w[3] | A.u128)) continue;
+        const bool left_cont = A.prevpix && !(R.RS.w[0] & 1u) && (R.M.w[0] & 1u);    // the run at t = 0 continues a run
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int t = 32 * j + lane, g = ub + t;
             const bool mt = (R.M.w[j] >> lane) & 1u, rs = (R.RS.w[j] >> lane) & 1u;
-            if (mt && ((R.S.w[j] >> lane) & 1u) && !rs) {
-                if (t == 0 && prevpix) uf_union(par, g, g - 1);
-                if ((Uprev.w[j] >> lane) & 1u) uf_union(par, g, g - w - 1);                       // (B)
+            int tc = -1, tu = 0, col = 0;          // pixel of this row, pixel of the row above, contact column
+            if ((A.US.w[j] >> lane) & 1u) {
+                if (mt) { tc = t; tu = g - w; col = t; }
+                else if (t >= 1 && !rs && bit_of(R.M, t - 1)) { tc = t - 1; tu = g - w; col = t; }
             }
-            if ((US.w[j] >> lane) & 1u) {                                                       // (A)
-                if (mt) uf_union(par, g, g - w);
-                else if (t >= 1 && !rs && bit_of(R.M, t - 1)) uf_union(par, g - 1, g - w);
+            if (t == CCL_UNIT - 1 && mt && A.u128 && !((A.U.w[3] >> 31) & 1u) && (R.x0 + CCL_UNIT) % w != 0) {
+                // an upper run starts right after the 128 pixels above: up-right neighbour of pixel 127
+                const int s = last_set_at_or_below(R.S, t);
+                if ((s == 0 && left_cont) || first_upper_contact(R, A, s, t, w) != CCL_UNIT) uf_union(par, g, g - w + 1);
             }
-            if (t == CCL_UNIT - 1 && mt && u128 && !((U.w[3] >> 31) & 1u) && (R.x0 + CCL_UNIT) % w != 0)
-                uf_union(par, g, g - w + 1);
+            if (tc >= 0) {
+                const int s = last_set_at_or_below(R.S, tc);
+                const bool linked_by_init = !(s == 0 && left_cont) &&
+                                            first_upper_contact(R, A, s, first_set_at_or_above(R.E, s), w) == col;
+                if (!linked_by_init) uf_union(par, ub + tc, tu);
+            }
         }
     }
 }
@@ -1621,15 +1684,37 @@ __global__ void ccl_boxes_init_kernel(int32_t* boxes, size_t boxes_stride, int m
 }
 
 // labels_out may alias parent: a warp reads only the parent entries of its own unit's run starts, all before its
-// first label store; background pixels were zeroed before the init pass.  Boxes: one update per RUN; the bounds are
-// read first (L2, monotone values: a stale read can only cause a redundant atomic, never a missed one).
+// first label store; background pixels were zeroed before the init pass.
+// Boxes: one contribution per RUN.  A warp walks ~100 units; consecutive list entries mostly belong to the same frame
+// and, in dense masks, to the same component, whose five box words would otherwise take an atomic per run from every
+// warp at once.  So the warp keeps ONE (frame, label) box in registers: runs of that label are folded in with warp
+// reductions, the box is flushed (five atomics by one lane) only when the unit's first label changes; runs of other
+// labels in the unit go out directly, bounds first checked against the current value (monotone: a stale read can only
+// cause a redundant atomic, never a missed one).
+struct BoxAcc {
+    int key = -1;            // frame * (max_boxes + 1) + label, -1 = empty
+    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -1, y1 = -1, area = 0;
+};
+
+__device__ __forceinline__ void box_flush(BoxAcc& acc, int32_t* boxes, size_t boxes_stride, int max_boxes) {
+    if (acc.key >= 0 && acc.area > 0 && (threadIdx.x & 31) == 0) {
+        const int f = acc.key / (max_boxes + 1), l = acc.key - f * (max_boxes + 1);
+        int32_t* bx = boxes + (size_t)f * boxes_stride + (l - 1) * 5;
+        atomicMin(bx + 0, acc.x0); atomicMin(bx + 1, acc.y0); atomicMax(bx + 2, acc.x1); atomicMax(bx + 3, acc.y1);
+        atomicAdd(bx + 4, acc.area);
+    }
+    acc = BoxAcc();
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_relabel_kernel(const uint8_t* __restrict__ mask, const int* parent,
                                                          const int* __restrict__ rank, int w, int npx, CclList L,
-                                                         int* labels_out, int32_t* __restrict__ boxes,
+                                                         int* labels_out, int32_t* boxes,
                                                          size_t boxes_stride, int max_boxes) {
     const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
     const int cnt = *L.count;
+    BoxAcc acc;
     for (int q = gw; q < cnt; q += warps) {
         const int e = L.entries[q];
         const int f = e / L.n_units, u = e - f * L.n_units, ub = u * CCL_UNIT;
@@ -1642,19 +1727,46 @@ __global__ void __launch_bounds__(256) ccl_relabel_kernel(const uint8_t* __restr
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             lab[j] = 0;
-            if (!((R.S.w[j] >> lane) & 1u)) continue;
-            const int t = 32 * j + lane, g = ub + t;
-            const int l = rank[base + parent[base + g]];
-            lab[j] = l;
-            if (boxes && l <= max_boxes) {
+            if ((R.S.w[j] >> lane) & 1u) lab[j] = rank[base + parent[base + ub + 32 * j + lane]];
+        }
+        if (boxes) {
+            // the unit's first run decides which label the warp accumulates
+            const int s0 = first_set_at_or_above(R.S, 0);
+            int l0 = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int v = __shfl_sync(FULL, lab[jj], s0 & 31);
+                if ((s0 >> 5) == jj) l0 = v;
+            }
+            const int key0 = l0 <= max_boxes ? f * (max_boxes + 1) + l0 : -1;
+            if (key0 != acc.key) {
+                box_flush(acc, boxes, boxes_stride, max_boxes);
+                acc.key = key0;
+            }
+            int ax0 = 0x7fffffff, ay0 = 0x7fffffff, ax1 = -1, ay1 = -1, aarea = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!((R.S.w[j] >> lane) & 1u)) continue;
+                const int l = lab[j];
+                if (l > max_boxes) continue;
+                const int t = 32 * j + lane, g = ub + t;
                 const int len = first_set_at_or_above(R.E, t) - t + 1;
                 const int y = g / w, xs = g - y * w, xe = xs + len - 1;
-                int32_t* bx = boxes + (size_t)f * boxes_stride + (l - 1) * 5;
-                if (xs < __ldcg(bx + 0)) atomicMin(bx + 0, xs);
-                if (y < __ldcg(bx + 1)) atomicMin(bx + 1, y);
-                if (xe > __ldcg(bx + 2)) atomicMax(bx + 2, xe);
-                if (y > __ldcg(bx + 3)) atomicMax(bx + 3, y);
-                atomicAdd(bx + 4, len);
+                if (l == l0 && key0 >= 0) {
+                    ax0 = min(ax0, xs); ay0 = min(ay0, y); ax1 = max(ax1, xe); ay1 = max(ay1, y); aarea += len;
+                } else {
+                    int32_t* bx = boxes + (size_t)f * boxes_stride + (l - 1) * 5;
+                    if (xs < __ldcg(bx + 0)) atomicMin(bx + 0, xs);
+                    if (y < __ldcg(bx + 1)) atomicMin(bx + 1, y);
+                    if (xe > __ldcg(bx + 2)) atomicMax(bx + 2, xe);
+                    if (y > __ldcg(bx + 3)) atomicMax(bx + 3, y);
+                    atomicAdd(bx + 4, len);
+                }
+            }
+            if (key0 >= 0) {
+                acc.x0 = min(acc.x0, __reduce_min_sync(FULL, ax0)); acc.y0 = min(acc.y0, __reduce_min_sync(FULL, ay0));
+                acc.x1 = max(acc.x1, __reduce_max_sync(FULL, ax1)); acc.y1 = max(acc.y1, __reduce_max_sync(FULL, ay1));
+                acc.area += __reduce_add_sync(FULL, aarea);
             }
         }
         if (labels_out) {
@@ -1667,13 +1779,14 @@ __global__ void __launch_bounds__(256) ccl_relabel_kernel(const uint8_t* __restr
                 int l = 0;
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    const int v = __shfl_sync(0xffffffffu, lab[jj], s & 31);
+                    const int v = __shfl_sync(FULL, lab[jj], s & 31);
                     if ((s >> 5) == jj) l = v;
                 }
                 if (on) labels_out[base + ub + t] = l;
             }
         }
     }
+    if (boxes) box_flush(acc, boxes, boxes_stride, max_boxes);
 }
 
 __global__ void ccl_boxes_final_kernel(int32_t* boxes, size_t boxes_stride, int max_boxes, int n) {

@@ -235,6 +235,88 @@ __device__ __forceinline__ void blur3_words(uint32_t a, uint32_t b, uint32_t c, 
     hv[3] = 0.25f * v6 + 0.5f * v7 + 0.25f * v8;
 }
 
+// The two separable passes of the expansion on a staged tile: raw[(PE_TY + 2 PE_H) x PE_RW] (row PE_H - n is the
+// first staged row) -> t[3] (vertical sums) -> R.  Called by every polyexp kernel after its staging barrier.
+template <int N_>
+__device__ __forceinline__ void polyexp_passes(const float* __restrict__ raw, float (*t)[PE_TY * PE_RW], const PolyConst& pc,
+                                               int n, int tid, int x0, int y0, int h, int pitch, float* __restrict__ R,
+                                               size_t plane) {
+    // vertical pass
+    for (int task = tid; task < PE_RW * (PE_TY / 4); task += 256) {
+        int c = task % PE_RW, g4 = task / PE_RW;
+        float v[4 + 2 * PE_H];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * PE_H; ++j)
+            v[j] = (j >= PE_H - n && j < 4 + PE_H + n) ? raw[(g4 * 4 + j) * PE_RW + c] : 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float a0 = v[PE_H + o] * pc.g[0], a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= kMaxPolyN; ++k) {
+                if (k <= n) {
+                    float up = v[PE_H + o - k], dn = v[PE_H + o + k];
+                    float sum = up + dn;
+                    a0 += pc.g[k] * sum;
+                    a1 += pc.xg[k] * (dn - up);
+                    a2 += pc.xxg[k] * sum;
+                }
+            }
+            int r = g4 * 4 + o;
+            t[0][r * PE_RW + c] = a0;
+            t[1][r * PE_RW + c] = a1;
+            t[2][r * PE_RW + c] = a2;
+        }
+    }
+    __syncthreads();
+
+    // horizontal pass
+    for (int task = tid; task < PE_TY * (PE_TX / 4); task += 256) {
+        int q = task % (PE_TX / 4), r = task / (PE_TX / 4);
+        int y = y0 + r;
+        if (y >= h) continue;
+        float u0[4 + 2 * PE_H], u1[4 + 2 * PE_H], u2[4 + 2 * PE_H];
+        const float4* p0 = reinterpret_cast<const float4*>(&t[0][r * PE_RW + 4 * q]);
+        const float4* p1 = reinterpret_cast<const float4*>(&t[1][r * PE_RW + 4 * q]);
+        const float4* p2 = reinterpret_cast<const float4*>(&t[2][r * PE_RW + 4 * q]);
+#pragma unroll
+        for (int j = 0; j < (4 + 2 * PE_H) / 4; ++j) {
+            float4 a = p0[j], b = p1[j], c = p2[j];
+            u0[4 * j] = a.x; u0[4 * j + 1] = a.y; u0[4 * j + 2] = a.z; u0[4 * j + 3] = a.w;
+            u1[4 * j] = b.x; u1[4 * j + 1] = b.y; u1[4 * j + 2] = b.z; u1[4 * j + 3] = b.w;
+            u2[4 * j] = c.x; u2[4 * j + 1] = c.y; u2[4 * j + 2] = c.z; u2[4 * j + 3] = c.w;
+        }
+        float o0[4], o1[4], o2[4], o3[4], o4[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int c = PE_H + o;
+            float b1 = u0[c] * pc.g[0], b2 = 0.f, b3 = u1[c] * pc.g[0], b4 = 0.f, b5 = u2[c] * pc.g[0], b6 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= kMaxPolyN; ++k) {
+                if (k <= n) {
+                    float tg = u0[c + k] + u0[c - k];
+                    b1 += tg * pc.g[k];
+                    b4 += tg * pc.xxg[k];
+                    b2 += (u0[c + k] - u0[c - k]) * pc.xg[k];
+                    b3 += (u1[c + k] + u1[c - k]) * pc.g[k];
+                    b6 += (u1[c + k] - u1[c - k]) * pc.xg[k];
+                    b5 += (u2[c + k] + u2[c - k]) * pc.g[k];
+                }
+            }
+            o0[o] = b3 * pc.ig11;
+            o1[o] = b2 * pc.ig11;
+            o2[o] = b1 * pc.ig03 + b5 * pc.ig33;
+            o3[o] = b1 * pc.ig03 + b4 * pc.ig33;
+            o4[o] = b6 * pc.ig55;
+        }
+        float* dst = R + (size_t)y * pitch + x0 + 4 * q;
+        *reinterpret_cast<float4*>(dst) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        *reinterpret_cast<float4*>(dst + plane) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+        *reinterpret_cast<float4*>(dst + 2 * plane) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+        *reinterpret_cast<float4*>(dst + 3 * plane) = make_float4(o3[0], o3[1], o3[2], o3[3]);
+        *reinterpret_cast<float4*>(dst + 4 * plane) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+}
+
 // N_ > 0: poly_n known at compile time (5, 7 and 8 are instantiated: OpenCV's sample value, its other GPU value
 // and the reference's) so the tap loops carry no predicates; N_ == 0: any poly_n <= 8 at run time.
 template <bool U8, int N_>
@@ -340,81 +422,7 @@ __global__ void __launch_bounds__(256, 4) polyexp_kernel(const void* __restrict_
         }
     }
     __syncthreads();
-
-    // vertical pass
-    for (int task = tid; task < PE_RW * (PE_TY / 4); task += 256) {
-        int c = task % PE_RW, g4 = task / PE_RW;
-        float v[4 + 2 * PE_H];
-#pragma unroll
-        for (int j = 0; j < 4 + 2 * PE_H; ++j)
-            v[j] = (j >= PE_H - n && j < 4 + PE_H + n) ? raw[(g4 * 4 + j) * PE_RW + c] : 0.f;
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            float a0 = v[PE_H + o] * pc.g[0], a1 = 0.f, a2 = 0.f;
-#pragma unroll
-            for (int k = 1; k <= kMaxPolyN; ++k) {
-                if (k <= n) {
-                    float up = v[PE_H + o - k], dn = v[PE_H + o + k];
-                    float sum = up + dn;
-                    a0 += pc.g[k] * sum;
-                    a1 += pc.xg[k] * (dn - up);
-                    a2 += pc.xxg[k] * sum;
-                }
-            }
-            int r = g4 * 4 + o;
-            t[0][r * PE_RW + c] = a0;
-            t[1][r * PE_RW + c] = a1;
-            t[2][r * PE_RW + c] = a2;
-        }
-    }
-    __syncthreads();
-
-    // horizontal pass
-    for (int task = tid; task < PE_TY * (PE_TX / 4); task += 256) {
-        int q = task % (PE_TX / 4), r = task / (PE_TX / 4);
-        int y = y0 + r;
-        if (y >= h) continue;
-        float u0[4 + 2 * PE_H], u1[4 + 2 * PE_H], u2[4 + 2 * PE_H];
-        const float4* p0 = reinterpret_cast<const float4*>(&t[0][r * PE_RW + 4 * q]);
-        const float4* p1 = reinterpret_cast<const float4*>(&t[1][r * PE_RW + 4 * q]);
-        const float4* p2 = reinterpret_cast<const float4*>(&t[2][r * PE_RW + 4 * q]);
-#pragma unroll
-        for (int j = 0; j < (4 + 2 * PE_H) / 4; ++j) {
-            float4 a = p0[j], b = p1[j], c = p2[j];
-            u0[4 * j] = a.x; u0[4 * j + 1] = a.y; u0[4 * j + 2] = a.z; u0[4 * j + 3] = a.w;
-            u1[4 * j] = b.x; u1[4 * j + 1] = b.y; u1[4 * j + 2] = b.z; u1[4 * j + 3] = b.w;
-            u2[4 * j] = c.x; u2[4 * j + 1] = c.y; u2[4 * j + 2] = c.z; u2[4 * j + 3] = c.w;
-        }
-        float o0[4], o1[4], o2[4], o3[4], o4[4];
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            const int c = PE_H + o;
-            float b1 = u0[c] * pc.g[0], b2 = 0.f, b3 = u1[c] * pc.g[0], b4 = 0.f, b5 = u2[c] * pc.g[0], b6 = 0.f;
-#pragma unroll
-            for (int k = 1; k <= kMaxPolyN; ++k) {
-                if (k <= n) {
-                    float tg = u0[c + k] + u0[c - k];
-                    b1 += tg * pc.g[k];
-                    b4 += tg * pc.xxg[k];
-                    b2 += (u0[c + k] - u0[c - k]) * pc.xg[k];
-                    b3 += (u1[c + k] + u1[c - k]) * pc.g[k];
-                    b6 += (u1[c + k] - u1[c - k]) * pc.xg[k];
-                    b5 += (u2[c + k] + u2[c - k]) * pc.g[k];
-                }
-            }
-            o0[o] = b3 * pc.ig11;
-            o1[o] = b2 * pc.ig11;
-            o2[o] = b1 * pc.ig03 + b5 * pc.ig33;
-            o3[o] = b1 * pc.ig03 + b4 * pc.ig33;
-            o4[o] = b6 * pc.ig55;
-        }
-        float* dst = R + (size_t)blockIdx.z * 5 * plane + (size_t)y * pitch + x0 + 4 * q;
-        *reinterpret_cast<float4*>(dst) = make_float4(o0[0], o0[1], o0[2], o0[3]);
-        *reinterpret_cast<float4*>(dst + plane) = make_float4(o1[0], o1[1], o1[2], o1[3]);
-        *reinterpret_cast<float4*>(dst + 2 * plane) = make_float4(o2[0], o2[1], o2[2], o2[3]);
-        *reinterpret_cast<float4*>(dst + 3 * plane) = make_float4(o3[0], o3[1], o3[2], o3[3]);
-        *reinterpret_cast<float4*>(dst + 4 * plane) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-    }
+    polyexp_passes<N_>(raw, t, pc, n, tid, x0, y0, h, pitch, R + (size_t)blockIdx.z * 5 * plane, plane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -800,6 +808,99 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
                  ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Polynomial expansion with the tile staged by TMA (tuning.polyexp_tma, default): ONE cp.async.bulk.tensor brings the
+// tile + halo into shared memory — the u8 frame box {96 bytes, 34 + 2n rows} for level 0, the float image box
+// {80, 32 + 2n} for the coarser levels — instead of every thread issuing (and waiting for) its own global loads.
+// Level 0 then applies the 3x3 [1/4 1/2 1/4] blur from shared-memory words; out-of-image cells arrive as zeros and are
+// fixed up for border tiles only: the one-pixel REFLECT_101 ring the blur reads, then (on the blurred floats) the
+// replicated rows / columns the expansion reads.  Arithmetic and its order are those of polyexp_kernel: bit-identical R.
+// ------------------------------------------------------------------------------------------------
+constexpr int PE_BW = 96;   // bytes per staged u8 row: x0 - 16 .. x0 + 79 (16-byte aligned box origin)
+
+template <bool U8, int N_>
+__global__ void __launch_bounds__(256, 4) polyexp_tma_kernel(const __grid_constant__ CUtensorMap tmap, int w, int h,
+                                                         int pitch, PolyConst pc, float* __restrict__ R, size_t plane) {
+    __shared__ __align__(128) float raw[(PE_TY + 2 * PE_H) * PE_RW];
+    __shared__ __align__(128) float t[3][PE_TY * PE_RW];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * PE_TX, y0 = blockIdx.y * PE_TY;
+    const int n = N_ > 0 ? N_ : pc.n;
+    const int rows = PE_TY + 2 * n;
+    // level 0: the byte box is parked in the (not yet used) vertical-sum area: (rows + 2) x 96 bytes <= 50 x 96
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(&t[0][0]);
+    float* raw0 = raw;                                      // first staged row (TMA destination: 128-byte aligned)
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        if (U8) {
+            mbar_expect_tx(&bar, (uint32_t)((rows + 2) * PE_BW));
+            tma_load_3d(bytes, &tmap, x0 - 16, y0 - n - 1, blockIdx.z, &bar);
+        } else {
+            mbar_expect_tx(&bar, (uint32_t)(rows * PE_RW * sizeof(float)));
+            tma_load_3d(raw0, &tmap, x0 - PE_H, y0 - n, blockIdx.z, &bar);
+        }
+    }
+    const bool interior = (x0 - PE_H - 1 >= 0) && (x0 + PE_TX + PE_H + 1 <= w) && (y0 - n - 1 >= 0) &&
+                          (y0 + PE_TY + n + 1 <= h);
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    if (U8) {
+        if (!interior) {
+            // REFLECT_101 ring of the source: column -1 <- 1, column w <- w - 2, then row -1 <- 1, row h <- h - 2
+            // (cells further out are never read by the blur of an in-image pixel)
+            for (int rr = tid; rr < rows + 2; rr += 256) {
+                uint8_t* row = bytes + rr * PE_BW;
+                const int bl = -1 - (x0 - 16), br = w - (x0 - 16);          // box columns of x = -1 and x = w
+                if (bl >= 0 && bl + 2 < PE_BW) row[bl] = row[bl + 2];
+                if (br >= 2 && br < PE_BW) row[br] = row[br - 2];
+            }
+            __syncthreads();
+            for (int cc = tid; cc < PE_BW; cc += 256) {
+                const int bt = -1 - (y0 - n - 1), bb = h - (y0 - n - 1);    // box rows of y = -1 and y = h
+                if (bt >= 0 && bt + 2 < rows + 2) bytes[bt * PE_BW + cc] = bytes[(bt + 2) * PE_BW + cc];
+                if (bb >= 2 && bb < rows + 2) bytes[bb * PE_BW + cc] = bytes[(bb - 2) * PE_BW + cc];
+            }
+            __syncthreads();
+        }
+        // blur: 20 groups of 4 cells x 12 row segments; staged row rr, cell cc = box row rr + 1, box byte cc + 8
+        const int g = tid % 20, seg = tid / 20;
+        const int rps = (rows + 11) / 12;
+        const int r0 = seg * rps, r1 = min(rows, r0 + rps);
+        if (seg < 12 && r0 < r1) {
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(bytes + r0 * PE_BW + 4 * g + 4);   // word left of the cells
+            float hp[4], hc[4], hn[4];
+            blur3_words(wp[0], wp[1], wp[2], hp);
+            blur3_words(wp[PE_BW / 4], wp[PE_BW / 4 + 1], wp[PE_BW / 4 + 2], hc);
+            for (int i = 0; i < r1 - r0; ++i) {
+                const uint32_t* q = wp + (i + 2) * (PE_BW / 4);
+                blur3_words(q[0], q[1], q[2], hn);
+                float4 v;
+                v.x = 0.25f * hp[0] + 0.5f * hc[0] + 0.25f * hn[0];
+                v.y = 0.25f * hp[1] + 0.5f * hc[1] + 0.25f * hn[1];
+                v.z = 0.25f * hp[2] + 0.5f * hc[2] + 0.25f * hn[2];
+                v.w = 0.25f * hp[3] + 0.5f * hc[3] + 0.25f * hn[3];
+                *reinterpret_cast<float4*>(&raw0[(r0 + i) * PE_RW + 4 * g]) = v;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { hp[k] = hc[k]; hc[k] = hn[k]; }
+            }
+        }
+        __syncthreads();          // the byte box (in t) is dead from here on; raw is complete for in-image cells
+    }
+    if (!interior) {
+        // the expansion reads replicated rows / columns: out-of-image cells take the clamped cell's value
+        for (int idx = tid; idx < rows * PE_RW; idx += 256) {
+            const int rr = idx / PE_RW, cc = idx - rr * PE_RW;
+            const int gy = y0 - n + rr, gx = x0 - PE_H + cc;
+            const int cy = clampi(gy, 0, h - 1), cx = clampi(gx, 0, w - 1);
+            if (cy != gy || cx != gx) raw0[idx] = raw0[(cy - (y0 - n)) * PE_RW + (cx - (x0 - PE_H))];
+        }
+        __syncthreads();
+    }
+    // the passes address the tile with its first staged row at row PE_H - n
+    polyexp_passes<N_>(raw0 - (PE_H - n) * PE_RW, t, pc, n, tid, x0, y0, h, pitch, R + (size_t)blockIdx.z * 5 * plane, plane);
 }
 
 // UpdateMatrices with 32-bit index arithmetic; `edge` is tile-uniform (tile within 5 px of a border).
@@ -1361,10 +1462,23 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         ProfScope ps(&H->prof, MAVD_PROF_POLYEXP, st);
         dim3 g(ceil_div(L.w, PE_TX), ceil_div(L.h, PE_TY), n_frames);
         const int aligned = ((reinterpret_cast<uintptr_t>(d_frames) & 3) == 0 && (W & 3) == 0) ? 1 : 0;
+        // TMA-staged tiles: level 0 needs a descriptor of the caller's frames (16-byte aligned rows), built per call
+        CUtensorMap tmap_u8;
+        bool use_tma = H->tune.polyexp_tma != 0;
+        if (use_tma && li == 0)
+            use_tma = (W % 16 == 0) && encode_tensor_map_3d(&tmap_u8, true, d_frames, (uint64_t)W, (uint64_t)Hh,
+                                                            (uint64_t)n_frames, (uint64_t)W, (uint64_t)W * Hh, PE_BW,
+                                                            (uint32_t)(PE_TY + 2 * H->poly.n + 2), 1u);
+        else if (use_tma)
+            use_tma = L.has_tmap_img;
 #define PE_LAUNCH(N)                                                                                                   \
         do {                                                                                                           \
-            if (li == 0) polyexp_kernel<true, N><<<g, 256, 0, st>>>(d_frames, frame_bytes, L.w, L.h, L.pitch, aligned,  \
-                                                                    H->poly, L.R, L.plane);                            \
+            if (li == 0 && use_tma) polyexp_tma_kernel<true, N><<<g, 256, 0, st>>>(tmap_u8, L.w, L.h, L.pitch, H->poly, \
+                                                                                   L.R, L.plane);                       \
+            else if (li == 0) polyexp_kernel<true, N><<<g, 256, 0, st>>>(d_frames, frame_bytes, L.w, L.h, L.pitch,      \
+                                                                         aligned, H->poly, L.R, L.plane);              \
+            else if (use_tma) polyexp_tma_kernel<false, N><<<g, 256, 0, st>>>(L.tmapImg, L.w, L.h, L.pitch, H->poly,    \
+                                                                              L.R, L.plane);                           \
             else polyexp_kernel<false, N><<<g, 256, 0, st>>>(L.img, L.plane, L.w, L.h, L.pitch, 0, H->poly, L.R,       \
                                                              L.plane);                                                 \
         } while (0)

@@ -430,3 +430,27 @@ def test_ccl_dense_and_structured_masks(size):
             k = min(32, stats.shape[0])
             assert np.array_equal(boxes[i, :k], stats[:k]), i
     eng.close()
+
+
+@pytest.mark.parametrize('size', [(1920, 1080), (752, 480), (333, 257), (64, 48), (1024, 96)])
+@pytest.mark.parametrize('poly_n', [5, 8, 3])
+def test_tma_staged_polyexp_is_bit_identical(size, poly_n):
+    """tuning.polyexp_tma: the expansion tile staged by one TMA box (u8 frame box + in-kernel 3x3 blur at level 0, float
+    image box at the coarser levels) against the per-thread-load kernel: every R plane of every level bit-equal —
+    interior tiles, all four borders (REFLECT_101 ring of the blur, replicated halo of the expansion), widths that
+    are not multiples of the tile (and, for 333, not of 16: level 0 then falls back to the load kernel)."""
+    import torch
+    from mav_detection_b200 import engine, synth
+    W, H = size
+    s = synth.make_sequence(W, H, 2, seq=23)
+    p = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=1, poly_n=poly_n, poly_sigma=1.2, flags=0)
+    eng = engine.Engine(W, H, p, max_pairs=1)
+    frames = torch.from_numpy(s.frames).cuda()
+    got = {}
+    for tma in (1, 0):
+        eng.set_tuning(polyexp_tma=tma)
+        flow = eng.farneback(frames).cpu().numpy()
+        got[tma] = [eng.tap('R', lvl, j).cpu().numpy() for lvl in range(len(eng.levels)) for j in (0, 1)] + [flow]
+    for a, b in zip(got[1], got[0]):
+        assert np.array_equal(a, b), float(np.abs(a - b).max())
+    eng.close()
