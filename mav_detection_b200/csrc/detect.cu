@@ -1433,33 +1433,11 @@ __device__ __forceinline__ UnitAbove unit_above(const uint8_t* __restrict__ m, i
     return A;
 }
 
-// First contact of the run [s, e] (unit-local bit positions, same row) with the row above, as a column in
-// [s - 1, e + 1] clipped to the row: -1 .. 128, or 129 when there is none.
-__device__ __forceinline__ int first_upper_contact(const UnitRuns& R, const UnitAbove& A, int s, int e, int w) {
-    if (!bit_of(R.RS, s) && ((s == 0) ? A.um1 : (unsigned)bit_of(A.U, s - 1))) return s - 1;
-    // columns s .. min(e + 1, 127) of U
-    const int hi = min(e + 1, CCL_UNIT - 1);
-    const bool e1_in_row = (e + 1 < CCL_UNIT) ? !bit_of(R.RS, e + 1) : ((R.x0 + CCL_UNIT) % w != 0);
-    int j = s >> 5;
-    unsigned wv = A.U.w[j] & (0xffffffffu << (s & 31));
-    while (true) {
-        if (wv) {
-            const int c = 32 * j + __ffs(wv) - 1;
-            if (c <= e || (c == e + 1 && c <= hi && e1_in_row)) return c;
-            break;
-        }
-        if (++j > (hi >> 5)) break;
-        wv = A.U.w[j];
-    }
-    if (e == CCL_UNIT - 1 && e1_in_row && A.u128) return CCL_UNIT;
-    return CCL_UNIT + 1;
-}
-
-// init: every set pixel points at the start of its run inside the unit; the run START itself is pre-linked without
-// an atomic: to the previous pixel when the run continues one that ends the previous unit, else to the first pixel
-// of the row above that touches the run (both have smaller indices and belong to the same component, so the forest
-// is valid).  Most runs have no further contact: the merge pass then has nothing to do for them — in particular a
-// fully set frame needs no union at all.
+// init: every set pixel points at the start of its run inside the unit.  A run that continues one ending the previous
+// unit (same row) is linked to it right here, without an atomic: its start points at the previous pixel (smaller
+// index, same component).  These chains are at most two hops per unit of a row, and they remove half of the unions of
+// a densely set frame; contacts with the row above stay with the merge pass (linking them here as well was measured:
+// it builds image-high chains that the later passes pay for).
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w,
                                                       int npx, CclList L) {
@@ -1473,34 +1451,24 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict
         R.M = ccl_load_bits<VEC>(m, ub, npx);
         R.RS = row_starts(ub, w, R.x0);
         unit_runs(R);
-        const UnitAbove A = unit_above<VEC>(m, ub, w, npx, R.RS);
+        const bool left_cont = (R.M.w[0] & 1u) && !(R.RS.w[0] & 1u) && ub >= 1 && m[ub - 1] != 0;   // warp-uniform
         int* par = parent + (size_t)f * npx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int t = 32 * j + lane;
             if (!((R.M.w[j] >> lane) & 1u)) continue;
-            int target;
-            if ((R.S.w[j] >> lane) & 1u) {
-                if (t == 0 && A.prevpix && !(R.RS.w[0] & 1u)) {
-                    target = ub - 1;
-                } else {
-                    const int c = first_upper_contact(R, A, t, first_set_at_or_above(R.E, t), w);
-                    target = c <= CCL_UNIT ? ub - w + c : ub + t;
-                }
-            } else {
-                target = ub + last_set_at_or_below(R.S, t);
-            }
-            par[ub + t] = target;
+            const int s = last_set_at_or_below(R.S, t);
+            par[ub + t] = (t == 0 && left_cont) ? ub - 1 : ub + s;
         }
     }
 }
 
-// merge: one union per contact between a run of this unit and an upper run that init has not linked already.  With
-// [s, e] a run of this row, its contacts with the row above are: the upper run that covers column s - 1 (if any), and
-// every upper run that STARTS at a column t in [s, e + 1].  The first of them in column order is the one init linked;
-// a run that continues from the previous unit has that unit's contacts through the previous pixel, so its contact at
-// s - 1 is implied.  A contact at column t is handled by the lane that owns t (with pixel t if it is set, else with
-// pixel t - 1, whose up-right neighbour it is); one at column 128 by pixel 127's owner.
+// merge: one union per contact between a run [s, e] of this unit and a run of the row above:
+//   (B)  the upper run covers column s - 1 (it started at or before s - 1): one union at s — unless the run continues
+//        from the previous unit, whose last pixel has that same upper run above it and has taken care of it
+//   (A)  an upper run STARTS at a column t in [s, e + 1]: one union, by the lane that owns t (with pixel t if it is
+//        set, else with pixel t - 1, whose up-right neighbour it is); a start at column 128 by pixel 127's owner
+// A fully set frame makes one union per image row.
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w,
                                                        int npx, CclList L) {
@@ -1516,29 +1484,20 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restric
         R.RS = row_starts(ub, w, R.x0);
         unit_runs(R);
         const UnitAbove A = unit_above<VEC>(m, ub, w, npx, R.RS);
-        // warp-uniform early out: no upper-run start anywhere above the unit (nor right after it) -> nothing to union
-        if (!(A.US.w[0] | A.US.w[1] | A.US.w[2] | A.US.w[3] | A.u128)) continue;
-        const bool left_cont = A.prevpix && !(R.RS.w[0] & 1u) && (R.M.w[0] & 1u);    // the run at t = 0 continues a run
+        if (!(A.U.w[0] | A.U.w[1] | A.U.w[2] | A.U.w[3] | A.um1 | A.u128)) continue;    // nothing above: warp-uniform
+        const bool left_cont = A.prevpix && !(R.RS.w[0] & 1u) && (R.M.w[0] & 1u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int t = 32 * j + lane, g = ub + t;
             const bool mt = (R.M.w[j] >> lane) & 1u, rs = (R.RS.w[j] >> lane) & 1u;
-            int tc = -1, tu = 0, col = 0;          // pixel of this row, pixel of the row above, contact column
-            if ((A.US.w[j] >> lane) & 1u) {
-                if (mt) { tc = t; tu = g - w; col = t; }
-                else if (t >= 1 && !rs && bit_of(R.M, t - 1)) { tc = t - 1; tu = g - w; col = t; }
+            if (mt && ((R.S.w[j] >> lane) & 1u) && !rs && !(t == 0 && left_cont) && ((A.Uprev.w[j] >> lane) & 1u))
+                uf_union(par, g, g - w - 1);                                                      // (B)
+            if ((A.US.w[j] >> lane) & 1u) {                                                       // (A)
+                if (mt) uf_union(par, g, g - w);
+                else if (t >= 1 && !rs && bit_of(R.M, t - 1)) uf_union(par, g - 1, g - w);
             }
-            if (t == CCL_UNIT - 1 && mt && A.u128 && !((A.U.w[3] >> 31) & 1u) && (R.x0 + CCL_UNIT) % w != 0) {
-                // an upper run starts right after the 128 pixels above: up-right neighbour of pixel 127
-                const int s = last_set_at_or_below(R.S, t);
-                if ((s == 0 && left_cont) || first_upper_contact(R, A, s, t, w) != CCL_UNIT) uf_union(par, g, g - w + 1);
-            }
-            if (tc >= 0) {
-                const int s = last_set_at_or_below(R.S, tc);
-                const bool linked_by_init = !(s == 0 && left_cont) &&
-                                            first_upper_contact(R, A, s, first_set_at_or_above(R.E, s), w) == col;
-                if (!linked_by_init) uf_union(par, ub + tc, tu);
-            }
+            if (t == CCL_UNIT - 1 && mt && A.u128 && !((A.U.w[3] >> 31) & 1u) && (R.x0 + CCL_UNIT) % w != 0)
+                uf_union(par, g, g - w + 1);
         }
     }
 }

@@ -1,7 +1,7 @@
 """CPU: the contact enumeration of the run-based labelling kernels (csrc/detect.cu: ccl_init_kernel / ccl_merge_kernel),
 restated with Python integers as 128-bit unit masks and a plain union-find, against the labelling oracle.  It checks the
-LOGIC the CUDA passes implement — which contacts init links without an atomic, which ones merge still has to union, and
-that together they connect exactly the 8-connected components — on widths that are / are not multiples of the
+LOGIC the CUDA passes implement — the left continuation init links without an atomic, the contacts with the row above
+merge unions, and that together they connect exactly the 8-connected components — on widths that are / are not multiples of the
 128-pixel unit, including units that straddle rows and rows shorter than a unit."""
 import numpy as np
 import pytest
@@ -46,20 +46,6 @@ class Unit:
         self.Uprev = ((self.U << 1) | self.um1) & full
         self.US = self.U & (~self.Uprev | self.RS) & full
 
-    def first_upper_contact(self, s, e):
-        if not _bit(self.RS, s) and (self.um1 if s == 0 else _bit(self.U, s - 1)):
-            return s - 1
-        e1_in_row = (not _bit(self.RS, e + 1)) if e + 1 < UNIT else ((self.x0 + UNIT) % self.w != 0)
-        above = self.U >> s
-        if above:
-            c = s + (above & -above).bit_length() - 1
-            if c <= e or (c == e + 1 and c <= UNIT - 1 and e1_in_row):
-                return c
-            return UNIT + 1
-        if e == UNIT - 1 and e1_in_row and self.u128:
-            return UNIT
-        return UNIT + 1
-
 
 def _find(par, i):
     while par[i] != i:
@@ -83,44 +69,31 @@ def emulate(mask):
     units = [Unit(flat, ub, w) for ub in range(0, npx, UNIT)]
     units = [u for u in units if u.M]
     for u in units:                                              # ccl_init_kernel
+        left_cont = bool(_bit(u.M, 0) and not _bit(u.RS, 0) and u.prevpix)
         for t in range(UNIT):
-            if not _bit(u.M, t):
-                continue
-            if _bit(u.S, t):
-                if t == 0 and u.prevpix and not _bit(u.RS, 0):
-                    target = u.ub - 1
-                else:
-                    c = u.first_upper_contact(t, _first_set_at_or_above(u.E, t))
-                    target = u.ub - w + c if c <= UNIT else u.ub + t
-            else:
-                target = u.ub + _last_set_at_or_below(u.S, t)
-            assert target <= u.ub + t and flat[target]
-            par[u.ub + t] = target
+            if _bit(u.M, t):
+                par[u.ub + t] = u.ub - 1 if (t == 0 and left_cont) else u.ub + _last_set_at_or_below(u.S, t)
     unions = 0
     for u in units:                                              # ccl_merge_kernel
-        if not (u.US or u.u128):
+        if not (u.U or u.um1 or u.u128):
             continue
         left_cont = bool(u.prevpix and not _bit(u.RS, 0) and _bit(u.M, 0))
         for t in range(UNIT):
             g = u.ub + t
             mt, rs = _bit(u.M, t), _bit(u.RS, t)
-            tc = -1
-            if _bit(u.US, t):
+            if mt and _bit(u.S, t) and not rs and not (t == 0 and left_cont) and _bit(u.Uprev, t):
+                _union(par, g, g - w - 1)                                           # (B)
+                unions += 1
+            if _bit(u.US, t):                                                        # (A)
                 if mt:
-                    tc, tu, col = t, g - w, t
+                    _union(par, g, g - w)
+                    unions += 1
                 elif t >= 1 and not rs and _bit(u.M, t - 1):
-                    tc, tu, col = t - 1, g - w, t
+                    _union(par, g - 1, g - w)
+                    unions += 1
             if t == UNIT - 1 and mt and u.u128 and not _bit(u.U, UNIT - 1) and (u.x0 + UNIT) % w != 0:
-                s = _last_set_at_or_below(u.S, t)
-                if (s == 0 and left_cont) or u.first_upper_contact(s, t) != UNIT:
-                    _union(par, g, g - w + 1)
-                    unions += 1
-            if tc >= 0:
-                s = _last_set_at_or_below(u.S, tc)
-                linked = not (s == 0 and left_cont) and u.first_upper_contact(s, _first_set_at_or_above(u.E, s)) == col
-                if not linked:
-                    _union(par, u.ub + tc, tu)
-                    unions += 1
+                _union(par, g, g - w + 1)
+                unions += 1
     labels = np.zeros(npx, np.int32)
     order = {}
     for i in range(npx):
@@ -144,4 +117,4 @@ def test_run_contacts_connect_exactly_the_components(size):
         ref, _ = ccl_np.label(m)
         assert np.array_equal(got, ref), (size, i)
         if i == 0:
-            assert unions == 0          # a fully set frame is linked by init alone
+            assert unions == h - 1      # a fully set frame: init links the rows, merge makes one union per row
