@@ -108,8 +108,10 @@ typedef struct mavd_tuning {
     int32_t pyr_staged;   /* pyramid: horizontal pass of the coarse levels through shared memory (default 1) */
     int32_t use_graph;    /* replay the per-batch launch sequence from a CUDA graph keyed by (n_pairs, pair_stride,
                              outputs requested) instead of launching kernel by kernel (default 1) */
-    int32_t polyexp_tma;  /* level-0 expansion: u8 tile staged by one TMA box (default 1) */
-    int32_t reserved[5];
+    int32_t polyexp_tma;  /* polynomial expansion: tile staged by one TMA box (default 1) */
+    int32_t iter_small_tiles; /* fused iteration: 64 x 16 tiles for launches too small to fill the GPU with 64 x 32
+                                 ones (single pairs, coarse levels; default 1) */
+    int32_t reserved[4];
 } mavd_tuning;
 
 /* Optional per-frame inputs of the detection stages.  All pointers are DEVICE pointers for the d_ entry points and

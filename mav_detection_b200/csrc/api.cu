@@ -381,6 +381,10 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
                          make_plane_tensor_map(&L.tmapM[1], L.M[1], L.pitch, L.h, B * 5, L.plane, 32 + 2 * m, 5) &&
                          make_plane_tensor_map(&L.tmapR, L.R, L.pitch, L.h, F * 5, L.plane, 48, 10) &&
                          make_plane_tensor_map(&L.tmapRbox, L.R, L.pitch, L.h, F * 5, L.plane, 32 + 2 * m, 5);
+        if (L.has_tmap)
+            L.has_tmap16 = make_plane_tensor_map(&L.tmapM16[0], L.M[0], L.pitch, L.h, B * 5, L.plane, 16 + 2 * m, 5) &&
+                           make_plane_tensor_map(&L.tmapM16[1], L.M[1], L.pitch, L.h, B * 5, L.plane, 16 + 2 * m, 5) &&
+                           make_plane_tensor_map(&L.tmapRbox16, L.R, L.pitch, L.h, F * 5, L.plane, 16 + 2 * m, 5);
     }
     for (int li = 0; li + 1 < H->n_levels; ++li) {
         Level& L = H->lv[li];
@@ -494,6 +498,7 @@ void mavd_default_tuning(mavd_tuning* t) {
     t->pyr_staged = 1;
     t->use_graph = 1;
     t->polyexp_tma = 1;
+    t->iter_small_tiles = 1;
 }
 
 int mavd_set_tuning(mavd_handle h, const mavd_tuning* t) {

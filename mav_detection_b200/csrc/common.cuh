@@ -111,6 +111,9 @@ struct Level {
     CUtensorMap tmapR;      // TMA descriptor of R: dims {pitch, h, frames*5}, box {80, 48, 10} (L2 prefetch only)
     CUtensorMap tmapRbox;   // TMA descriptor of R with the M box geometry {80, 32+2m, 5}: R1 staged in shared memory
     bool has_tmap = false;
+    CUtensorMap tmapM16[2]; // the same with 64 x 16 tiles: box {80, 16+2m, 5}
+    CUtensorMap tmapRbox16;
+    bool has_tmap16 = false;
     CUtensorMap tmapImg;    // TMA descriptor of img: dims {pitch, h, frames}, box {80, 32+2 poly_n, 1} (polynomial expansion)
     bool has_tmap_img = false;
 };

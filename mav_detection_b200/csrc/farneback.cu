@@ -1038,13 +1038,16 @@ __device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, 
 // memory to reach the x-fastest pixel mapping of the update phase (640 -> 256 wavefronts per tile for that hand-over,
 // one more barrier; same hsum_box, same solve expressions: identical results).  (A variant that parked the flow vectors
 // in the dead raw rows below the vertical sums to save that barrier measured 0.5 % slower and was removed.)
-template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0>
+// TY: tile height, 32 by default; 16 for launches whose 32-row tiling would leave SMs idle (single pairs, the coarse
+// levels): twice the CTAs, half the serial work per CTA.  The vertical sums are re-seeded at absolute rows that are
+// multiples of 8 in both tilings and the horizontal groups start at multiples of 4: the results are bit-identical.
+template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0, int TY = IT_TY>
 __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                              const __grid_constant__ CUtensorMap tmapR,
                                                                              const __grid_constant__ CUtensorMap tmapRbox,
                                                                              IterArgs a) {
     constexpr int RW = IT_TX + 16;          // 80 staged columns (halo 8 each side, 16-byte aligned)
-    constexpr int RH = IT_TY + 2 * M_;      // staged rows
+    constexpr int RH = TY + 2 * M_;      // staged rows
     constexpr int CH = RH * RW;             // floats per plane box
     constexpr int NC = IT_TX + 2 * M_;      // columns the vertical pass must produce
     constexpr int NW = NT / 32;             // warps
@@ -1068,7 +1071,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         tile = rem / gsize;
         p = gidx * a.group + (rem - tile * gsize);
     }
-    const int x0 = (tile % a.tiles_x) * IT_TX, y0 = (tile / a.tiles_x) * IT_TY;
+    const int x0 = (tile % a.tiles_x) * IT_TX, y0 = (tile / a.tiles_x) * TY;
     const int w = a.w, h = a.h, pitch = a.pitch;
     const int plane = (int)a.plane;
 
@@ -1082,7 +1085,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         // phase: start their HBM -> L2 transfer now (10 consecutive planes = both frames' expansions)
         if (!LAST) tma_prefetch_3d(&tmapR, x0 - 8, y0 - 8, p * a.pair_stride * 5);
     }
-    const bool interior = (x0 - 8 >= 0) && (x0 + IT_TX + 8 <= w) && (y0 - M_ >= 0) && (y0 + IT_TY + M_ <= h);
+    const bool interior = (x0 - 8 >= 0) && (x0 + IT_TX + 8 <= w) && (y0 - M_ >= 0) && (y0 + TY + M_ <= h);
     __syncthreads();
     mbar_wait(&bar, 0);
 
@@ -1113,9 +1116,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
             // running sums, re-seeded from the window every 8 rows (bounds the float32 drift; the same association
             // as iter_kernel's 8-row segments, so both kernels produce bit-identical sums)
 #pragma unroll
-            for (int y = 0; y < IT_TY; ++y) {
+            for (int y = 0; y < TY; ++y) {
                 q[y * RW] = s;
-                if (y < IT_TY - 1) {
+                if (y < TY - 1) {
                     in[y + 2 * M_ + 1] = q[(y + 2 * M_ + 1) * RW];
                     if (((y + 1) & 7) == 0) {
                         s = 0.f;
@@ -1141,7 +1144,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         const float scale = a.scale;
         const bool vec_ok = (a.flow_pitch & 1) == 0 && (reinterpret_cast<uintptr_t>(fl) & 15) == 0;
 #pragma unroll 1
-        for (int it = 0; it < IT_TY / ROWS_PER_IT; ++it) {
+        for (int it = 0; it < TY / ROWS_PER_IT; ++it) {
             const int r = it * ROWS_PER_IT + rsub;
             float o[5][4];
 #pragma unroll
@@ -1183,9 +1186,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         const int q4 = tid & 15, rsub = tid >> 4;
         constexpr int ROWS_PER_IT = NT / 16;
 #pragma unroll 2
-        for (int it = 0; it < (5 * IT_TY) / ROWS_PER_IT; ++it) {
+        for (int it = 0; it < (5 * TY) / ROWS_PER_IT; ++it) {
             const int task = it * ROWS_PER_IT + rsub;
-            const int c = task / IT_TY, r = task - c * IT_TY;
+            const int c = task / TY, r = task - c * TY;
             float* row = box + c * CH + r * RW + 4 * q4;
             float u[20];
 #pragma unroll
@@ -1210,7 +1213,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
     // IMAD.WIDE.U32 on the 32-bit element offset
     asm volatile("" : "+l"(Mout));
     float2* fl = a.flow ? a.flow + (size_t)p * a.flow_stride : nullptr;
-    const bool edge = (x0 < 5) || (y0 < 5) || (x0 + IT_TX > w - 5) || (y0 + IT_TY > h - 5);
+    const bool edge = (x0 < 5) || (y0 < 5) || (x0 + IT_TX > w - 5) || (y0 + TY > h - 5);
     const float scale = a.scale;
     if (R1S && !LAST) {
         // ---- R1 through shared memory ----
@@ -1219,16 +1222,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         //     into the box; (c) the bilinear gather reads shared memory with immediate offsets (one base address per
         //     pixel, ~30-cycle latency) instead of 20 global loads.  Pixels whose footprint leaves the box (flow
         //     differs from the centre's by more than ~5 px) take the global path; values are identical either way.
-        constexpr int PPT = (IT_TX * IT_TY) / NT;
+        constexpr int PPT = (IT_TX * TY) / NT;
         __shared__ int s_org[2];
         float ffx[PPT], ffy[PPT];
         if (FUSE) {
             // (a0) horizontal sums of the five planes + solve for 4 adjacent pixels per task, in registers
-            static_assert(!FUSE || NT == 256, "FUSE assumes 16 rows per pass");
+            static_assert(!FUSE || (NT == 256 && TY % 16 == 0), "FUSE assumes 16 rows per pass");
             const int q4 = tid & 15, rsub = tid >> 4;
-            float4 gx[2], gy[2];
+            constexpr int NPASS = TY / 16;
+            float4 gx[NPASS], gy[NPASS];
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
+            for (int it = 0; it < NPASS; ++it) {
                 const int r = it * 16 + rsub;
                 float o[5][4];
 #pragma unroll
@@ -1258,10 +1262,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                 __syncthreads();                   // every vertical sum has been consumed: the box is free
                 // (a1) the flow vectors through shared memory: [2][32][64] floats at the start of the box
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
+                for (int it = 0; it < NPASS; ++it) {
                     const int o4 = (it * 16 + rsub) * IT_TX + 4 * q4;
                     *reinterpret_cast<float4*>(box + o4) = gx[it];
-                    *reinterpret_cast<float4*>(box + IT_TX * IT_TY + o4) = gy[it];
+                    *reinterpret_cast<float4*>(box + IT_TX * TY + o4) = gy[it];
                 }
             }
             __syncthreads();
@@ -1272,7 +1276,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
             const int cx = idx & 63, r = idx >> 6;
             if (FUSE) {
                 ffx[j] = box[idx];
-                ffy[j] = box[IT_TX * IT_TY + idx];
+                ffy[j] = box[IT_TX * TY + idx];
             } else {
                 const float* sp = box + r * RW + 8 + cx;
                 const float g11 = sp[0] * scale, g12 = sp[CH] * scale, g22 = sp[2 * CH] * scale, h1 = sp[3 * CH] * scale,
@@ -1281,7 +1285,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                 ffx[j] = (g11 * h2 - g12 * h1) * idet;
                 ffy[j] = (g22 * h1 - g12 * h2) * idet;
             }
-            if (cx == IT_TX / 2 && r == IT_TY / 2) {
+            if (cx == IT_TX / 2 && r == TY / 2) {
                 // box origin: tile origin displaced by the centre pixel's flow, x a multiple of 4
                 const float cfx = fminf(fmaxf(ffx[j], -1.0e5f), 1.0e5f), cfy = fminf(fmaxf(ffy[j], -1.0e5f), 1.0e5f);
                 s_org[0] = ((x0 + (int)floorf(cfx == cfx ? cfx : 0.f)) & ~3) - 8;
@@ -1317,7 +1321,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
         return;
     }
 #pragma unroll 2
-    for (int j = 0; j < (IT_TX * IT_TY) / NT; ++j) {
+    for (int j = 0; j < (IT_TX * TY) / NT; ++j) {
         const int idx = j * NT + tid;
         const int cx = idx & 63, r = idx >> 6;
         const int x = x0 + cx, y = y0 + r;
@@ -1359,24 +1363,33 @@ static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s
     return MAVD_OK;
 }
 
-template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0>
+template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0, int TY = IT_TY>
 static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const CUtensorMap& mapRbox, const IterArgs& a,
                            dim3 grid, cudaStream_t s) {
-    constexpr size_t smem = sizeof(float) * 5 * (IT_TY + 2 * M_) * (IT_TX + 16);
-    MAVD_CUDA((ensure_dynamic_smem<iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE>>(smem)));
-    iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE><<<grid, NT, smem, s>>>(map, mapR, mapRbox, a);
+    constexpr size_t smem = sizeof(float) * 5 * (TY + 2 * M_) * (IT_TX + 16);
+    MAVD_CUDA((ensure_dynamic_smem<iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE, TY>>(smem)));
+    iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE, TY><<<grid, NT, smem, s>>>(map, mapR, mapRbox, a);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
 
 template <bool LAST>
-static int launch_iter_tma_m(int m, const mavd_tuning& tune, const CUtensorMap& map, const CUtensorMap& mapR,
-                             const CUtensorMap& mapRbox, const IterArgs& a, dim3 grid, cudaStream_t s) {
+static int launch_iter_tma_m(int m, const mavd_tuning& tune, bool small_tiles, const CUtensorMap& map,
+                             const CUtensorMap& mapR, const CUtensorMap& mapRbox, const IterArgs& a, dim3 grid,
+                             cudaStream_t s) {
     // R1 staged in shared memory by a second TMA load: 4.36 vs 4.56 ms per 64-pair step (tuning.r1_staged)
     const bool r1s = tune.r1_staged != 0;
     // horizontal sums + solve in registers for the not-last iterations too, flow vectors handed to the update phase
     // through shared memory: iter_full 4.27 vs 4.39 ms per 64-pair step (tuning.iter_fuse)
     const int fuse = tune.iter_fuse;
+    if (small_tiles) {      // 64 x 16 tiles (the caller built `grid` and the descriptors for them): production variants only
+        switch (m) {
+            case 5: return launch_iter_tma<5, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s);
+            case 6: return launch_iter_tma<6, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s);
+            case 7: return launch_iter_tma<7, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s);
+            default: return launch_iter_tma<8, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s);
+        }
+    }
     if (r1s && !LAST && fuse != 0) {
         switch (m) {
             case 5: return launch_iter_tma<5, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
@@ -1542,14 +1555,22 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             a.tiles_x = g.x;
             a.group = pair_group;
             a.last_fused = (last && H->tune.last_fused != 0) ? 1 : 0;
-            const dim3 g1(g.x * g.y * g.z);
+            // launches that cannot give every SM its three 64 x 32 tiles (a single pair, the coarse levels) use 64 x 16
+            // tiles: twice the CTAs, half the serial work per CTA (tuning.iter_small_tiles; production variants only)
+            const bool small_tiles = H->tune.iter_small_tiles != 0 && L.has_tmap16 && H->tune.r1_staged != 0 &&
+                                     H->tune.iter_fuse != 0 && H->tune.last_fused != 0 &&
+                                     (long long)g.x * g.y * g.z <= 3LL * 148;
+            const dim3 g1(small_tiles ? g.x * ceil_div(L.h, 16) * g.z : g.x * g.y * g.z);
             const int RW = IT_TX + 2 * hx, RH = IT_TY + 2 * m;
             const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
             ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), st);
             int rc;
-            if (!gauss && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter)
-                rc = last ? launch_iter_tma_m<true>(m, H->tune, L.tmapM[cur], L.tmapR, L.tmapRbox, a, g1, st)
-                          : launch_iter_tma_m<false>(m, H->tune, L.tmapM[cur], L.tmapR, L.tmapRbox, a, g1, st);
+            if (!gauss && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter) {
+                const CUtensorMap& mM = small_tiles ? L.tmapM16[cur] : L.tmapM[cur];
+                const CUtensorMap& mRb = small_tiles ? L.tmapRbox16 : L.tmapRbox;
+                rc = last ? launch_iter_tma_m<true>(m, H->tune, small_tiles, mM, L.tmapR, mRb, a, g1, st)
+                          : launch_iter_tma_m<false>(m, H->tune, small_tiles, mM, L.tmapR, mRb, a, g1, st);
+            }
             else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, st) : launch_iter<true, false>(a, g, smem, st);
             else       rc = last ? launch_iter<false, true>(a, g, smem, st) : launch_iter<false, false>(a, g, smem, st);
             if (rc != MAVD_OK) return rc;

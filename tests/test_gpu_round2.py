@@ -455,3 +455,27 @@ def test_tma_staged_polyexp_is_bit_identical(size, poly_n):
     for a, b in zip(got[1], got[0]):
         assert np.array_equal(a, b), float(np.abs(a - b).max())
     eng.close()
+
+
+@pytest.mark.parametrize('winsize', [12, 15, 17])
+def test_small_tile_iteration_is_bit_identical(winsize):
+    """tuning.iter_small_tiles: launches too small to fill the GPU with 64 x 32 tiles (one 640x480 pair; the coarse
+    levels) run the fused iteration on 64 x 16 tiles.  Same sums, same order: flows bit-equal, every level."""
+    import torch
+    from mav_detection_b200 import engine, synth
+    W, H = 640, 480
+    s = synth.make_sequence(W, H, 2, seq=24)
+    p = dict(pyr_scale=0.5, levels=3, winsize=winsize, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+    eng = engine.Engine(W, H, p, max_pairs=1)
+    frames = torch.from_numpy(s.frames).cuda()
+    got = {}
+    for small in (1, 0):
+        eng.set_tuning(iter_small_tiles=small)
+        flow = eng.farneback(frames).cpu().numpy()
+        got[small] = [flow] + [eng.tap('flow', lvl, 0).cpu().numpy() for lvl in range(1, len(eng.levels))] + \
+            [eng.tap('M', lvl, 0).cpu().numpy() for lvl in range(len(eng.levels))]
+    for a, b in zip(got[1], got[0]):
+        assert np.array_equal(a, b), float(np.abs(a - b).max())
+    eng.force_generic_iteration(True)
+    assert np.array_equal(eng.farneback(frames).cpu().numpy(), got[1][0])
+    eng.close()
