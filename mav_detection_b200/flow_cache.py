@@ -79,7 +79,7 @@ class FloCache:
         if previous is not None:                  # write batch k while batch k+1 is on its way
             first, n, st, ev = previous
             ev.synchronize()
-            self._write_frames(first, st[:n].numpy())
+            self._write_frames(first, st[:n])
         self._pending = (first_index, int(flow.shape[0]), stage.numpy(), event)
 
     # -- reading (the Dataset.get_flow_uv seam) -----------------------------------------------------
