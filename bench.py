@@ -338,17 +338,29 @@ def measure(name, args, steps, world, rank, local, headline):
         # (2) per-kernel-class device times: the same steps again with CUDA events around every launch group
         # (profiling launches kernel by kernel, so it is kept out of the timed region above)
         psteps = max(2, min(steps, 8))
-        eng.profile_enable(True)
-        for s in range(psteps):
-            step(warm + s)
-        sync_all()
-        prof = eng.profile_read()
-        eng.profile_enable(False)
+        if args.device_only:
+            psteps, prof = 1, {}
+        else:
+            eng.profile_enable(True)
+            for s in range(psteps):
+                step(warm + s)
+            sync_all()
+            prof = eng.profile_read()
+            eng.profile_enable(False)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     value = world * B * steps / (elapsed_ms * 1e-3)
+
+    if args.device_only:
+        line = None
+        if rank == 0:
+            line = {'metric': metric_name(W), 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': steps,
+                    'warmup': warm, 'ms_per_step': elapsed_ms / steps, 'gpu_launches': int(launches),
+                    'config': {'workload': wl['label'], 'pairs_per_step': B, 'device_only': True}}
+        eng.close()
+        return line
 
     # ---- e2e: host buffers through the C-ABI host call, copies inside the timed region ----
     def pinned(a):
@@ -555,6 +567,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS) + ['all'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--device-only', action='store_true',
+                    help='warm-up + timed device steps only (no per-kernel event pass, no e2e, no CPU leg): the command '
+                         'ncu captures, so that its launch list is whole steps of the hot path and nothing else')
     ap.add_argument('--pairs', type=int, default=0, help='frame pairs per step (default: the workload\'s)')
     ap.add_argument('--tune', default=os.environ.get('MAVD_TUNE', ''),
                     help='mavd_tuning fields, e.g. pair_group=8,use_graph=0 (A/B runs; results never depend on them)')
