@@ -425,6 +425,12 @@ __global__ void __launch_bounds__(256, 4) polyexp_kernel(const void* __restrict_
     polyexp_passes<N_>(raw, t, pc, n, tid, x0, y0, h, pitch, R + (size_t)blockIdx.z * 5 * plane, plane);
 }
 
+// a global store whose address space survives the register pinning of the base pointer below (a plain store through
+// a pointer that went through an asm operand would be emitted as a generic ST)
+__device__ __forceinline__ void st_global_f32(float* p, float v) {
+    asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+
 // ------------------------------------------------------------------------------------------------
 // FarnebackUpdateMatrices for one pixel.  R0/R1 point at plane 0 of the two frames' expansions.
 // ------------------------------------------------------------------------------------------------
@@ -488,6 +494,58 @@ __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, i
     Mout[4 * plane + o] = r6 * r2 + r5 * r3;
 }
 
+// The same with unsigned 32-bit element offsets from base pointers that are pinned in one register pair each: every
+// address is one IMAD.WIDE.U32 (plus an add shared by the neighbours of a plane) instead of a 64-bit add / shift chain.
+// Same operations in the same order: identical results (tuning.mat_u32).
+__device__ __forceinline__ void update_matrices_px_u32(int x, int y, int w, int h, int pitch, unsigned plane, float dx,
+                                                       float dy, const R0Px& r0, const float* __restrict__ R1,
+                                                       float* Mout) {
+    const unsigned o = (unsigned)(y * pitch + x);
+    float fx = (float)x + dx, fy = (float)y + dy;
+    const float flx = floorf(fx), fly = floorf(fy);
+    const int x1 = (int)fminf(fmaxf(flx, -2.f), 1.0e6f), y1 = (int)fminf(fmaxf(fly, -2.f), 1.0e6f);
+    fx -= flx;
+    fy -= fly;
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        unsigned q = (unsigned)(y1 * pitch + x1);
+        const float* p0 = R1 + q;
+        const float* p1 = R1 + (q + (unsigned)pitch);
+        r2 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        q += plane; p0 = R1 + q; p1 = R1 + (q + (unsigned)pitch);
+        r3 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        q += plane; p0 = R1 + q; p1 = R1 + (q + (unsigned)pitch);
+        r4 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        q += plane; p0 = R1 + q; p1 = R1 + (q + (unsigned)pitch);
+        r5 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        q += plane; p0 = R1 + q; p1 = R1 + (q + (unsigned)pitch);
+        r6 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
+        r4 = (r0.yy + r4) * 0.5f;
+        r5 = (r0.xx + r5) * 0.5f;
+        r6 = (r0.xy + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = r0.yy;
+        r5 = r0.xx;
+        r6 = r0.xy * 0.5f;
+    }
+    r2 = (r0.y - r2) * 0.5f;
+    r3 = (r0.x - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float sc = (x < 5 ? border_factor(x) : 1.f) * (x >= w - 5 ? border_factor(w - x - 1) : 1.f) *
+                         (y < 5 ? border_factor(y) : 1.f) * (y >= h - 5 ? border_factor(h - y - 1) : 1.f);
+        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
+    }
+    st_global_f32(Mout + o, r4 * r4 + r6 * r6);
+    st_global_f32(Mout + (o + plane), (r4 + r5) * r6);
+    st_global_f32(Mout + (o + 2 * plane), r5 * r5 + r6 * r6);
+    st_global_f32(Mout + (o + 3 * plane), r4 * r2 + r6 * r3);
+    st_global_f32(Mout + (o + 4 * plane), r6 * r2 + r5 * r3);
+}
+
 // Level entry: flow_l = resize(flow_{l+1}) * (1/pyr_scale) (zeros on the coarsest level), then
 // UpdateMatrices.  The upsampled flow itself is never stored: BlurBox rebuilds the flow from M alone.
 // cv::resize(INTER_LINEAR) source index / weight of destination index d (api.cu: resize_tables), evaluated with the
@@ -525,7 +583,7 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
                                                            const int* __restrict__ fyi0,
                                                            const float* __restrict__ fya, float up_scale,
                                                            float* __restrict__ M, double xscale, double yscale,
-                                                           int txlog, int r0_first) {
+                                                           int txlog, int r0_first, int u32) {
     // 3-D grid (pairs, tiles_x, tiles_y): blocks are scheduled x-fastest, so the pair index is fastest (same L2 sharing
     // of R between consecutive pairs as in iter_box_tma_kernel) and no thread pays for an integer division: with one
     // pixel per thread the two divisions of a 1-D grid were 55 of the kernel's 400 instructions
@@ -568,6 +626,13 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
     // 8 pixels per thread that halve the instruction count (2.45-2.67 vs 2.22 ms per 64-pair step), and a tiled
     // variant with the R1 footprint staged by TMA like the fused iteration's (2.57 ms), all lose more to occupancy
     // than they save: the kernel is bound by the latency of its dependent memory round trips.
+    if (u32) {
+        const float* R1 = R0 + 5 * plane;
+        float* Mp = M + (size_t)p * 5 * plane;
+        asm volatile("" : "+l"(Mp));
+        update_matrices_px_u32(x, y, w, h, pitch, (unsigned)plane, dx, dy, r0, R1, Mp);
+        return;
+    }
     update_matrices_px(x, y, w, h, pitch, plane, dx, dy, r0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
 }
 
@@ -890,14 +955,29 @@ __global__ void __launch_bounds__(256, 4) polyexp_tma_kernel(const __grid_consta
         __syncthreads();          // the byte box (in t) is dead from here on; raw is complete for in-image cells
     }
     if (!interior) {
-        // the expansion reads replicated rows / columns: out-of-image cells take the clamped cell's value
-        for (int idx = tid; idx < rows * PE_RW; idx += 256) {
-            const int rr = idx / PE_RW, cc = idx - rr * PE_RW;
-            const int gy = y0 - n + rr, gx = x0 - PE_H + cc;
-            const int cy = clampi(gy, 0, h - 1), cx = clampi(gx, 0, w - 1);
-            if (cy != gy || cx != gx) raw0[idx] = raw0[(cy - (y0 - n)) * PE_RW + (cx - (x0 - PE_H))];
+        // the expansion reads replicated rows / columns: out-of-image cells take the clamped cell's value (columns
+        // beside the image on the in-image rows first, then whole rows above / below it)
+        const int xlo = max(0, PE_H - x0), xhi = min(PE_RW, w - x0 + PE_H);      // in-image columns [xlo, xhi)
+        const int ylo = max(0, n - y0), yhi = min(rows, h - y0 + n);             // in-image rows [ylo, yhi)
+        const int ncol = xlo + (PE_RW - xhi);
+        if (ncol > 0) {
+            for (int idx = tid; idx < (yhi - ylo) * ncol; idx += 256) {
+                const int rr = ylo + idx / ncol, k = idx % ncol;
+                float* row = raw0 + rr * PE_RW;
+                row[k < xlo ? k : xhi + (k - xlo)] = row[k < xlo ? xlo : xhi - 1];
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        const int nrow_out = ylo + (rows - yhi);
+        if (nrow_out > 0) {
+            for (int idx = tid; idx < nrow_out * (PE_RW / 4); idx += 256) {
+                const int k = idx / (PE_RW / 4), q = idx - k * (PE_RW / 4);
+                const int rr = k < ylo ? k : yhi + (k - ylo);
+                reinterpret_cast<float4*>(raw0 + rr * PE_RW)[q] =
+                    reinterpret_cast<const float4*>(raw0 + (k < ylo ? ylo : yhi - 1) * PE_RW)[q];
+            }
+            __syncthreads();
+        }
     }
     // the passes address the tile with its first staged row at row PE_H - n
     polyexp_passes<N_>(raw0 - (PE_H - n) * PE_RW, t, pc, n, tid, x0, y0, h, pitch, R + (size_t)blockIdx.z * 5 * plane, plane);
@@ -964,12 +1044,6 @@ __device__ __forceinline__ R0Px load_r0(const float* __restrict__ R0, unsigned o
     r.y = __ldg(R0 + o); r.x = __ldg(R0 + (o + plane)); r.yy = __ldg(R0 + (o + 2 * plane));
     r.xx = __ldg(R0 + (o + 3 * plane)); r.xy = __ldg(R0 + (o + 4 * plane));
     return r;
-}
-
-// a global store whose address space survives the register pinning of the base pointer below (a plain store through
-// a pointer that went through an asm operand would be emitted as a generic ST)
-__device__ __forceinline__ void st_global_f32(float* p, float v) {
-    asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v));
 }
 
 template <int RW, int RH>
@@ -1090,15 +1164,37 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
     mbar_wait(&bar, 0);
 
     if (!interior) {
-        // replicate borders: every out-of-image cell takes the value of the clamped (in-image) cell
-        for (int idx = tid; idx < 5 * CH; idx += NT) {
-            const int c = idx / CH, rem = idx - c * CH;
-            const int rr = rem / RW, cc = rem - rr * RW;
-            const int y = y0 - M_ + rr, x = x0 - 8 + cc;
-            const int yc = clampi(y, 0, h - 1), xc = clampi(x, 0, w - 1);
-            if (yc != y || xc != x) box[idx] = box[c * CH + (yc - (y0 - M_)) * RW + (xc - (x0 - 8))];
+        // replicate borders: every out-of-image cell takes the value of the clamped (in-image) cell.  Only the
+        // out-of-image cells are visited — first the columns left / right of the image on the in-image rows, then
+        // whole rows above / below it (which copy already completed rows) — a few hundred cells per plane, not the
+        // whole box: border tiles are 12 % of a 1080p level and up to 40 % of the coarse ones, and walking all
+        // 5 x RH x 80 cells with a division each made such a tile cost twice an interior one
+        const int xlo = max(0, 8 - x0), xhi = min(RW, w - x0 + 8);          // in-image box columns [xlo, xhi)
+        const int ylo = max(0, M_ - y0), yhi = min(RH, h - y0 + M_);        // in-image box rows [ylo, yhi)
+        const int ncol = xlo + (RW - xhi), nrow_in = yhi - ylo;
+        if (ncol > 0) {
+            const int per_plane = nrow_in * ncol;
+            for (int idx = tid; idx < 5 * per_plane; idx += NT) {
+                const int c = idx / per_plane, rem = idx - c * per_plane;
+                const int rr = ylo + rem / ncol, k = rem % ncol;
+                const int cc = k < xlo ? k : xhi + (k - xlo);
+                float* row = box + c * CH + rr * RW;
+                row[cc] = row[k < xlo ? xlo : xhi - 1];
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        const int nrow_out = ylo + (RH - yhi);
+        if (nrow_out > 0) {
+            const int per_plane = nrow_out * (RW / 4);
+            for (int idx = tid; idx < 5 * per_plane; idx += NT) {
+                const int c = idx / per_plane, rem = idx - c * per_plane;
+                const int k = rem / (RW / 4), q = rem - k * (RW / 4);
+                const int rr = k < ylo ? k : yhi + (k - ylo);
+                float* pl = box + c * CH;
+                reinterpret_cast<float4*>(pl + rr * RW)[q] = reinterpret_cast<const float4*>(pl + (k < ylo ? ylo : yhi - 1) * RW)[q];
+            }
+            __syncthreads();
+        }
     }
 
     // ---- vertical running sums, in place: 15 warp-tasks (plane, 32-column block) ----
@@ -1522,7 +1618,8 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             const dim3 g3(g.z, ceil_div(L.w, 1 << txlog), ceil_div(L.h, 256 >> txlog));       // pair index fastest
 #define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, (size_t)pair_stride * 5 * L.plane,                                     \
                 top ? nullptr : (const float2*)C->flow, top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch,             \
-                top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale, txlog, r0_first
+                top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale, txlog, r0_first, \
+                (H->tune.mat_u32 != 0 && 10.0 * (double)L.plane < 4.0e9) ? 1 : 0
             if (coord == MI_COORD_TABLES) matrices_init_kernel<MI_COORD_TABLES><<<g3, 256, 0, st>>>(MI_ARGS);
             else if (coord == MI_COORD_POW2) matrices_init_kernel<MI_COORD_POW2><<<g3, 256, 0, st>>>(MI_ARGS);
             else matrices_init_kernel<MI_COORD_F64><<<g3, 256, 0, st>>>(MI_ARGS);
