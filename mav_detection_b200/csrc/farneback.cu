@@ -445,6 +445,13 @@ __device__ __forceinline__ R0Px load_r0_px(const float* __restrict__ R0, size_t 
     return r;
 }
 
+__device__ __forceinline__ R0Px load_r0_u32(const float* __restrict__ R0, unsigned o, unsigned plane) {
+    R0Px r;
+    r.y = __ldg(R0 + o); r.x = __ldg(R0 + (o + plane)); r.yy = __ldg(R0 + (o + 2 * plane));
+    r.xx = __ldg(R0 + (o + 3 * plane)); r.xy = __ldg(R0 + (o + 4 * plane));
+    return r;
+}
+
 __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, int pitch, size_t plane, float dx,
                                                    float dy, const R0Px& r0,
                                                    const float* __restrict__ R1, float* __restrict__ Mout) {
@@ -573,7 +580,7 @@ __device__ __forceinline__ void resize_coord_pow2(int d, float scale, int src, i
     i0 = s;
 }
 
-template <int COORD>
+template <int COORD, bool U32>
 __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
                                                            int pitch, size_t R_pair_stride,
                                                            const float2* __restrict__ cflow, int cw, int ch,
@@ -583,7 +590,7 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
                                                            const int* __restrict__ fyi0,
                                                            const float* __restrict__ fya, float up_scale,
                                                            float* __restrict__ M, double xscale, double yscale,
-                                                           int txlog, int r0_first, int u32) {
+                                                           int txlog, int r0_first) {
     // 3-D grid (pairs, tiles_x, tiles_y): blocks are scheduled x-fastest, so the pair index is fastest (same L2 sharing
     // of R between consecutive pairs as in iter_box_tma_kernel) and no thread pays for an integer division: with one
     // pixel per thread the two divisions of a 1-D grid were 55 of the kernel's 400 instructions
@@ -596,7 +603,7 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
     // second memory round trip of the thread is the R1 gather alone
     const float* R0 = R + (size_t)p * R_pair_stride;
     R0Px r0;
-    if (r0_first) r0 = load_r0_px(R0, (size_t)y * pitch + x, plane);
+    if (r0_first) r0 = U32 ? load_r0_u32(R0, (unsigned)(y * pitch + x), (unsigned)plane) : load_r0_px(R0, (size_t)y * pitch + x, plane);
     float dx = 0.f, dy = 0.f;
     if (cflow) {
         const float2* cf = cflow + (size_t)p * cflow_stride;
@@ -613,20 +620,27 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
             resize_coord(y, yscale, ch, ya0, ay);
         }
         const int xa1 = min(xa0 + 1, cw - 1), ya1 = min(ya0 + 1, ch - 1);
-        const float2 f00 = cf[(size_t)ya0 * cpitch + xa0], f01 = cf[(size_t)ya0 * cpitch + xa1];
-        const float2 f10 = cf[(size_t)ya1 * cpitch + xa0], f11 = cf[(size_t)ya1 * cpitch + xa1];
+        float2 f00, f01, f10, f11;
+        if (U32) {
+            const unsigned b0 = (unsigned)(ya0 * cpitch), b1 = (unsigned)(ya1 * cpitch);
+            f00 = cf[b0 + (unsigned)xa0]; f01 = cf[b0 + (unsigned)xa1];
+            f10 = cf[b1 + (unsigned)xa0]; f11 = cf[b1 + (unsigned)xa1];
+        } else {
+            f00 = cf[(size_t)ya0 * cpitch + xa0]; f01 = cf[(size_t)ya0 * cpitch + xa1];
+            f10 = cf[(size_t)ya1 * cpitch + xa0]; f11 = cf[(size_t)ya1 * cpitch + xa1];
+        }
         const float tx0 = f00.x * (1.f - ax) + f01.x * ax, tx1 = f10.x * (1.f - ax) + f11.x * ax;
         const float ty0 = f00.y * (1.f - ax) + f01.y * ax, ty1 = f10.y * (1.f - ax) + f11.y * ax;
         dx = (tx0 * (1.f - ay) + tx1 * ay) * up_scale;
         dy = (ty0 * (1.f - ay) + ty1 * ay) * up_scale;
     }
-    if (!r0_first) r0 = load_r0_px(R0, (size_t)y * pitch + x, plane);
+    if (!r0_first) r0 = U32 ? load_r0_u32(R0, (unsigned)(y * pitch + x), (unsigned)plane) : load_r0_px(R0, (size_t)y * pitch + x, plane);
     // One pixel per thread at 32 registers (full occupancy) is the fastest form measured: the 32-bit-offset
     // UpdateMatrices of the fused iteration (> 32 registers: 0.87 vs 0.675 ms per 16-pair step) and variants with
     // 8 pixels per thread that halve the instruction count (2.45-2.67 vs 2.22 ms per 64-pair step), and a tiled
     // variant with the R1 footprint staged by TMA like the fused iteration's (2.57 ms), all lose more to occupancy
     // than they save: the kernel is bound by the latency of its dependent memory round trips.
-    if (u32) {
+    if (U32) {
         const float* R1 = R0 + 5 * plane;
         float* Mp = M + (size_t)p * 5 * plane;
         asm volatile("" : "+l"(Mp));
@@ -1618,11 +1632,13 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             const dim3 g3(g.z, ceil_div(L.w, 1 << txlog), ceil_div(L.h, 256 >> txlog));       // pair index fastest
 #define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, (size_t)pair_stride * 5 * L.plane,                                     \
                 top ? nullptr : (const float2*)C->flow, top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch,             \
-                top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale, txlog, r0_first, \
-                (H->tune.mat_u32 != 0 && 10.0 * (double)L.plane < 4.0e9) ? 1 : 0
-            if (coord == MI_COORD_TABLES) matrices_init_kernel<MI_COORD_TABLES><<<g3, 256, 0, st>>>(MI_ARGS);
-            else if (coord == MI_COORD_POW2) matrices_init_kernel<MI_COORD_POW2><<<g3, 256, 0, st>>>(MI_ARGS);
-            else matrices_init_kernel<MI_COORD_F64><<<g3, 256, 0, st>>>(MI_ARGS);
+                top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale, txlog, r0_first
+            const bool u32 = H->tune.mat_u32 != 0 && 10.0 * (double)L.plane < 4.0e9;
+            if (coord == MI_COORD_TABLES) matrices_init_kernel<MI_COORD_TABLES, false><<<g3, 256, 0, st>>>(MI_ARGS);
+            else if (coord == MI_COORD_POW2 && u32) matrices_init_kernel<MI_COORD_POW2, true><<<g3, 256, 0, st>>>(MI_ARGS);
+            else if (coord == MI_COORD_POW2) matrices_init_kernel<MI_COORD_POW2, false><<<g3, 256, 0, st>>>(MI_ARGS);
+            else if (u32) matrices_init_kernel<MI_COORD_F64, true><<<g3, 256, 0, st>>>(MI_ARGS);
+            else matrices_init_kernel<MI_COORD_F64, false><<<g3, 256, 0, st>>>(MI_ARGS);
 #undef MI_ARGS
             MAVD_LAUNCHED();
         }
