@@ -111,8 +111,7 @@ typedef struct mavd_tuning {
     int32_t polyexp_tma;  /* polynomial expansion: tile staged by one TMA box (default 1) */
     int32_t iter_small_tiles; /* fused iteration: 64 x 16 tiles for launches too small to fill the GPU with 64 x 32
                                  ones (single pairs, coarse levels; default 1) */
-    int32_t mat_u32;      /* level-entry matrices: 32-bit element offsets from pinned base pointers (default 0) */
-    int32_t reserved[3];
+    int32_t reserved[4];
 } mavd_tuning;
 
 /* Optional per-frame inputs of the detection stages.  All pointers are DEVICE pointers for the d_ entry points and

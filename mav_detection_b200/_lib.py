@@ -56,7 +56,7 @@ class Tuning(C.Structure):
     _fields_ = [('overlap', C.c_int32), ('pair_group', C.c_int32), ('r1_staged', C.c_int32), ('iter_fuse', C.c_int32),
                 ('last_fused', C.c_int32), ('mat_coord', C.c_int32), ('mat_r0_first', C.c_int32),
                 ('mat_txlog', C.c_int32), ('pyr_staged', C.c_int32), ('use_graph', C.c_int32),
-                ('polyexp_tma', C.c_int32), ('iter_small_tiles', C.c_int32), ('mat_u32', C.c_int32), ('reserved', C.c_int32 * 3)]
+                ('polyexp_tma', C.c_int32), ('iter_small_tiles', C.c_int32), ('reserved', C.c_int32 * 4)]
 
 
 class AuxInputs(C.Structure):

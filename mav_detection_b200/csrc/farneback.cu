@@ -445,13 +445,6 @@ __device__ __forceinline__ R0Px load_r0_px(const float* __restrict__ R0, size_t 
     return r;
 }
 
-__device__ __forceinline__ R0Px load_r0_u32(const float* __restrict__ R0, unsigned o, unsigned plane) {
-    R0Px r;
-    r.y = __ldg(R0 + o); r.x = __ldg(R0 + (o + plane)); r.yy = __ldg(R0 + (o + 2 * plane));
-    r.xx = __ldg(R0 + (o + 3 * plane)); r.xy = __ldg(R0 + (o + 4 * plane));
-    return r;
-}
-
 __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, int pitch, size_t plane, float dx,
                                                    float dy, const R0Px& r0,
                                                    const float* __restrict__ R1, float* __restrict__ Mout) {
@@ -501,58 +494,6 @@ __device__ __forceinline__ void update_matrices_px(int x, int y, int w, int h, i
     Mout[4 * plane + o] = r6 * r2 + r5 * r3;
 }
 
-// The same with unsigned 32-bit element offsets from base pointers that are pinned in one register pair each: every
-// address is one IMAD.WIDE.U32 (plus an add shared by the neighbours of a plane) instead of a 64-bit add / shift chain.
-// Same operations in the same order: identical results (tuning.mat_u32).
-__device__ __forceinline__ void update_matrices_px_u32(int x, int y, int w, int h, int pitch, unsigned plane, float dx,
-                                                       float dy, const R0Px& r0, const float* __restrict__ R1,
-                                                       float* Mout) {
-    const unsigned o = (unsigned)(y * pitch + x);
-    float fx = (float)x + dx, fy = (float)y + dy;
-    const float flx = floorf(fx), fly = floorf(fy);
-    const int x1 = (int)fminf(fmaxf(flx, -2.f), 1.0e6f), y1 = (int)fminf(fmaxf(fly, -2.f), 1.0e6f);
-    fx -= flx;
-    fy -= fly;
-    float r2, r3, r4, r5, r6;
-    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        unsigned q = (unsigned)(y1 * pitch + x1);
-        const float* p0 = R1 + q;
-        const float* p1 = R1 + (q + (unsigned)pitch);
-        r2 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
-        q += plane; p0 = R1 + q; p1 = R1 + (q + (unsigned)pitch);
-        r3 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
-        q += plane; p0 = R1 + q; p1 = R1 + (q + (unsigned)pitch);
-        r4 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
-        q += plane; p0 = R1 + q; p1 = R1 + (q + (unsigned)pitch);
-        r5 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
-        q += plane; p0 = R1 + q; p1 = R1 + (q + (unsigned)pitch);
-        r6 = a00 * __ldg(p0) + a01 * __ldg(p0 + 1) + a10 * __ldg(p1) + a11 * __ldg(p1 + 1);
-        r4 = (r0.yy + r4) * 0.5f;
-        r5 = (r0.xx + r5) * 0.5f;
-        r6 = (r0.xy + r6) * 0.25f;
-    } else {
-        r2 = r3 = 0.f;
-        r4 = r0.yy;
-        r5 = r0.xx;
-        r6 = r0.xy * 0.5f;
-    }
-    r2 = (r0.y - r2) * 0.5f;
-    r3 = (r0.x - r3) * 0.5f;
-    r2 += r4 * dy + r6 * dx;
-    r3 += r6 * dy + r5 * dx;
-    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-        const float sc = (x < 5 ? border_factor(x) : 1.f) * (x >= w - 5 ? border_factor(w - x - 1) : 1.f) *
-                         (y < 5 ? border_factor(y) : 1.f) * (y >= h - 5 ? border_factor(h - y - 1) : 1.f);
-        r2 *= sc; r3 *= sc; r4 *= sc; r5 *= sc; r6 *= sc;
-    }
-    st_global_f32(Mout + o, r4 * r4 + r6 * r6);
-    st_global_f32(Mout + (o + plane), (r4 + r5) * r6);
-    st_global_f32(Mout + (o + 2 * plane), r5 * r5 + r6 * r6);
-    st_global_f32(Mout + (o + 3 * plane), r4 * r2 + r6 * r3);
-    st_global_f32(Mout + (o + 4 * plane), r6 * r2 + r5 * r3);
-}
-
 // Level entry: flow_l = resize(flow_{l+1}) * (1/pyr_scale) (zeros on the coarsest level), then
 // UpdateMatrices.  The upsampled flow itself is never stored: BlurBox rebuilds the flow from M alone.
 // cv::resize(INTER_LINEAR) source index / weight of destination index d (api.cu: resize_tables), evaluated with the
@@ -580,7 +521,7 @@ __device__ __forceinline__ void resize_coord_pow2(int d, float scale, int src, i
     i0 = s;
 }
 
-template <int COORD, bool U32>
+template <int COORD>
 __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __restrict__ R, size_t plane, int w, int h,
                                                            int pitch, size_t R_pair_stride,
                                                            const float2* __restrict__ cflow, int cw, int ch,
@@ -603,7 +544,7 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
     // second memory round trip of the thread is the R1 gather alone
     const float* R0 = R + (size_t)p * R_pair_stride;
     R0Px r0;
-    if (r0_first) r0 = U32 ? load_r0_u32(R0, (unsigned)(y * pitch + x), (unsigned)plane) : load_r0_px(R0, (size_t)y * pitch + x, plane);
+    if (r0_first) r0 = load_r0_px(R0, (size_t)y * pitch + x, plane);
     float dx = 0.f, dy = 0.f;
     if (cflow) {
         const float2* cf = cflow + (size_t)p * cflow_stride;
@@ -620,33 +561,21 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
             resize_coord(y, yscale, ch, ya0, ay);
         }
         const int xa1 = min(xa0 + 1, cw - 1), ya1 = min(ya0 + 1, ch - 1);
-        float2 f00, f01, f10, f11;
-        if (U32) {
-            const unsigned b0 = (unsigned)(ya0 * cpitch), b1 = (unsigned)(ya1 * cpitch);
-            f00 = cf[b0 + (unsigned)xa0]; f01 = cf[b0 + (unsigned)xa1];
-            f10 = cf[b1 + (unsigned)xa0]; f11 = cf[b1 + (unsigned)xa1];
-        } else {
-            f00 = cf[(size_t)ya0 * cpitch + xa0]; f01 = cf[(size_t)ya0 * cpitch + xa1];
-            f10 = cf[(size_t)ya1 * cpitch + xa0]; f11 = cf[(size_t)ya1 * cpitch + xa1];
-        }
+        const float2 f00 = cf[(size_t)ya0 * cpitch + xa0], f01 = cf[(size_t)ya0 * cpitch + xa1];
+        const float2 f10 = cf[(size_t)ya1 * cpitch + xa0], f11 = cf[(size_t)ya1 * cpitch + xa1];
         const float tx0 = f00.x * (1.f - ax) + f01.x * ax, tx1 = f10.x * (1.f - ax) + f11.x * ax;
         const float ty0 = f00.y * (1.f - ax) + f01.y * ax, ty1 = f10.y * (1.f - ax) + f11.y * ax;
         dx = (tx0 * (1.f - ay) + tx1 * ay) * up_scale;
         dy = (ty0 * (1.f - ay) + ty1 * ay) * up_scale;
     }
-    if (!r0_first) r0 = U32 ? load_r0_u32(R0, (unsigned)(y * pitch + x), (unsigned)plane) : load_r0_px(R0, (size_t)y * pitch + x, plane);
+    if (!r0_first) r0 = load_r0_px(R0, (size_t)y * pitch + x, plane);
     // One pixel per thread at 32 registers (full occupancy) is the fastest form measured: the 32-bit-offset
     // UpdateMatrices of the fused iteration (> 32 registers: 0.87 vs 0.675 ms per 16-pair step) and variants with
     // 8 pixels per thread that halve the instruction count (2.45-2.67 vs 2.22 ms per 64-pair step), and a tiled
     // variant with the R1 footprint staged by TMA like the fused iteration's (2.57 ms), all lose more to occupancy
-    // than they save: the kernel is bound by the latency of its dependent memory round trips.
-    if (U32) {
-        const float* R1 = R0 + 5 * plane;
-        float* Mp = M + (size_t)p * 5 * plane;
-        asm volatile("" : "+l"(Mp));
-        update_matrices_px_u32(x, y, w, h, pitch, (unsigned)plane, dx, dy, r0, R1, Mp);
-        return;
-    }
+    // than they save: the kernel is bound by the latency of its dependent memory round trips.  Round 2 repeated the
+    // experiment at 32 registers (unsigned 32-bit element offsets from pinned base pointers, one IMAD.WIDE.U32 per
+    // address, 352 instead of 384 SASS instructions, no spills): 2.20 vs 2.04 ms per 64-pair step — slower again.
     update_matrices_px(x, y, w, h, pitch, plane, dx, dy, r0, R0 + 5 * plane, M + (size_t)p * 5 * plane);
 }
 
@@ -1633,12 +1562,9 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
 #define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, (size_t)pair_stride * 5 * L.plane,                                     \
                 top ? nullptr : (const float2*)C->flow, top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch,             \
                 top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale, txlog, r0_first
-            const bool u32 = H->tune.mat_u32 != 0 && 10.0 * (double)L.plane < 4.0e9;
-            if (coord == MI_COORD_TABLES) matrices_init_kernel<MI_COORD_TABLES, false><<<g3, 256, 0, st>>>(MI_ARGS);
-            else if (coord == MI_COORD_POW2 && u32) matrices_init_kernel<MI_COORD_POW2, true><<<g3, 256, 0, st>>>(MI_ARGS);
-            else if (coord == MI_COORD_POW2) matrices_init_kernel<MI_COORD_POW2, false><<<g3, 256, 0, st>>>(MI_ARGS);
-            else if (u32) matrices_init_kernel<MI_COORD_F64, true><<<g3, 256, 0, st>>>(MI_ARGS);
-            else matrices_init_kernel<MI_COORD_F64, false><<<g3, 256, 0, st>>>(MI_ARGS);
+            if (coord == MI_COORD_TABLES) matrices_init_kernel<MI_COORD_TABLES><<<g3, 256, 0, st>>>(MI_ARGS);
+            else if (coord == MI_COORD_POW2) matrices_init_kernel<MI_COORD_POW2><<<g3, 256, 0, st>>>(MI_ARGS);
+            else matrices_init_kernel<MI_COORD_F64><<<g3, 256, 0, st>>>(MI_ARGS);
 #undef MI_ARGS
             MAVD_LAUNCHED();
         }
