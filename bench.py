@@ -61,10 +61,12 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons every 25 ms from before the warm-up on; stop(t0, t1) reports the
+    samples that arrived inside the timed region [t0, t1] (host clock), or, if the region was too short to catch two
+    of them, all samples taken while the GPU was busy (the warm-up steps run the same kernels back to back)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+         'clocks_event_reasons.sw_power_cap,utilization.gpu')
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
@@ -72,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '25'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,9 +83,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0: float = 0.0, t1: float = float('inf')):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -91,21 +93,27 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        rows = []
+        for ts, ln in self.lines:
             parts = [p.strip() for p in ln.split(',')]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+                rows.append((ts, float(parts[0]), float(parts[1]), float(parts[2]),
+                             [n for n, v in zip(names, parts[3:7]) if v.lower().startswith('active')], float(parts[7])))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+        timed = [r for r in rows if t0 <= r[0] <= t1 + 0.03]
+        window = 'timed region'
+        if len(timed) < 2:
+            timed = [r for r in rows if r[5] >= 50.0 or r[3] >= 300.0] or rows
+            window = 'warm-up + timed region (GPU busy)'
+        sm = [r[1] for r in timed]
+        reasons = sorted({n for r in timed for n in r[4]})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max((r[2] for r in rows), default=None),
+                'power_w_max': max((r[3] for r in timed), default=None), 'samples': len(timed), 'window': window,
+                'reasons': reasons}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -314,17 +322,18 @@ def measure(name, args, steps, world, rank, local, headline):
             torch.cuda.synchronize(dev)
 
     warm = max(args.warmup, N_BATCHES + 1)     # every resident batch once: its launch sequence is captured then
+    sampler = ClockSampler(local)
+    if rank == 0 and headline:
+        sampler.start()
     with torch.cuda.stream(stream):
         for s in range(warm):
             step(s)
         sync_all()
         # (1) the timed region: K steps as the caller sees them (graph replay when tuning.use_graph)
         launches0 = eng.launch_count()
-        sampler = ClockSampler(local)
-        if rank == 0 and headline:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
+        t_host0 = time.time()
         e0.record()
         for s in range(steps):
             step(warm + s)
@@ -332,8 +341,9 @@ def measure(name, args, steps, world, rank, local, headline):
             torch.cuda.current_stream(dev).wait_stream(side)
         e1.record()
         sync_all()
+        t_host1 = time.time()
         elapsed_ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if (rank == 0 and headline) else None
+        clocks = sampler.stop(t_host0, t_host1) if (rank == 0 and headline) else None
         launches = eng.launch_count() - launches0
         # (2) per-kernel-class device times: the same steps again with CUDA events around every launch group
         # (profiling launches kernel by kernel, so it is kept out of the timed region above)
