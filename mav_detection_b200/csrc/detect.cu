@@ -502,7 +502,7 @@ __device__ __forceinline__ bool pixel_fast(float fx, float fy, float dx, float d
 constexpr int RES_ITEMS = 4;     // pixel groups per thread
 
 template <int MODE, bool FAST, int VEC>
-__global__ void __launch_bounds__(256, 3) residual_kernel(const ResidualArgs A, const FastPrm fp) {
+__global__ void __launch_bounds__(256, 4) residual_kernel(const ResidualArgs A, const FastPrm fp) {
     const int f = blockIdx.y;
     DerotRow dr;
     dr.on = 0;
