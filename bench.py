@@ -2,7 +2,7 @@
 """Benchmark of the mav-detection hot path (Farneback flow -> derotate -> FoE -> phi/masks -> components).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload c2|c2rot|c2dense|c2ref|c1|c3|c4|all] [--tune field=value,...]
+                    [--workload c2|c2rot|c2dense|c2gauss|c2w21|c2ref|c1|c3|c4|all] [--tune field=value,...]
 
 One "step" = one pass of the whole hot path over one batch of frame pairs taken from a synthetic
 sequence that is resident in HBM (device arm) / in pinned host memory (e2e).  Prints ONE JSON line.
@@ -41,6 +41,10 @@ WORKLOADS = {
     'c2dense': (1920, 1080, SAMPLE, 64,
                 'C2 frames under a sideways translation: no FoE consensus, ~100 % of the pixels in both masks '
                 '(dense residual / components stress)', dict(motion='translate')),
+    'c2gauss': (1920, 1080, dict(SAMPLE, flags=256), 64,
+                'C2 with OPTFLOW_FARNEBACK_GAUSSIAN (flags=256): the generic, non-TMA iteration kernel', {}),
+    'c2w21': (1920, 1080, dict(SAMPLE, winsize=21), 64,
+              'C2 with winsize 21 (half-width 10, outside the TMA kernel\'s 5..8): the generic iteration kernel', {}),
     'c2ref': (1920, 1080, REFPRM, 32, "C2': 1920x1080 with the reference's own parameters (0.4,1,12,10,8,1.2,0)", {}),
     'c1': (640, 480, REFPRM, 1, 'C1: one 640x480 pair, reference parameters', {}),
     'c3': (640, 480, SAMPLE, 64, 'C3: 640x480, 64 pairs per launch', {}),
