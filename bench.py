@@ -42,7 +42,7 @@ WORKLOADS = {
                 'C2 frames under a sideways translation: no FoE consensus, ~100 % of the pixels in both masks '
                 '(dense residual / components stress)', dict(motion='translate')),
     'c2gauss': (1920, 1080, dict(SAMPLE, flags=256), 64,
-                'C2 with OPTFLOW_FARNEBACK_GAUSSIAN (flags=256): the generic, non-TMA iteration kernel', {}),
+                'C2 with OPTFLOW_FARNEBACK_GAUSSIAN (flags=256): Gaussian windows on the TMA-staged iteration kernel', {}),
     'c2w21': (1920, 1080, dict(SAMPLE, winsize=21), 64,
               'C2 with winsize 21 (half-width 10, outside the TMA kernel\'s 5..8): the generic iteration kernel', {}),
     'c2ref': (1920, 1080, REFPRM, 32, "C2': 1920x1080 with the reference's own parameters (0.4,1,12,10,8,1.2,0)", {}),

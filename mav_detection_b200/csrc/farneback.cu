@@ -627,9 +627,21 @@ __device__ __forceinline__ void hsum_gauss(const float (&u)[20], const float* __
     for (int i = 0; i <= M_; ++i) k[i] = gk[i];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float s = u[8 + j] * k[0];
+        // explicit multiply / fused multiply-add: every kernel that evaluates this filter rounds identically
+        float s = __fmul_rn(u[8 + j], k[0]);
 #pragma unroll
-        for (int i = 1; i <= M_; ++i) s += (u[8 + j - i] + u[8 + j + i]) * k[i];
+        for (int i = 1; i <= M_; ++i) s = __fmaf_rn(u[8 + j - i] + u[8 + j + i], k[i], s);
+        o[j] = s;
+    }
+}
+
+template <int M_>
+__device__ __forceinline__ void hsum_gauss_reg(const float (&u)[20], const float (&k)[M_ + 1], float (&o)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float s = __fmul_rn(u[8 + j], k[0]);
+#pragma unroll
+        for (int i = 1; i <= M_; ++i) s = __fmaf_rn(u[8 + j - i] + u[8 + j + i], k[i], s);
         o[j] = s;
     }
 }
@@ -692,8 +704,8 @@ __global__ void __launch_bounds__(256, 3) iter_kernel(IterArgs a) {
             for (int task = tid; task < ncols * IT_TY; task += 256) {
                 int cc = task % ncols + (hx - m), r = task / ncols;
                 const float* col = raw + r * RW + cc;
-                float s = col[m * RW] * __ldg(a.gk);
-                for (int i = 1; i <= m; ++i) s += (col[(m - i) * RW] + col[(m + i) * RW]) * __ldg(a.gk + i);
+                float s = __fmul_rn(col[m * RW], __ldg(a.gk));
+                for (int i = 1; i <= m; ++i) s = __fmaf_rn(col[(m - i) * RW] + col[(m + i) * RW], __ldg(a.gk + i), s);
                 vs[r * RW + cc] = s;
             }
         }
@@ -738,8 +750,8 @@ __global__ void __launch_bounds__(256, 3) iter_kernel(IterArgs a) {
                     s = 0.f;
                     for (int j = -m; j <= m; ++j) s += row[j];
                 } else {
-                    s = row[0] * __ldg(a.gk);
-                    for (int i = 1; i <= m; ++i) s += (row[-i] + row[i]) * __ldg(a.gk + i);
+                    s = __fmul_rn(row[0], __ldg(a.gk));
+                    for (int i = 1; i <= m; ++i) s = __fmaf_rn(row[-i] + row[i], __ldg(a.gk + i), s);
                 }
                 Sc[idx] = s;
             }
@@ -1058,7 +1070,10 @@ __device__ __forceinline__ void update_matrices_box(int x, int y, int w, int h, 
 // TY: tile height, 32 by default; 16 for launches whose 32-row tiling would leave SMs idle (single pairs, the coarse
 // levels): twice the CTAs, half the serial work per CTA.  The vertical sums are re-seeded at absolute rows that are
 // multiples of 8 in both tilings and the horizontal groups start at multiples of 4: the results are bit-identical.
-template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0, int TY = IT_TY>
+// GAUSS: OPTFLOW_FARNEBACK_GAUSSIAN windows (FarnebackUpdateFlow_GaussianBlur): the vertical pass is the 2m+1-tap
+// filter on the same register window (in place, like the running sums), the horizontal one hsum_gauss; both with the
+// generic kernel's expressions, so the two kernels stay bit-identical.
+template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0, int TY = IT_TY, bool GAUSS = false>
 __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                              const __grid_constant__ CUtensorMap tmapR,
                                                                              const __grid_constant__ CUtensorMap tmapRbox,
@@ -1091,6 +1106,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
     const int x0 = (tile % a.tiles_x) * IT_TX, y0 = (tile / a.tiles_x) * TY;
     const int w = a.w, h = a.h, pitch = a.pitch;
     const int plane = (int)a.plane;
+    float gk[M_ + 1];                        // Gaussian half kernel (GAUSS only)
+#pragma unroll
+    for (int i = 0; i <= M_; ++i) gk[i] = GAUSS ? __ldg(a.gk + i) : 0.f;
+    auto hsum = [&](const float (&u)[20], float (&o)[4]) {
+        if (GAUSS) hsum_gauss_reg<M_>(u, gk, o);
+        else hsum_box<M_>(u, o);
+    };
 
     if (tid == 0) {
         // the issuing thread initialises the barrier and starts the load before the block-wide sync that publishes
@@ -1152,6 +1174,18 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                 in[j] = q[j * RW];
                 s += in[j];
             }
+            if (GAUSS) {
+                // weighted window: centre tap first, then the symmetric pairs outwards (iter_kernel's expression)
+#pragma unroll
+                for (int y = 0; y < TY; ++y) {
+                    float g = __fmul_rn(in[y + M_], gk[0]);
+#pragma unroll
+                    for (int i = 1; i <= M_; ++i) g = __fmaf_rn(in[y + M_ - i] + in[y + M_ + i], gk[i], g);
+                    q[y * RW] = g;
+                    if (y < TY - 1) in[y + 2 * M_ + 1] = q[(y + 2 * M_ + 1) * RW];
+                }
+                continue;
+            }
             // running sums, re-seeded from the window every 8 rows (bounds the float32 drift; the same association
             // as iter_kernel's 8-row segments, so both kernels produce bit-identical sums)
 #pragma unroll
@@ -1195,7 +1229,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                     const float4 v = *reinterpret_cast<const float4*>(row + 4 * j);
                     u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w;
                 }
-                hsum_box<M_>(u, o[c]);
+                hsum(u, o[c]);
             }
             const int x = x0 + 4 * q4, y = y0 + r;
             if (y >= h || x >= w) continue;
@@ -1236,7 +1270,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                 u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w;
             }
             float o[4];
-            hsum_box<M_>(u, o);
+            hsum(u, o);
             __syncwarp();
             *reinterpret_cast<float4*>(row + 8) = make_float4(o[0], o[1], o[2], o[3]);
         }
@@ -1283,7 +1317,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                         const float4 v = *reinterpret_cast<const float4*>(row + 4 * j);
                         u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w;
                     }
-                    hsum_box<M_>(u, o[c]);
+                    hsum(u, o[c]);
                 }
                 float fx4[4], fy4[4];
 #pragma unroll
@@ -1402,12 +1436,12 @@ static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s
     return MAVD_OK;
 }
 
-template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0, int TY = IT_TY>
+template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0, int TY = IT_TY, bool GAUSS = false>
 static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const CUtensorMap& mapRbox, const IterArgs& a,
                            dim3 grid, cudaStream_t s) {
     constexpr size_t smem = sizeof(float) * 5 * (TY + 2 * M_) * (IT_TX + 16);
-    MAVD_CUDA((ensure_dynamic_smem<iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE, TY>>(smem)));
-    iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE, TY><<<grid, NT, smem, s>>>(map, mapR, mapRbox, a);
+    MAVD_CUDA((ensure_dynamic_smem<iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE, TY, GAUSS>>(smem)));
+    iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE, TY, GAUSS><<<grid, NT, smem, s>>>(map, mapR, mapRbox, a);
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
@@ -1421,6 +1455,17 @@ static int launch_iter_tma_m(int m, const mavd_tuning& tune, bool small_tiles, c
     // horizontal sums + solve in registers for the not-last iterations too, flow vectors handed to the update phase
     // through shared memory: iter_full 4.27 vs 4.39 ms per 64-pair step (tuning.iter_fuse)
     const int fuse = tune.iter_fuse;
+    if (a.gk != nullptr) {  // Gaussian windows: production variants only (the caller checked the tuning), both tile heights
+#define GAUSS_CASE(M)                                                                                                        \
+        case M: return small_tiles ? launch_iter_tma<M, LAST, 256, !LAST, LAST ? 0 : 1, 16, true>(map, mapR, mapRbox, a, grid, s) \
+                                   : launch_iter_tma<M, LAST, 256, !LAST, LAST ? 0 : 1, IT_TY, true>(map, mapR, mapRbox, a, grid, s);
+        switch (m) {
+            GAUSS_CASE(5) GAUSS_CASE(6) GAUSS_CASE(7)
+            default: return small_tiles ? launch_iter_tma<8, LAST, 256, !LAST, LAST ? 0 : 1, 16, true>(map, mapR, mapRbox, a, grid, s)
+                                        : launch_iter_tma<8, LAST, 256, !LAST, LAST ? 0 : 1, IT_TY, true>(map, mapR, mapRbox, a, grid, s);
+        }
+#undef GAUSS_CASE
+    }
     if (small_tiles) {      // 64 x 16 tiles (the caller built `grid` and the descriptors for them): production variants only
         switch (m) {
             case 5: return launch_iter_tma<5, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s);
@@ -1604,7 +1649,9 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
             ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), st);
             int rc;
-            if (!gauss && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter) {
+            // Gaussian windows use the TMA kernel's production variants (R1 staged, sums in registers) only
+            const bool prod = H->tune.r1_staged != 0 && H->tune.iter_fuse != 0 && H->tune.last_fused != 0;
+            if ((!gauss || prod) && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter) {
                 const CUtensorMap& mM = small_tiles ? L.tmapM16[cur] : L.tmapM[cur];
                 const CUtensorMap& mRb = small_tiles ? L.tmapRbox16 : L.tmapRbox;
                 rc = last ? launch_iter_tma_m<true>(m, H->tune, small_tiles, mM, L.tmapR, mRb, a, g1, st)

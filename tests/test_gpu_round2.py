@@ -479,3 +479,28 @@ def test_small_tile_iteration_is_bit_identical(winsize):
     eng.force_generic_iteration(True)
     assert np.array_equal(eng.farneback(frames).cpu().numpy(), got[1][0])
     eng.close()
+
+
+@pytest.mark.parametrize('winsize', [11, 13, 15, 17])
+def test_gaussian_windows_on_the_tma_iteration_kernel(winsize):
+    """OPTFLOW_FARNEBACK_GAUSSIAN with winsize/2 in 5..8 runs on the TMA-staged kernel (both tile heights) since round
+    2: equal to the generic kernel (same filter expressions) and to cv2 within the flow tolerance."""
+    cv2 = pytest.importorskip('cv2')
+    import torch
+    from mav_detection_b200 import engine, synth
+    s = synth.make_sequence(700, 500, 3, seq=25)
+    p = dict(pyr_scale=0.5, levels=3, winsize=winsize, iterations=3, poly_n=5, poly_sigma=1.2, flags=256)
+    eng = engine.Engine(700, 500, p, max_pairs=2)
+    frames = torch.from_numpy(s.frames).cuda()
+    a = eng.farneback(frames).cpu().numpy()
+    eng.force_generic_iteration(True)
+    b = eng.farneback(frames).cpu().numpy()
+    eng.force_generic_iteration(False)
+    eng.set_tuning(iter_small_tiles=0)
+    c = eng.farneback(frames).cpu().numpy()
+    assert np.array_equal(a, c), float(np.abs(a - c).max())                    # 64 x 16 vs 64 x 32 tiles
+    assert np.array_equal(a, b), float(np.abs(a - b).max())                    # TMA vs generic
+    ref = cv2.calcOpticalFlowFarneback(s.frames[0], s.frames[1], None, 0.5, 3, winsize, 3, 5, 1.2, 256)
+    epe = np.linalg.norm(a[0] - ref, axis=-1)
+    assert epe.mean() < 1e-4 and epe.max() < 5e-3, (epe.mean(), epe.max())
+    eng.close()
