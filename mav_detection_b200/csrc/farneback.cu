@@ -10,12 +10,13 @@
 // Kernels (algorithmic bytes per level pixel P):
 //   pyr_vfirst / pyr_hsecond / pyr_hsecond_staged
 //                             blur+resize from full-res u8 for all coarse levels, three launches
-//   polyexp_kernel            separable polynomial expansion, smem tile          4P -> 20P (level 0: 1P -> 20P)
+//   polyexp_tma_kernel        separable polynomial expansion, tile staged by one TMA box  4P -> 20P (level 0: 1P -> 20P)
+//   polyexp_kernel            the same with per-thread loads (rows that are not 16-byte aligned)
 //   matrices_init_kernel      flow upsample (x 1/pyr_scale) fused with UpdateMatrices   (8P' +) 40P -> 20P
-//   iter_box_tma_kernel       box blur of M + 2x2 solve + UpdateMatrices, TMA-staged     88P (28P for the last)
-//   iter_kernel               the same for Gaussian windows and window sizes outside 11..17 (generic staging)
+//   iter_box_tma_kernel       box / Gaussian blur of M + 2x2 solve + UpdateMatrices, TMA-staged, window half-widths
+//                             5..8 (winsize 10..17), 64x32 or 64x16 tiles                88P (28P for the last)
+//   iter_kernel               the same for the other window sizes (generic staging); reference of the bit-equality tests
 #include <math.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
