@@ -509,7 +509,7 @@ def measure(name, args, steps, world, rank, local, headline):
                                     % (eng.workspace_bytes / 1e9),
                        'sharding': 'each rank runs its own sequence; records all_gathered over NCCL per step'
                                    if world > 1 else 'single GPU',
-                       'tuning': eng.get_tuning()},
+                       'tuning': eng.get_tuning(), 'launch_sequences': eng.graph_stats()},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'call': 'mavd_submit_host_ex/mavd_wait_host (C ABI, pinned host buffers, %d batches in flight; '

@@ -111,7 +111,10 @@ typedef struct mavd_tuning {
     int32_t polyexp_tma;  /* polynomial expansion: tile staged by one TMA box (default 1) */
     int32_t iter_small_tiles; /* fused iteration: 64 x 16 tiles for launches too small to fill the GPU with 64 x 32
                                  ones (single pairs, coarse levels; default 1) */
-    int32_t reserved[4];
+    int32_t use_pdl;      /* programmatic dependent launch: every kernel of the batch is set up while its predecessor
+                             on the stream drains and waits for it with griddepcontrol.wait, so launch latency and
+                             the ramp of the first wave leave the critical path (default 1) */
+    int32_t reserved[3];
 } mavd_tuning;
 
 /* Optional per-frame inputs of the detection stages.  All pointers are DEVICE pointers for the d_ entry points and
@@ -387,6 +390,10 @@ int mavd_debug_force_exact_residual(mavd_handle h, int32_t on);
 
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t mavd_launch_count(void);
+
+/* Captured launch sequences the handle holds (tuning.use_graph): how many replay as a CUDA graph and how many could
+ * not be captured or instantiated and run kernel by kernel instead (expected 0; a diagnostic, results are the same). */
+int mavd_graph_stats(mavd_handle h, int32_t* n_captured, int32_t* n_direct);
 
 #ifdef __cplusplus
 }

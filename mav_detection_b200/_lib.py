@@ -56,7 +56,8 @@ class Tuning(C.Structure):
     _fields_ = [('overlap', C.c_int32), ('pair_group', C.c_int32), ('r1_staged', C.c_int32), ('iter_fuse', C.c_int32),
                 ('last_fused', C.c_int32), ('mat_coord', C.c_int32), ('mat_r0_first', C.c_int32),
                 ('mat_txlog', C.c_int32), ('pyr_staged', C.c_int32), ('use_graph', C.c_int32),
-                ('polyexp_tma', C.c_int32), ('iter_small_tiles', C.c_int32), ('reserved', C.c_int32 * 4)]
+                ('polyexp_tma', C.c_int32), ('iter_small_tiles', C.c_int32), ('use_pdl', C.c_int32),
+                ('reserved', C.c_int32 * 3)]
 
 
 class AuxInputs(C.Structure):
@@ -132,6 +133,7 @@ SIGNATURES = {
     'mavd_phi_colormap': (C.c_int, [_P, C.c_int32, C.c_int64, C.c_double, _P, _P, _P]),
     'mavd_mask_overlay': (C.c_int, [_P, C.c_int32, _P, C.c_int64, _P, _P, _P]),
     'mavd_launch_count': (C.c_int64, []),
+    'mavd_graph_stats': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'mavd_debug_force_generic_iteration': (C.c_int, [_P, C.c_int32]),
     'mavd_debug_force_exact_residual': (C.c_int, [_P, C.c_int32]),
     'mavd_profile_enable': (C.c_int, [_P, C.c_int32]),

@@ -499,6 +499,7 @@ void mavd_default_tuning(mavd_tuning* t) {
     t->use_graph = 1;
     t->polyexp_tma = 1;
     t->iter_small_tiles = 1;
+    t->use_pdl = 1;
 }
 
 int mavd_set_tuning(mavd_handle h, const mavd_tuning* t) {
@@ -510,6 +511,13 @@ int mavd_set_tuning(mavd_handle h, const mavd_tuning* t) {
     MAVD_CUDA(cudaDeviceSynchronize());
     drop_graphs(h);
     h->tune = *t;
+    return MAVD_OK;
+}
+
+int mavd_graph_stats(mavd_handle h, int32_t* n_captured, int32_t* n_direct) {
+    MAVD_REQUIRE(h && n_captured && n_direct, MAVD_ERR_INVALID, "graph_stats: NULL argument");
+    *n_captured = *n_direct = 0;
+    for (const auto& g : h->graphs) ++*(g.exec ? n_captured : n_direct);
     return MAVD_OK;
 }
 
@@ -598,6 +606,8 @@ int mavd_bgr2gray(const uint8_t* d_bgr, uint8_t* d_gray, int64_t n_pixels, void*
 
 static int check_batch(mavd_handle h, int n, const char* what) {
     MAVD_REQUIRE(h != nullptr, MAVD_ERR_INVALID, "%s: handle is NULL", what);
+    pdl_break(h, 0);        // the first kernel of a call is never chained to whatever ran before it on the stream
+    pdl_break(h, 1);
     MAVD_REQUIRE(n >= 0 && n <= h->cfg.max_pairs, MAVD_ERR_INVALID, "%s: batch %d exceeds max_pairs %d", what, n,
                  h->cfg.max_pairs);
     return MAVD_OK;
@@ -784,6 +794,7 @@ int mavd_flow_vis(const float* d_flow, int64_t n_pixels, uint8_t* d_bgr, uint32_
 }
 
 __global__ void records_fill_kernel(mavd_frame_record* rec, const double* foe, const int32_t* ninter, int n) {
+    pdl_entry();
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
     rec[f].foe[0] = foe[2 * f];
@@ -808,7 +819,7 @@ static int detect_run(mavd_handle h, const float* flow, int n, const mavd_detect
     char* nl0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, n_labels);
     TRY(ccl_run(h, fixed, n, nullptr, boxes0, sizeof(mavd_frame_record) / sizeof(int32_t), MAVD_MAX_BOXES,
                 reinterpret_cast<int32_t*>(nl0), sizeof(mavd_frame_record), s, true));
-    records_fill_kernel<<<ceil_div(n, 128), 128, 0, s>>>(d_records, h->d_foe, h->d_ninter, n);
+    MAVD_CUDA(launch_chained(pdl_next(h), records_fill_kernel, ceil_div(n, 128), 128, 0, s, d_records, h->d_foe, h->d_ninter, n));
     MAVD_LAUNCHED();
     return MAVD_OK;
 }

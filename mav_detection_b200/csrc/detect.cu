@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(1024) foe_kernel(const void* __restrict__ flow
                                                   const int32_t* __restrict__ samples, int w, int h,
                                                   double mag_thr, double sq_thr, double* __restrict__ foe,
                                                   int32_t* __restrict__ ninter) {
+    pdl_entry();
     __shared__ double2 E[kNP];
     __shared__ int warp_cnt[32];
     __shared__ unsigned long long warp_best[32];
@@ -263,8 +264,8 @@ static double sqrt_threshold(double T) {
 int foe_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu,
             const mavd_detect_params& prm, const int32_t* d_samples, double* d_foe, int32_t* d_ninter, cudaStream_t s) {
     ProfScope ps(&H->prof, MAVD_PROF_FOE, s);
-    foe_kernel<<<n, 1024, 0, s>>>(d_flow, flow_kind, d_imu, d_samples, H->cfg.width, H->cfg.height,
-                                  prm.magnitude_threshold, sqrt_threshold(prm.ransac_threshold), d_foe, d_ninter);
+    MAVD_CUDA(launch_chained(pdl_next(H), foe_kernel, n, 1024, 0, s, d_flow, flow_kind, d_imu, d_samples, H->cfg.width,
+                             H->cfg.height, prm.magnitude_threshold, sqrt_threshold(prm.ransac_threshold), d_foe, d_ninter));
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
@@ -377,6 +378,7 @@ __device__ __forceinline__ unsigned long long dmax_key(double v) { return (unsig
 // max over a uint8 image, 16 bytes per load where the alignment allows
 __global__ void __launch_bounds__(256) seg_max_kernel(const uint8_t* __restrict__ seg, int64_t seg_stride, int64_t npx,
                                                      int* __restrict__ seg_max) {
+    pdl_entry();
     const int f = blockIdx.y;
     const uint8_t* p = seg + (size_t)f * seg_stride;
     unsigned mx4 = 0;
@@ -503,6 +505,7 @@ constexpr int RES_ITEMS = 4;     // pixel groups per thread
 
 template <int MODE, bool FAST, int VEC>
 __global__ void __launch_bounds__(256, 4) residual_kernel(const ResidualArgs A, const FastPrm fp) {
+    pdl_entry();
     const int f = blockIdx.y;
     DerotRow dr;
     dr.on = 0;
@@ -770,6 +773,7 @@ __global__ void __launch_bounds__(256, 4) residual_kernel(const ResidualArgs A, 
 }
 
 __global__ void stats_init_kernel(char* stats_base, size_t stats_stride, int n, int* seg_max) {
+    pdl_entry();
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
     mavd_frame_stats* st = reinterpret_cast<mavd_frame_stats*>(stats_base + (size_t)f * stats_stride);
@@ -783,6 +787,7 @@ __global__ void stats_init_kernel(char* stats_base, size_t stats_stride, int n, 
 
 // no_max_phi: the FAST path ran (for the frames with imu.derotate != 0, or for all frames when imu is NULL)
 __global__ void stats_final_kernel(char* stats_base, size_t stats_stride, int n, int no_max_phi, const mavd_imu* imu) {
+    pdl_entry();
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n) return;
     mavd_frame_stats* st = reinterpret_cast<mavd_frame_stats*>(stats_base + (size_t)f * stats_stride);
@@ -791,14 +796,14 @@ __global__ void stats_final_kernel(char* stats_base, size_t stats_stride, int n,
 }
 
 template <int MODE, bool FAST>
-static int launch_residual(const ResidualArgs& A, const FastPrm& fp, int n, bool vec4, cudaStream_t s) {
+static int launch_residual(const ResidualArgs& A, const FastPrm& fp, int n, bool vec4, cudaStream_t s, bool pdl) {
     const int npx = A.w * A.h;
     if (vec4) {
         dim3 g(ceil_div(npx / 4, 256 * RES_ITEMS), n);
-        residual_kernel<MODE, FAST, 4><<<g, 256, 0, s>>>(A, fp);
+        MAVD_CUDA(launch_chained(pdl, residual_kernel<MODE, FAST, 4>, g, 256, 0, s, A, fp));
     } else {
         dim3 g(ceil_div(npx, 256 * RES_ITEMS), n);
-        residual_kernel<MODE, FAST, 1><<<g, 256, 0, s>>>(A, fp);
+        MAVD_CUDA(launch_chained(pdl, residual_kernel<MODE, FAST, 1>, g, 256, 0, s, A, fp));
     }
     MAVD_LAUNCHED();
     return MAVD_OK;
@@ -821,11 +826,12 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
                       p.fixed_angle <= 170.0 && p.dyn_offset + p.dyn_base < 160.0 && p.dyn_gain < 1e6 &&
                       p.dyn_min_mag < 1e3 && p.fixed_min_mag < 1e3;
     if (d_stats) {
-        stats_init_kernel<<<ceil_div(n, 128), 128, 0, s>>>((char*)d_stats, stats_stride, n, d_seg ? seg_max : nullptr);
+        MAVD_CUDA(launch_chained(pdl_next(H), stats_init_kernel, ceil_div(n, 128), 128, 0, s, (char*)d_stats, stats_stride, n,
+                                 d_seg ? seg_max : nullptr));
         MAVD_LAUNCHED();
         if (d_seg) {
             dim3 g(32, n);
-            seg_max_kernel<<<g, 256, 0, s>>>(d_seg, seg_stride, npx, seg_max);
+            MAVD_CUDA(launch_chained(pdl_next(H), seg_max_kernel, g, 256, 0, s, d_seg, seg_stride, npx, seg_max));
             MAVD_LAUNCHED();
         }
     }
@@ -854,17 +860,18 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
                       (sky_stride % 4 == 0) && (seg_stride % 4 == 0);
     bool used_fast = false;
     if (flow_kind == 2) {
-        if (fast) { used_fast = true; TRY_RC(launch_residual<2, true>(A, fp, n, vec4, s)); }
-        else      TRY_RC(launch_residual<2, false>(A, fp, n, vec4, s));
+        if (fast) { used_fast = true; TRY_RC(launch_residual<2, true>(A, fp, n, vec4, s, pdl_next(H))); }
+        else      TRY_RC(launch_residual<2, false>(A, fp, n, vec4, s, pdl_next(H)));
     } else {
         if (flow_kind == 0 && run_f64) {
-            if (fast) { used_fast = true; TRY_RC(launch_residual<0, true>(A, fp, n, vec4, s)); }
-            else      TRY_RC(launch_residual<0, false>(A, fp, n, vec4, s));
+            if (fast) { used_fast = true; TRY_RC(launch_residual<0, true>(A, fp, n, vec4, s, pdl_next(H))); }
+            else      TRY_RC(launch_residual<0, false>(A, fp, n, vec4, s, pdl_next(H)));
         }
-        if (flow_kind == 1 || run_f32) TRY_RC(launch_residual<1, false>(A, fp, n, vec4, s));
+        if (flow_kind == 1 || run_f32) TRY_RC(launch_residual<1, false>(A, fp, n, vec4, s, pdl_next(H)));
     }
     if (d_stats) {
-        stats_final_kernel<<<ceil_div(n, 128), 128, 0, s>>>((char*)d_stats, stats_stride, n, used_fast ? 1 : 0, A.imu);
+        MAVD_CUDA(launch_chained(pdl_next(H), stats_final_kernel, ceil_div(n, 128), 128, 0, s, (char*)d_stats, stats_stride, n,
+                                 used_fast ? 1 : 0, A.imu));
         MAVD_LAUNCHED();
     }
     return MAVD_OK;
@@ -1400,6 +1407,7 @@ __device__ __forceinline__ void unit_runs(UnitRuns& R) {
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_list_kernel(const uint8_t* __restrict__ mask, int npx, int n_units, int n,
                                                       int* __restrict__ entries, int* __restrict__ count) {
+    pdl_entry();
     const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int total = n * n_units;
     for (int e = gw; e < total; e += warps) {
@@ -1441,6 +1449,7 @@ __device__ __forceinline__ UnitAbove unit_above(const uint8_t* __restrict__ m, i
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w,
                                                       int npx, CclList L) {
+    pdl_entry();
     const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int cnt = *L.count;
     for (int q = gw; q < cnt; q += warps) {
@@ -1472,6 +1481,7 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w,
                                                        int npx, CclList L) {
+    pdl_entry();
     const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int cnt = *L.count;
     for (int q = gw; q < cnt; q += warps) {
@@ -1506,6 +1516,7 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restric
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_compress_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent, int w,
                                                           int npx, CclList L) {
+    pdl_entry();
     const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int cnt = *L.count;
     for (int q = gw; q < cnt; q += warps) {
@@ -1526,6 +1537,7 @@ __global__ void __launch_bounds__(256) ccl_compress_kernel(const uint8_t* __rest
 template <int VEC>
 __global__ void __launch_bounds__(256) ccl_flatten_count_kernel(const uint8_t* __restrict__ mask, int* __restrict__ parent,
                                                                int w, int npx, CclList L, int* __restrict__ unit_cnt) {
+    pdl_entry();
     const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int cnt = *L.count;
     for (int q = gw; q < cnt; q += warps) {
@@ -1560,6 +1572,7 @@ __global__ void __launch_bounds__(256) ccl_flatten_count_kernel(const uint8_t* _
 // exclusive scan of the per-unit root counts, one block per frame; writes the total label count
 __global__ void __launch_bounds__(1024) ccl_scan_kernel(int* __restrict__ unit_cnt, int n_units, char* nlabels_base,
                                                        size_t nlabels_stride) {
+    pdl_entry();
     __shared__ int wtot[32];
     __shared__ int carry_s;
     int* c = unit_cnt + (size_t)blockIdx.x * n_units;
@@ -1611,6 +1624,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) ccl_rank_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ parent,
                                                       int w, int npx, CclList L, const int* __restrict__ unit_off,
                                                       int* __restrict__ rank) {
+    pdl_entry();
     const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int cnt = *L.count;
     for (int q = gw; q < cnt; q += warps) {
@@ -1635,6 +1649,7 @@ __global__ void __launch_bounds__(256) ccl_rank_kernel(const uint8_t* __restrict
 }
 
 __global__ void ccl_boxes_init_kernel(int32_t* boxes, size_t boxes_stride, int max_boxes, int n) {
+    pdl_entry();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * max_boxes) return;
     int f = i / max_boxes, b = i - f * max_boxes;
@@ -1670,6 +1685,7 @@ __global__ void __launch_bounds__(256) ccl_relabel_kernel(const uint8_t* __restr
                                                          const int* __restrict__ rank, int w, int npx, CclList L,
                                                          int* labels_out, int32_t* boxes,
                                                          size_t boxes_stride, int max_boxes) {
+    pdl_entry();
     const int warps = gridDim.x * 8, gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const int cnt = *L.count;
@@ -1749,6 +1765,7 @@ __global__ void __launch_bounds__(256) ccl_relabel_kernel(const uint8_t* __restr
 }
 
 __global__ void ccl_boxes_final_kernel(int32_t* boxes, size_t boxes_stride, int max_boxes, int n) {
+    pdl_entry();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * max_boxes) return;
     int f = i / max_boxes, b = i - f * max_boxes;
@@ -1764,8 +1781,19 @@ int* ccl_unit_marks(mavd_handle H) { return ccl_count_ptr(H) + 4; }
 int* ccl_unit_list(mavd_handle H) { return ccl_unit_marks(H) + (size_t)H->cfg.max_pairs * ccl_n_units(H); }
 int* ccl_unit_count(mavd_handle H) { return ccl_count_ptr(H); }
 
+// zeroes the list counter and the per-unit marks of n frames (a kernel, not a memset: it stays inside the chain of
+// programmatic dependent launches, common.cuh)
+__global__ void __launch_bounds__(256) ccl_list_reset_kernel(int* __restrict__ p, size_t n_ints) {
+    pdl_entry();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ints; i += stride) p[i] = 0;
+}
+
 int ccl_list_reset(mavd_handle H, int n, cudaStream_t s) {
-    MAVD_CUDA(cudaMemsetAsync(ccl_count_ptr(H), 0, sizeof(int) * (4 + (size_t)n * ccl_n_units(H)), s));
+    const size_t n_ints = 4 + (size_t)n * ccl_n_units(H);
+    const int blocks = (int)min((size_t)148 * 8, (n_ints + 255) / 256);
+    MAVD_CUDA(launch_chained(pdl_next(H), ccl_list_reset_kernel, blocks, 256, 0, s, ccl_count_ptr(H), n_ints));
+    MAVD_LAUNCHED();
     return MAVD_OK;
 }
 
@@ -1780,33 +1808,39 @@ static int ccl_launch(mavd_handle H, const uint8_t* d_mask, int n, int* parent, 
     CclList L{ccl_unit_list(H), ccl_unit_count(H), n_units};
     if (!list_ready) {
         TRY_RC(ccl_list_reset(H, n, s));
-        ccl_list_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, npx, n_units, n, ccl_unit_list(H), ccl_unit_count(H));
+        MAVD_CUDA(launch_chained(pdl_next(H), ccl_list_kernel<VEC>, CCL_GRID, 256, 0, s, d_mask, npx, n_units, n,
+                                 ccl_unit_list(H), ccl_unit_count(H)));
         MAVD_LAUNCHED();
     }
-    if (labels_out) MAVD_CUDA(cudaMemsetAsync(labels_out, 0, sizeof(int32_t) * (size_t)n * npx, s));
-    ccl_init_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, w, npx, L);
+    if (labels_out) {
+        MAVD_CUDA(cudaMemsetAsync(labels_out, 0, sizeof(int32_t) * (size_t)n * npx, s));
+        pdl_break(H);
+    }
+    MAVD_CUDA(launch_chained(pdl_next(H), ccl_init_kernel<VEC>, CCL_GRID, 256, 0, s, d_mask, parent, w, npx, L));
     MAVD_LAUNCHED();
-    ccl_merge_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, w, npx, L);
+    MAVD_CUDA(launch_chained(pdl_next(H), ccl_merge_kernel<VEC>, CCL_GRID, 256, 0, s, d_mask, parent, w, npx, L));
     MAVD_LAUNCHED();
-    ccl_compress_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, w, npx, L);
+    MAVD_CUDA(launch_chained(pdl_next(H), ccl_compress_kernel<VEC>, CCL_GRID, 256, 0, s, d_mask, parent, w, npx, L));
     MAVD_LAUNCHED();
-    ccl_flatten_count_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, w, npx, L, unit_cnt);
+    MAVD_CUDA(launch_chained(pdl_next(H), ccl_flatten_count_kernel<VEC>, CCL_GRID, 256, 0, s, d_mask, parent, w, npx, L, unit_cnt));
     MAVD_LAUNCHED();
-    ccl_scan_kernel<<<n, 1024, 0, s>>>(unit_cnt, n_units, (char*)d_n_labels, nlabels_stride);
+    MAVD_CUDA(launch_chained(pdl_next(H), ccl_scan_kernel, n, 1024, 0, s, unit_cnt, n_units, (char*)d_n_labels, nlabels_stride));
     MAVD_LAUNCHED();
-    ccl_rank_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, w, npx, L, unit_cnt, rank);
+    MAVD_CUDA(launch_chained(pdl_next(H), ccl_rank_kernel<VEC>, CCL_GRID, 256, 0, s, d_mask, parent, w, npx, L, unit_cnt, rank));
     MAVD_LAUNCHED();
     if (d_boxes) {
-        ccl_boxes_init_kernel<<<ceil_div(n * max_boxes, 128), 128, 0, s>>>(d_boxes, boxes_stride, max_boxes, n);
+        MAVD_CUDA(launch_chained(pdl_next(H), ccl_boxes_init_kernel, ceil_div(n * max_boxes, 128), 128, 0, s, d_boxes,
+                                 boxes_stride, max_boxes, n));
         MAVD_LAUNCHED();
     }
     if (d_boxes || labels_out) {
-        ccl_relabel_kernel<VEC><<<CCL_GRID, 256, 0, s>>>(d_mask, parent, rank, w, npx, L, labels_out, d_boxes,
-                                                          boxes_stride, max_boxes);
+        MAVD_CUDA(launch_chained(pdl_next(H), ccl_relabel_kernel<VEC>, CCL_GRID, 256, 0, s, d_mask, parent, rank, w, npx, L,
+                                 labels_out, d_boxes, boxes_stride, max_boxes));
         MAVD_LAUNCHED();
     }
     if (d_boxes) {
-        ccl_boxes_final_kernel<<<ceil_div(n * max_boxes, 128), 128, 0, s>>>(d_boxes, boxes_stride, max_boxes, n);
+        MAVD_CUDA(launch_chained(pdl_next(H), ccl_boxes_final_kernel, ceil_div(n * max_boxes, 128), 128, 0, s, d_boxes,
+                                 boxes_stride, max_boxes, n));
         MAVD_LAUNCHED();
     }
     return MAVD_OK;

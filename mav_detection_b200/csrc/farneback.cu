@@ -74,6 +74,7 @@ __device__ __forceinline__ float byte_to_float(uint32_t v, uint32_t selector) {
 
 __global__ void __launch_bounds__(256) pyr_vfirst_kernel(const uint8_t* __restrict__ frames, size_t frame_stride, int W,
                                                         int H, int Wp, int word_ok, const __grid_constant__ PyrDesc d) {
+    pdl_entry();
     int l = 0;
     while (l + 1 < d.n && (int)blockIdx.y >= d.lv[l + 1].row0) ++l;
     const PyrLevel& L = d.lv[l];
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(256) pyr_vfirst_kernel(const uint8_t* __restri
 }
 
 __global__ void __launch_bounds__(256) pyr_hsecond_kernel(int W, int Wp, int row_begin, const __grid_constant__ PyrDesc d) {
+    pdl_entry();
     const int by = blockIdx.y + row_begin;
     int l = 0;
     while (l + 1 < d.n && by >= d.lv[l + 1].row0) ++l;
@@ -165,6 +167,7 @@ constexpr int PYR_SPAN_PAD = PYR_SPAN_MAX + PYR_SPAN_MAX / 32 + 3;
 
 __global__ void __launch_bounds__(256) pyr_hsecond_staged_kernel(int W, int Wp, int row_begin,
                                                                 const __grid_constant__ PyrDesc d) {
+    pdl_entry();
     __shared__ float s_src[4][PYR_SPAN_PAD];
     const int by = blockIdx.y + row_begin;
     int l = 0;
@@ -324,6 +327,7 @@ template <bool U8, int N_>
 __global__ void __launch_bounds__(256, 4) polyexp_kernel(const void* __restrict__ src_base, size_t src_stride, int w,
                                                      int h, int pitch, int u8_aligned, PolyConst pc,
                                                      float* __restrict__ R, size_t plane) {
+    pdl_entry();
     __shared__ __align__(16) float raw[(PE_TY + 2 * PE_H) * PE_RW];
     __shared__ __align__(16) float t[3][PE_TY * PE_RW];
     const int tid = threadIdx.x;
@@ -533,6 +537,7 @@ __global__ void __launch_bounds__(256, 8) matrices_init_kernel(const float* __re
                                                            const float* __restrict__ fya, float up_scale,
                                                            float* __restrict__ M, double xscale, double yscale,
                                                            int txlog, int r0_first) {
+    pdl_entry();
     // 3-D grid (pairs, tiles_x, tiles_y): blocks are scheduled x-fastest, so the pair index is fastest (same L2 sharing
     // of R between consecutive pairs as in iter_box_tma_kernel) and no thread pays for an integer division: with one
     // pixel per thread the two divisions of a 1-D grid were 55 of the kernel's 400 instructions
@@ -649,6 +654,7 @@ __device__ __forceinline__ void hsum_gauss_reg(const float (&u)[20], const float
 
 template <bool GAUSS, bool LAST>
 __global__ void __launch_bounds__(256, 3) iter_kernel(IterArgs a) {
+    pdl_entry();
     extern __shared__ __align__(16) float smem[];
     const int m = a.m, hx = a.hx;
     const int RW = IT_TX + 2 * hx;          // staged columns
@@ -844,6 +850,7 @@ constexpr int PE_BW = 96;   // bytes per staged u8 row: x0 - 16 .. x0 + 79 (16-b
 template <bool U8, int N_>
 __global__ void __launch_bounds__(256, 4) polyexp_tma_kernel(const __grid_constant__ CUtensorMap tmap, int w, int h,
                                                          int pitch, PolyConst pc, float* __restrict__ R, size_t plane) {
+    pdl_entry();
     __shared__ __align__(128) float raw[(PE_TY + 2 * PE_H) * PE_RW];
     __shared__ __align__(128) float t[3][PE_TY * PE_RW];
     __shared__ __align__(8) uint64_t bar;
@@ -1079,6 +1086,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                                                                              const __grid_constant__ CUtensorMap tmapR,
                                                                              const __grid_constant__ CUtensorMap tmapRbox,
                                                                              IterArgs a) {
+    pdl_entry();
     constexpr int RW = IT_TX + 16;          // 80 staged columns (halo 8 each side, 16-byte aligned)
     constexpr int RH = TY + 2 * M_;      // staged rows
     constexpr int CH = RH * RW;             // floats per plane box
@@ -1430,19 +1438,20 @@ __global__ void tap_flow_kernel(const float2* __restrict__ src, int w, int h, in
 // host-side orchestration
 // ------------------------------------------------------------------------------------------------
 template <bool GAUSS, bool LAST>
-static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+static int launch_iter(const IterArgs& a, dim3 grid, size_t smem, cudaStream_t s, bool pdl) {
     MAVD_CUDA((ensure_dynamic_smem<iter_kernel<GAUSS, LAST>>(200 * 1024)));
-    iter_kernel<GAUSS, LAST><<<grid, 256, smem, s>>>(a);
+    MAVD_CUDA(launch_chained(pdl, iter_kernel<GAUSS, LAST>, grid, 256, smem, s, a));
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
 
 template <int M_, bool LAST, int NT, bool R1S, int FUSE = 0, int TY = IT_TY, bool GAUSS = false>
 static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, const CUtensorMap& mapRbox, const IterArgs& a,
-                           dim3 grid, cudaStream_t s) {
+                           dim3 grid, cudaStream_t s, bool pdl) {
     constexpr size_t smem = sizeof(float) * 5 * (TY + 2 * M_) * (IT_TX + 16);
     MAVD_CUDA((ensure_dynamic_smem<iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE, TY, GAUSS>>(smem)));
-    iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE, TY, GAUSS><<<grid, NT, smem, s>>>(map, mapR, mapRbox, a);
+    MAVD_CUDA(launch_chained(pdl, iter_box_tma_kernel<M_, LAST, NT, R1S, FUSE, TY, GAUSS>, grid, NT, smem, s, map, mapR,
+                             mapRbox, a));
     MAVD_LAUNCHED();
     return MAVD_OK;
 }
@@ -1450,7 +1459,7 @@ static int launch_iter_tma(const CUtensorMap& map, const CUtensorMap& mapR, cons
 template <bool LAST>
 static int launch_iter_tma_m(int m, const mavd_tuning& tune, bool small_tiles, const CUtensorMap& map,
                              const CUtensorMap& mapR, const CUtensorMap& mapRbox, const IterArgs& a, dim3 grid,
-                             cudaStream_t s) {
+                             cudaStream_t s, bool pdl) {
     // R1 staged in shared memory by a second TMA load: 4.36 vs 4.56 ms per 64-pair step (tuning.r1_staged)
     const bool r1s = tune.r1_staged != 0;
     // horizontal sums + solve in registers for the not-last iterations too, flow vectors handed to the update phase
@@ -1458,44 +1467,44 @@ static int launch_iter_tma_m(int m, const mavd_tuning& tune, bool small_tiles, c
     const int fuse = tune.iter_fuse;
     if (a.gk != nullptr) {  // Gaussian windows: production variants only (the caller checked the tuning), both tile heights
 #define GAUSS_CASE(M)                                                                                                        \
-        case M: return small_tiles ? launch_iter_tma<M, LAST, 256, !LAST, LAST ? 0 : 1, 16, true>(map, mapR, mapRbox, a, grid, s) \
-                                   : launch_iter_tma<M, LAST, 256, !LAST, LAST ? 0 : 1, IT_TY, true>(map, mapR, mapRbox, a, grid, s);
+        case M: return small_tiles ? launch_iter_tma<M, LAST, 256, !LAST, LAST ? 0 : 1, 16, true>(map, mapR, mapRbox, a, grid, s, pdl) \
+                                   : launch_iter_tma<M, LAST, 256, !LAST, LAST ? 0 : 1, IT_TY, true>(map, mapR, mapRbox, a, grid, s, pdl);
         switch (m) {
             GAUSS_CASE(5) GAUSS_CASE(6) GAUSS_CASE(7)
-            default: return small_tiles ? launch_iter_tma<8, LAST, 256, !LAST, LAST ? 0 : 1, 16, true>(map, mapR, mapRbox, a, grid, s)
-                                        : launch_iter_tma<8, LAST, 256, !LAST, LAST ? 0 : 1, IT_TY, true>(map, mapR, mapRbox, a, grid, s);
+            default: return small_tiles ? launch_iter_tma<8, LAST, 256, !LAST, LAST ? 0 : 1, 16, true>(map, mapR, mapRbox, a, grid, s, pdl)
+                                        : launch_iter_tma<8, LAST, 256, !LAST, LAST ? 0 : 1, IT_TY, true>(map, mapR, mapRbox, a, grid, s, pdl);
         }
 #undef GAUSS_CASE
     }
     if (small_tiles) {      // 64 x 16 tiles (the caller built `grid` and the descriptors for them): production variants only
         switch (m) {
-            case 5: return launch_iter_tma<5, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s);
-            case 6: return launch_iter_tma<6, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s);
-            case 7: return launch_iter_tma<7, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s);
-            default: return launch_iter_tma<8, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s);
+            case 5: return launch_iter_tma<5, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s, pdl);
+            case 6: return launch_iter_tma<6, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s, pdl);
+            case 7: return launch_iter_tma<7, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s, pdl);
+            default: return launch_iter_tma<8, LAST, 256, !LAST, LAST ? 0 : 1, 16>(map, mapR, mapRbox, a, grid, s, pdl);
         }
     }
     if (r1s && !LAST && fuse != 0) {
         switch (m) {
-            case 5: return launch_iter_tma<5, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
-            case 6: return launch_iter_tma<6, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
-            case 7: return launch_iter_tma<7, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
-            default: return launch_iter_tma<8, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s);
+            case 5: return launch_iter_tma<5, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s, pdl);
+            case 6: return launch_iter_tma<6, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s, pdl);
+            case 7: return launch_iter_tma<7, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s, pdl);
+            default: return launch_iter_tma<8, false, 256, true, 1>(map, mapR, mapRbox, a, grid, s, pdl);
         }
     }
     if (r1s && !LAST) {
         switch (m) {
-            case 5: return launch_iter_tma<5, LAST, 256, true>(map, mapR, mapRbox, a, grid, s);
-            case 6: return launch_iter_tma<6, LAST, 256, true>(map, mapR, mapRbox, a, grid, s);
-            case 7: return launch_iter_tma<7, LAST, 256, true>(map, mapR, mapRbox, a, grid, s);
-            default: return launch_iter_tma<8, LAST, 256, true>(map, mapR, mapRbox, a, grid, s);
+            case 5: return launch_iter_tma<5, LAST, 256, true>(map, mapR, mapRbox, a, grid, s, pdl);
+            case 6: return launch_iter_tma<6, LAST, 256, true>(map, mapR, mapRbox, a, grid, s, pdl);
+            case 7: return launch_iter_tma<7, LAST, 256, true>(map, mapR, mapRbox, a, grid, s, pdl);
+            default: return launch_iter_tma<8, LAST, 256, true>(map, mapR, mapRbox, a, grid, s, pdl);
         }
     }
     switch (m) {
-        case 5: return launch_iter_tma<5, LAST, 256, false>(map, mapR, mapRbox, a, grid, s);
-        case 6: return launch_iter_tma<6, LAST, 256, false>(map, mapR, mapRbox, a, grid, s);
-        case 7: return launch_iter_tma<7, LAST, 256, false>(map, mapR, mapRbox, a, grid, s);
-        default: return launch_iter_tma<8, LAST, 256, false>(map, mapR, mapRbox, a, grid, s);
+        case 5: return launch_iter_tma<5, LAST, 256, false>(map, mapR, mapRbox, a, grid, s, pdl);
+        case 6: return launch_iter_tma<6, LAST, 256, false>(map, mapR, mapRbox, a, grid, s, pdl);
+        case 7: return launch_iter_tma<7, LAST, 256, false>(map, mapR, mapRbox, a, grid, s, pdl);
+        default: return launch_iter_tma<8, LAST, 256, false>(map, mapR, mapRbox, a, grid, s, pdl);
     }
 }
 
@@ -1511,6 +1520,10 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
 
     // pyramid images of every coarser level for all frames: two launches
     // pyramid images of levels lo..hi (1 <= lo <= hi) for all frames: two launches
+    // programmatic dependent launch: lane 0 = the caller's stream, lane 1 = the side stream (common.cuh: pdl_next)
+    auto lane = [&](cudaStream_t st) { return (st == H->s_aux && st != s) ? 1 : 0; };
+    pdl_break(H, 0);
+    pdl_break(H, 1);
     auto build_pyramid = [&](cudaStream_t st, int lo, int hi) -> int {
         if (H->n_levels <= 1 || lo > hi) return MAVD_OK;
         ProfScope ps(&H->prof, MAVD_PROF_PYRAMID, st);
@@ -1534,7 +1547,8 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         }
         MAVD_REQUIRE(rows <= 65535 && n_frames <= 65535, MAVD_ERR_UNSUPPORTED, "pyramid: grid too large");
         const int word_ok = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) ? 1 : 0;
-        pyr_vfirst_kernel<<<dim3(ceil_div(W, 256), rows, n_frames), 256, 0, st>>>(d_frames, frame_bytes, W, Hh, Wp, word_ok, d);
+        MAVD_CUDA(launch_chained(pdl_next(H, lane(st)), pyr_vfirst_kernel, dim3(ceil_div(W, 256), rows, n_frames), 256, 0, st,
+                                 d_frames, frame_bytes, W, Hh, Wp, word_ok, d));
         MAVD_LAUNCHED();
         // levels whose outputs are >= 8 source samples apart go through the shared-memory variant: one launch per run
         // of consecutive levels of the same kind (normally two: the fine levels direct, the coarse tail staged)
@@ -1542,8 +1556,8 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             int a1 = a0, hx = 0;
             while (a1 < d.n && d.lv[a1].staged == d.lv[a0].staged) { hx = max(hx, d.lv[a1].htiles_x); ++a1; }
             const int r0 = d.lv[a0].row0, r1 = a1 < d.n ? d.lv[a1].row0 : rows;
-            if (d.lv[a0].staged) pyr_hsecond_staged_kernel<<<dim3(hx, r1 - r0, n_frames), 256, 0, st>>>(W, Wp, r0, d);
-            else pyr_hsecond_kernel<<<dim3(hx, r1 - r0, n_frames), 256, 0, st>>>(W, Wp, r0, d);
+            MAVD_CUDA(launch_chained(pdl_next(H, lane(st)), d.lv[a0].staged ? pyr_hsecond_staged_kernel : pyr_hsecond_kernel,
+                                     dim3(hx, r1 - r0, n_frames), 256, 0, st, W, Wp, r0, d));
             MAVD_LAUNCHED();
             a0 = a1;
         }
@@ -1569,16 +1583,21 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
                                                             (uint32_t)(PE_TY + 2 * H->poly.n + 2), 1u);
         else if (use_tma)
             use_tma = L.has_tmap_img;
+        const bool pdl = pdl_next(H, lane(st));
 #define PE_LAUNCH(N)                                                                                                   \
         do {                                                                                                           \
-            if (li == 0 && use_tma) polyexp_tma_kernel<true, N><<<g, 256, 0, st>>>(tmap_u8, L.w, L.h, L.pitch, H->poly, \
-                                                                                   L.R, L.plane);                       \
-            else if (li == 0) polyexp_kernel<true, N><<<g, 256, 0, st>>>(d_frames, frame_bytes, L.w, L.h, L.pitch,      \
-                                                                         aligned, H->poly, L.R, L.plane);              \
-            else if (use_tma) polyexp_tma_kernel<false, N><<<g, 256, 0, st>>>(L.tmapImg, L.w, L.h, L.pitch, H->poly,    \
-                                                                              L.R, L.plane);                           \
-            else polyexp_kernel<false, N><<<g, 256, 0, st>>>(L.img, L.plane, L.w, L.h, L.pitch, 0, H->poly, L.R,       \
-                                                             L.plane);                                                 \
+            if (li == 0 && use_tma)                                                                                    \
+                MAVD_CUDA(launch_chained(pdl, polyexp_tma_kernel<true, N>, g, 256, 0, st, tmap_u8, L.w, L.h, L.pitch,   \
+                                         H->poly, L.R, L.plane));                                                      \
+            else if (li == 0)                                                                                          \
+                MAVD_CUDA(launch_chained(pdl, polyexp_kernel<true, N>, g, 256, 0, st, (const void*)d_frames,            \
+                                         frame_bytes, L.w, L.h, L.pitch, aligned, H->poly, L.R, L.plane));              \
+            else if (use_tma)                                                                                          \
+                MAVD_CUDA(launch_chained(pdl, polyexp_tma_kernel<false, N>, g, 256, 0, st, L.tmapImg, L.w, L.h,         \
+                                         L.pitch, H->poly, L.R, L.plane));                                             \
+            else                                                                                                       \
+                MAVD_CUDA(launch_chained(pdl, polyexp_kernel<false, N>, g, 256, 0, st, (const void*)L.img, L.plane,     \
+                                         L.w, L.h, L.pitch, 0, H->poly, L.R, L.plane));                                \
         } while (0)
         switch (H->poly.n) {
             case 5: PE_LAUNCH(5); break;
@@ -1608,9 +1627,10 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
 #define MI_ARGS L.R, L.plane, L.w, L.h, L.pitch, (size_t)pair_stride * 5 * L.plane,                                     \
                 top ? nullptr : (const float2*)C->flow, top ? 0 : C->w, top ? 0 : C->h, top ? 0 : C->pitch,             \
                 top ? 0 : C->plane, L.fxi0, L.fxa, L.fyi0, L.fya, (float)(1.0 / fp.pyr_scale), L.M[0], xscale, yscale, txlog, r0_first
-            if (coord == MI_COORD_TABLES) matrices_init_kernel<MI_COORD_TABLES><<<g3, 256, 0, st>>>(MI_ARGS);
-            else if (coord == MI_COORD_POW2) matrices_init_kernel<MI_COORD_POW2><<<g3, 256, 0, st>>>(MI_ARGS);
-            else matrices_init_kernel<MI_COORD_F64><<<g3, 256, 0, st>>>(MI_ARGS);
+            const bool pdl = pdl_next(H, lane(st));
+            if (coord == MI_COORD_TABLES) MAVD_CUDA(launch_chained(pdl, matrices_init_kernel<MI_COORD_TABLES>, g3, 256, 0, st, MI_ARGS));
+            else if (coord == MI_COORD_POW2) MAVD_CUDA(launch_chained(pdl, matrices_init_kernel<MI_COORD_POW2>, g3, 256, 0, st, MI_ARGS));
+            else MAVD_CUDA(launch_chained(pdl, matrices_init_kernel<MI_COORD_F64>, g3, 256, 0, st, MI_ARGS));
 #undef MI_ARGS
             MAVD_LAUNCHED();
         }
@@ -1650,16 +1670,17 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             const size_t smem = sizeof(float) * ((size_t)RH * RW + (size_t)IT_TY * RW + 5 * IT_TX * IT_TY);
             ProfScope ps(&H->prof, li > 0 ? MAVD_PROF_ITER_COARSE : (last ? MAVD_PROF_ITER_FULL_LAST : MAVD_PROF_ITER_FULL), st);
             int rc;
+            const bool pdl = pdl_next(H, lane(st));
             // Gaussian windows use the TMA kernel's production variants (R1 staged, sums in registers) only
             const bool prod = H->tune.r1_staged != 0 && H->tune.iter_fuse != 0 && H->tune.last_fused != 0;
             if ((!gauss || prod) && m >= 5 && m <= 8 && L.has_tmap && !H->force_generic_iter) {
                 const CUtensorMap& mM = small_tiles ? L.tmapM16[cur] : L.tmapM[cur];
                 const CUtensorMap& mRb = small_tiles ? L.tmapRbox16 : L.tmapRbox;
-                rc = last ? launch_iter_tma_m<true>(m, H->tune, small_tiles, mM, L.tmapR, mRb, a, g1, st)
-                          : launch_iter_tma_m<false>(m, H->tune, small_tiles, mM, L.tmapR, mRb, a, g1, st);
+                rc = last ? launch_iter_tma_m<true>(m, H->tune, small_tiles, mM, L.tmapR, mRb, a, g1, st, pdl)
+                          : launch_iter_tma_m<false>(m, H->tune, small_tiles, mM, L.tmapR, mRb, a, g1, st, pdl);
             }
-            else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, st) : launch_iter<true, false>(a, g, smem, st);
-            else       rc = last ? launch_iter<false, true>(a, g, smem, st) : launch_iter<false, false>(a, g, smem, st);
+            else if (gauss) rc = last ? launch_iter<true, true>(a, g, smem, st, pdl) : launch_iter<true, false>(a, g, smem, st, pdl);
+            else       rc = last ? launch_iter<false, true>(a, g, smem, st, pdl) : launch_iter<false, false>(a, g, smem, st, pdl);
             if (rc != MAVD_OK) return rc;
             if (!last) cur ^= 1;
         }
@@ -1677,6 +1698,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         // the pyramid too goes to the side stream: level 0's expansion reads only the u8 frames
         MAVD_CUDA(cudaEventRecord(H->ev_fork, s));
         MAVD_CUDA(cudaStreamWaitEvent(H->s_aux, H->ev_fork, 0));
+        pdl_break(H, lane(H->s_aux));
         TRY_RC(build_pyramid(H->s_aux, 1, top_level));
         MAVD_CUDA(cudaEventRecord(H->ev_pyr, H->s_aux));
         for (int li = H->n_levels - 1; li >= 2; --li) {
@@ -1686,14 +1708,17 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         MAVD_CUDA(cudaEventRecord(H->ev_join, H->s_aux));
         TRY_RC(expand_level(0, s));
         MAVD_CUDA(cudaStreamWaitEvent(s, H->ev_pyr, 0));
+        pdl_break(H, lane(s));
         TRY_RC(expand_level(1, s));
         MAVD_CUDA(cudaStreamWaitEvent(s, H->ev_join, 0));
+        pdl_break(H, lane(s));
         TRY_RC(solve_level(1, s));
         TRY_RC(solve_level(0, s));
     } else if (fork) {
         TRY_RC(build_pyramid(s, 1, top_level));
         MAVD_CUDA(cudaEventRecord(H->ev_fork, s));
         MAVD_CUDA(cudaStreamWaitEvent(H->s_aux, H->ev_fork, 0));
+        pdl_break(H, lane(H->s_aux));
         for (int li = H->n_levels - 1; li >= 2; --li) {
             TRY_RC(expand_level(li, H->s_aux));
             TRY_RC(solve_level(li, H->s_aux));
@@ -1702,6 +1727,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         TRY_RC(expand_level(1, s));
         TRY_RC(expand_level(0, s));
         MAVD_CUDA(cudaStreamWaitEvent(s, H->ev_join, 0));
+        pdl_break(H, lane(s));
         TRY_RC(solve_level(1, s));
         TRY_RC(solve_level(0, s));
     } else {

@@ -512,6 +512,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.mavd_launch_count())
 
+    def graph_stats(self) -> Dict[str, int]:
+        """Launch sequences held by the handle: replayed as CUDA graphs / run kernel by kernel (capture failed)."""
+        a, b = C.c_int32(), C.c_int32()
+        check(self.lib.mavd_graph_stats(self._h, C.byref(a), C.byref(b)))
+        return {'captured': a.value, 'direct': b.value}
+
 
 _SHARED: Dict[tuple, 'Engine'] = {}
 

@@ -284,10 +284,38 @@ def test_graph_replay_equals_direct_launches():
     # buffers differ from call to call in _run_device (fresh tensors): each is its own graph; the launch counter counts
     # the replayed kernels too
     assert eng.launch_count() - before > 20
+    # every sequence was captured and instantiated (programmatic dependent launches included): nothing fell back
+    assert eng.get_tuning()['use_pdl'] == 1
+    gs = eng.graph_stats()
+    assert gs['captured'] >= 1 and gs['direct'] == 0, gs
     eng.set_tuning(pair_group=2, overlap=0, iter_fuse=0, last_fused=0, mat_txlog=5)    # other launch shapes, same results
     flow3, fixed3, rec3 = _run_device(eng, seq, n, samples)
     assert np.array_equal(flow3, flow0) and np.array_equal(fixed3, fixed0)
     assert direct_launches > 20
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('graph', [0, 1])
+def test_programmatic_dependent_launch_changes_nothing(graph):
+    """tuning.use_pdl: kernels made resident behind their predecessor (griddepcontrol) wait for its completion before
+    they touch memory — flows, masks and records are bit-equal to the fully serialised launches, kernel by kernel and
+    inside captured graphs, over repeated calls (a kernel released too early would read a half-written field)."""
+    from mav_detection_b200 import engine, sharded, synth
+    W, H, n = 640, 480, 6
+    seq = synth.make_sequence(W, H, n + 1, seq=23, with_rotation=True)
+    samples = _samples(n, H, W, 41)
+    eng = engine.Engine(W, H, engine.SAMPLE_PARAMS, max_pairs=n)
+    eng.set_tuning(use_pdl=0, use_graph=graph)
+    flow0, fixed0, rec0 = _run_device(eng, seq, n, samples)
+    eng.set_tuning(use_pdl=1, use_graph=graph)
+    for trial in range(4):
+        flow1, fixed1, rec1 = _run_device(eng, seq, n, samples)
+        assert np.array_equal(flow1, flow0) and np.array_equal(fixed1, fixed0), trial
+        assert sharded.compare_records(rec1, rec0) == [], trial
+    if graph:
+        gs = eng.graph_stats()
+        assert gs['captured'] >= 1 and gs['direct'] == 0, gs
     eng.close()
 
 
