@@ -114,7 +114,9 @@ typedef struct mavd_tuning {
     int32_t use_pdl;      /* programmatic dependent launch: every kernel of the batch is set up while its predecessor
                              on the stream drains and waits for it with griddepcontrol.wait, so launch latency and
                              the ramp of the first wave leave the critical path (default 1) */
-    int32_t reserved[3];
+    int32_t pyr_sweep;    /* pyramid: exact power-of-two levels (pyr_scale 0.5) through the sweep / vectorised kernels;
+                             0 = off, 1 = on with an automatic band count (default), n >= 2 = on with n bands */
+    int32_t reserved[2];
 } mavd_tuning;
 
 /* Optional per-frame inputs of the detection stages.  All pointers are DEVICE pointers for the d_ entry points and

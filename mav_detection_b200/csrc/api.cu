@@ -347,6 +347,18 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
                         tab[(size_t)d * taps + j] = (1.f - a[d]) * k0 + a[d] * k1;
                     }
                 }
+                {
+                    // pyr_scale 0.5 with src = dst * 2^li: the level is an exact decimation (farneback.cu: HalfPyr)
+                    static const int kT[5] = {0, 4, 10, 20, 40}, kNB[5] = {0, 1, 3, 6, 12};
+                    bool half = li <= 4 && L.ksz + 1 == kT[std::min(li, 4)] && dst >= 1 && src == dst << li;
+                    for (int d = 0; half && d < dst; ++d) {
+                        half = base[d] == (d << li) - kNB[li];
+                        for (int j = 0; half && j < taps; ++j) half = tab[(size_t)d * taps + j] == tab[j];
+                    }
+                    for (int j = kT[std::min(li, 4)]; half && j < taps; ++j) half = tab[j] == 0.f;
+                    (axis == 0 ? L.x_half : L.y_half) = half;
+                    if (half) std::copy(tab.begin(), tab.begin() + kT[li], axis == 0 ? L.xwt : L.ywt);
+                }
                 if (axis == 0) {
                     C_TRY(A.upload(&L.xbase, base)); C_TRY(A.upload(&L.xtab, tab));
                     std::vector<float> tabT((size_t)dst * taps);
@@ -500,6 +512,7 @@ void mavd_default_tuning(mavd_tuning* t) {
     t->polyexp_tma = 1;
     t->iter_small_tiles = 1;
     t->use_pdl = 1;
+    t->pyr_sweep = 1;
 }
 
 int mavd_set_tuning(mavd_handle h, const mavd_tuning* t) {

@@ -132,6 +132,10 @@ struct Level {
     int hstride_min = 0;                            // smallest distance between the sources of adjacent outputs
     int* ybase = nullptr;  float* ytab = nullptr;   // [h], [h][ksz+1]
     float* tmp = nullptr;                           // [frames][h][Wp] vertical pass output (levels >= 1)
+    // exact power-of-two level (farneback.cu: HalfPyr): every output sample has the same ksz + 1 weights and its window
+    // starts 2^k samples after its neighbour's; host copies of those weights for the kernels that exploit it
+    bool x_half = false, y_half = false;
+    float xwt[40] = {}, ywt[40] = {};
     // flow upsample tables (next-coarser level -> this level)
     int* fxi0 = nullptr; float* fxa = nullptr;  // [w]
     int* fyi0 = nullptr; float* fya = nullptr;  // [h]

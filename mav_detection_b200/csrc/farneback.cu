@@ -205,6 +205,146 @@ __global__ void __launch_bounds__(256) pyr_hsecond_staged_kernel(int W, int Wp, 
     L.img[(size_t)blockIdx.z * L.img_stride + (size_t)dy * L.pitch + dx] = acc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Exact power-of-two levels (pyr_scale 0.5, frame size divisible by 2^l; api.cu checks the tables): every output
+// sample of level l has the SAME T = ksz + 1 weights and its window starts S = 2^l samples after its neighbour's,
+// at S * d - NB.  The generic kernels above do not know that: they convert every u8 sample once per tap that uses it
+// (2.5 times per level) and spend most of their instructions finding their level and their table rows.
+//   pyr_vsweep   vertical pass of levels 1..NLV in ONE sweep down the frame: thread = 4 adjacent columns (one 32-bit
+//                word per row, coalesced), each row is loaded and converted once and added to the <= 3 live output
+//                rows of every level (polyphase decimation: the tap index of (row, live output) is a compile-time
+//                constant, the weight a constant-bank operand of the FFMA); a finished output row is stored and its
+//                accumulator starts the next one.  11 instead of ~50 instructions per source sample.
+//   pyr_hpass    horizontal pass of level 1 or 2: thread = 4 adjacent outputs of one row, source span read as float4
+// Per output sample the products are accumulated in the same tap order with the same FMAs as in the generic kernels:
+// the images are bit-identical (test_pyramid_sweep_is_bit_identical).
+// ------------------------------------------------------------------------------------------------
+struct HalfPyr {    // level l = 1..4: stride, taps, -(window start of output 0), live outputs per source row
+    __host__ __device__ static constexpr int S(int l) { return 1 << l; }
+    __host__ __device__ static constexpr int T(int l) { return l == 1 ? 4 : l == 2 ? 10 : l == 3 ? 20 : 40; }
+    __host__ __device__ static constexpr int NB(int l) { return l == 1 ? 1 : l == 2 ? 3 : l == 3 ? 6 : 12; }
+    __host__ __device__ static constexpr int K(int l) { return (T(l) + S(l) - 1) / S(l); }
+};
+constexpr int VS_MAXLV = 4, VS_MAXT = 40;
+struct VSweepDesc {
+    float* tmp[VS_MAXLV];
+    size_t tmp_stride[VS_MAXLV];   // floats per frame
+    int h[VS_MAXLV];
+    float w[VS_MAXLV][VS_MAXT];
+    int band_rows;                 // output rows of level NLV per band (grid.y)
+};
+
+template <int NLV>
+__global__ void __launch_bounds__(192) pyr_vsweep_kernel(const uint8_t* __restrict__ frames, size_t frame_stride, int W,
+                                                        int H, int Wp, const __grid_constant__ VSweepDesc d) {
+    pdl_entry();
+    constexpr int U = 1 << NLV;      // source rows per unrolled step = stride of the coarsest swept level
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= W) return;
+    const uint8_t* src = frames + (size_t)blockIdx.z * frame_stride + x;
+    const int D0 = blockIdx.y * d.band_rows, D1 = min(D0 + d.band_rows, d.h[NLV - 1]);
+    float acc[NLV][3][4];
+#pragma unroll
+    for (int l = 0; l < NLV; ++l)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[l][k][c] = 0.f;
+    // the window of output D0 of level l starts at U * D0 - NB(l) >= U * (D0 - 1); that of output D1 - 1 ends before
+    // U * (D1 + 2): steps q = D0 - 1 .. D1 + 1.  Outputs outside the band (their sums are incomplete) are not stored.
+#pragma unroll 1
+    for (int q = D0 - 1; q <= D1 + 1; ++q) {
+        const int r0 = q * U;
+        uint32_t wv[U];
+        if (r0 >= 0 && r0 + U <= H) {
+            const uint8_t* p = src + (size_t)r0 * W;
+#pragma unroll
+            for (int i = 0; i < U; ++i) wv[i] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)i * W));
+        } else {
+#pragma unroll
+            for (int i = 0; i < U; ++i)
+                wv[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)reflect101(r0 + i, H) * W));
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            const float v[4] = {byte_to_float(wv[i], 0x7540u), byte_to_float(wv[i], 0x7541u),
+                                byte_to_float(wv[i], 0x7542u), byte_to_float(wv[i], 0x7543u)};
+#pragma unroll
+            for (int l = 1; l <= NLV; ++l) {
+                const int S = HalfPyr::S(l), T = HalfPyr::T(l), NB = HalfPyr::NB(l), K = HalfPyr::K(l);
+                const int ph = (i + NB) % S;                 // row r0 + i is tap ph + k S of the k-th newest output
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k < K && ph + k * S < T) {
+                        const float wt = d.w[l - 1][ph + k * S];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[l - 1][k][c] = fmaf(wt, v[c], acc[l - 1][k][c]);
+                    }
+                if (ph == S - 1) {
+                    // the oldest live output is complete: index = newest - (K - 1)
+                    const int dn = (U / S) * q + (i + NB) / S - (K - 1);
+                    if (dn >= D0 * (U / S) && dn < min(D1 * (U / S), d.h[l - 1])) {
+                        float* out = d.tmp[l - 1] + (size_t)blockIdx.z * d.tmp_stride[l - 1] + (size_t)dn * Wp + x;
+                        *reinterpret_cast<float4*>(out) = make_float4(acc[l - 1][K - 1][0], acc[l - 1][K - 1][1],
+                                                                     acc[l - 1][K - 1][2], acc[l - 1][K - 1][3]);
+                    }
+#pragma unroll
+                    for (int k = 2; k >= 1; --k)
+                        if (k < K) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) acc[l - 1][k][c] = acc[l - 1][k - 1][c];
+                        }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[l - 1][0][c] = 0.f;
+                }
+            }
+        }
+    }
+}
+
+struct HPassW { float w[VS_MAXT]; };
+
+template <int LV>
+__global__ void __launch_bounds__(128) pyr_hpass_kernel(const float* __restrict__ tmp, size_t tmp_stride, int W, int Wp,
+                                                       int wl, float* __restrict__ img, size_t img_stride, int pitch,
+                                                       const __grid_constant__ HPassW wts) {
+    pdl_entry();
+    constexpr int S = HalfPyr::S(LV), T = HalfPyr::T(LV), NB = HalfPyr::NB(LV);
+    constexpr int OFF = (4 - NB % 4) % 4;               // the window of output x starts OFF floats into a 16-byte group
+    constexpr int NV = (OFF + 3 * S + T + 3) / 4;       // float4 groups that hold the windows of 4 adjacent outputs
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x >= wl) return;
+    const float* row = tmp + (size_t)blockIdx.z * tmp_stride + (size_t)y * Wp;
+    const int a0 = S * x - NB - OFF;                    // a multiple of 4
+    float u[4 * NV];
+    if (a0 >= 0 && a0 + 4 * NV <= W) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(row + a0) + j);
+            u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4 * NV; ++e) u[e] = row[reflect101(a0 + e, W)];
+    }
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < T; ++j) acc = fmaf(wts.w[j], u[OFF + k * S + j], acc);
+        o[k] = acc;
+    }
+    float* dst = img + (size_t)blockIdx.z * img_stride + (size_t)y * pitch + x;
+    if (x + 4 <= wl) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x + k < wl) dst[k] = o[k];
+    }
+}
+
 // level-0 image on its own (tests / taps only): 3x3 [1/4 1/2 1/4] blur of the u8 frame, REFLECT_101
 __global__ void pyr0_kernel(const uint8_t* __restrict__ frame, int W, int H, float* __restrict__ img, int pitch) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -1528,38 +1668,101 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         if (H->n_levels <= 1 || lo > hi) return MAVD_OK;
         ProfScope ps(&H->prof, MAVD_PROF_PYRAMID, st);
         const int Wp = round_up(W, 4);
-        PyrDesc d;
-        d.n = hi - lo + 1;
         const bool pyr_staged_env = H->tune.pyr_staged != 0;
-        int rows = 0, hx_max = 1;
-        for (int li = lo; li <= hi; ++li) {
-            const Level& L = H->lv[li];
-            PyrLevel& P = d.lv[li - lo];
-            P.w = L.w; P.h = L.h; P.pitch = L.pitch; P.taps = round_up(L.ksz + 1, 4);
-            P.xbase = L.xbase; P.xtab = L.xtab; P.ybase = L.ybase; P.ytab = L.ytab;
-            P.tmp = L.tmp; P.img = L.img; P.tmp_stride = (size_t)L.h * Wp; P.img_stride = L.plane;
-            P.xtabT = L.xtabT;
-            P.staged = (pyr_staged_env && L.hspan_max <= PYR_SPAN_MAX && L.hstride_min >= 8) ? 1 : 0;
-            P.row0 = rows;
-            rows += ceil_div(L.h, 4);
-            P.htiles_x = ceil_div(L.w, 64);
-            hx_max = max(hx_max, P.htiles_x);
-        }
-        MAVD_REQUIRE(rows <= 65535 && n_frames <= 65535, MAVD_ERR_UNSUPPORTED, "pyramid: grid too large");
         const int word_ok = ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) ? 1 : 0;
-        MAVD_CUDA(launch_chained(pdl_next(H, lane(st)), pyr_vfirst_kernel, dim3(ceil_div(W, 256), rows, n_frames), 256, 0, st,
-                                 d_frames, frame_bytes, W, Hh, Wp, word_ok, d));
-        MAVD_LAUNCHED();
-        // levels whose outputs are >= 8 source samples apart go through the shared-memory variant: one launch per run
-        // of consecutive levels of the same kind (normally two: the fine levels direct, the coarse tail staged)
-        for (int a0 = 0; a0 < d.n;) {
-            int a1 = a0, hx = 0;
-            while (a1 < d.n && d.lv[a1].staged == d.lv[a0].staged) { hx = max(hx, d.lv[a1].htiles_x); ++a1; }
-            const int r0 = d.lv[a0].row0, r1 = a1 < d.n ? d.lv[a1].row0 : rows;
-            MAVD_CUDA(launch_chained(pdl_next(H, lane(st)), d.lv[a0].staged ? pyr_hsecond_staged_kernel : pyr_hsecond_kernel,
-                                     dim3(hx, r1 - r0, n_frames), 256, 0, st, W, Wp, r0, d));
+        // descriptor of levels a..b for the generic kernels
+        auto make_desc = [&](int a, int b, PyrDesc& d, int& rows) {
+            d.n = b - a + 1;
+            rows = 0;
+            for (int li = a; li <= b; ++li) {
+                const Level& L = H->lv[li];
+                PyrLevel& P = d.lv[li - a];
+                P.w = L.w; P.h = L.h; P.pitch = L.pitch; P.taps = round_up(L.ksz + 1, 4);
+                P.xbase = L.xbase; P.xtab = L.xtab; P.ybase = L.ybase; P.ytab = L.ytab;
+                P.tmp = L.tmp; P.img = L.img; P.tmp_stride = (size_t)L.h * Wp; P.img_stride = L.plane;
+                P.xtabT = L.xtabT;
+                P.staged = (pyr_staged_env && L.hspan_max <= PYR_SPAN_MAX && L.hstride_min >= 8) ? 1 : 0;
+                P.row0 = rows;
+                rows += ceil_div(L.h, 4);
+                P.htiles_x = ceil_div(L.w, 64);
+            }
+        };
+        // exact power-of-two levels (leading levels of a pyr_scale 0.5 pyramid): one sweep down the frame does their
+        // vertical passes, level 1 and 2 get the vectorised horizontal pass (tuning.pyr_sweep; HalfPyr above)
+        int nv = 0, nh = 0;
+        if (H->tune.pyr_sweep != 0 && lo == 1 && word_ok) {
+            while (nv < VS_MAXLV && 1 + nv <= hi && H->lv[1 + nv].y_half) ++nv;
+            while (nh < 2 && 1 + nh <= hi && H->lv[1 + nh].x_half) ++nh;
+        }
+        MAVD_REQUIRE(n_frames <= 65535, MAVD_ERR_UNSUPPORTED, "pyramid: grid too large");
+        if (nv > 0) {
+            VSweepDesc vd;
+            memset(&vd, 0, sizeof(vd));
+            for (int l = 0; l < nv; ++l) {
+                const Level& L = H->lv[1 + l];
+                vd.tmp[l] = L.tmp; vd.tmp_stride[l] = (size_t)L.h * Wp; vd.h[l] = L.h;
+                memcpy(vd.w[l], L.ywt, sizeof(float) * VS_MAXT);
+            }
+            const int words = W / 4, h_top = H->lv[nv].h;
+            // bands: enough threads to fill the GPU; each band sweeps 3 steps more than it owns
+            int nb = H->tune.pyr_sweep >= 2 ? H->tune.pyr_sweep
+                                            : ceil_div(148 * 768, max(1, words * n_frames));
+            nb = max(1, min(nb, max(1, h_top / 4)));
+            vd.band_rows = ceil_div(h_top, nb);
+            nb = ceil_div(h_top, vd.band_rows);
+            int tb = 128, waste = 1 << 30;
+            for (int cand : {192, 160, 128, 96, 64}) {
+                const int wst = ceil_div(words, cand) * cand - words;
+                if (wst < waste) { waste = wst; tb = cand; }
+            }
+            const dim3 g(ceil_div(words, tb), nb, n_frames);
+            const bool pdl = pdl_next(H, lane(st));
+            switch (nv) {
+                case 1: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<1>, g, tb, 0, st, d_frames, frame_bytes, W, Hh, Wp, vd)); break;
+                case 2: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<2>, g, tb, 0, st, d_frames, frame_bytes, W, Hh, Wp, vd)); break;
+                case 3: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<3>, g, tb, 0, st, d_frames, frame_bytes, W, Hh, Wp, vd)); break;
+                default: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<4>, g, tb, 0, st, d_frames, frame_bytes, W, Hh, Wp, vd)); break;
+            }
             MAVD_LAUNCHED();
-            a0 = a1;
+        }
+        if (lo + nv <= hi) {
+            PyrDesc d;
+            int rows = 0;
+            make_desc(lo + nv, hi, d, rows);
+            MAVD_REQUIRE(rows <= 65535, MAVD_ERR_UNSUPPORTED, "pyramid: grid too large");
+            MAVD_CUDA(launch_chained(pdl_next(H, lane(st)), pyr_vfirst_kernel, dim3(ceil_div(W, 256), rows, n_frames), 256, 0, st,
+                                     d_frames, frame_bytes, W, Hh, Wp, word_ok, d));
+            MAVD_LAUNCHED();
+        }
+        for (int l = 1; l <= nh; ++l) {
+            const Level& L = H->lv[l];
+            HPassW hw;
+            memcpy(hw.w, L.xwt, sizeof(hw.w));
+            const dim3 g(ceil_div(ceil_div(L.w, 4), 128), L.h, n_frames);
+            MAVD_REQUIRE(L.h <= 65535, MAVD_ERR_UNSUPPORTED, "pyramid: grid too large");
+            const bool pdl = pdl_next(H, lane(st));
+            if (l == 1) MAVD_CUDA(launch_chained(pdl, pyr_hpass_kernel<1>, g, 128, 0, st, (const float*)L.tmp, (size_t)L.h * Wp, W, Wp,
+                                                 L.w, L.img, L.plane, L.pitch, hw));
+            else MAVD_CUDA(launch_chained(pdl, pyr_hpass_kernel<2>, g, 128, 0, st, (const float*)L.tmp, (size_t)L.h * Wp, W, Wp, L.w,
+                                          L.img, L.plane, L.pitch, hw));
+            MAVD_LAUNCHED();
+        }
+        if (lo + nh <= hi) {
+            PyrDesc d;
+            int rows = 0;
+            make_desc(lo + nh, hi, d, rows);
+            MAVD_REQUIRE(rows <= 65535, MAVD_ERR_UNSUPPORTED, "pyramid: grid too large");
+            // levels whose outputs are >= 8 source samples apart go through the shared-memory variant: one launch per run
+            // of consecutive levels of the same kind (normally two: the fine levels direct, the coarse tail staged)
+            for (int a0 = 0; a0 < d.n;) {
+                int a1 = a0, hx = 0;
+                while (a1 < d.n && d.lv[a1].staged == d.lv[a0].staged) { hx = max(hx, d.lv[a1].htiles_x); ++a1; }
+                const int r0 = d.lv[a0].row0, r1 = a1 < d.n ? d.lv[a1].row0 : rows;
+                MAVD_CUDA(launch_chained(pdl_next(H, lane(st)), d.lv[a0].staged ? pyr_hsecond_staged_kernel : pyr_hsecond_kernel,
+                                         dim3(hx, r1 - r0, n_frames), 256, 0, st, W, Wp, r0, d));
+                MAVD_LAUNCHED();
+                a0 = a1;
+            }
         }
         return MAVD_OK;
     };

@@ -532,3 +532,36 @@ def test_gaussian_windows_on_the_tma_iteration_kernel(winsize):
     epe = np.linalg.norm(a[0] - ref, axis=-1)
     assert epe.mean() < 1e-4 and epe.max() < 5e-3, (epe.mean(), epe.max())
     eng.close()
+
+
+@pytest.mark.parametrize('size', [(1920, 1080), (640, 480), (648, 488), (3840, 2160), (2048, 1024), (644, 484)])
+def test_pyramid_sweep_is_bit_identical(size):
+    """tuning.pyr_sweep: the exact power-of-two levels of a pyr_scale 0.5 pyramid computed by one sweep down the frame
+    (vertical passes) and the vectorised horizontal pass equal the generic kernels' images bit for bit, for every band
+    count, on noise frames (every REFLECT_101 border row / column matters); sizes whose coarse levels are not exact
+    decimations (1080 / 16, 484 / 8) mix both kinds of kernels."""
+    import torch
+    from mav_detection_b200 import engine
+    W, H = size
+    p = dict(engine.SAMPLE_PARAMS)
+    p['levels'] = 6
+    eng = engine.Engine(W, H, p, max_pairs=1)
+    rng = np.random.default_rng(W + H)
+    frames = torch.from_numpy(rng.integers(0, 256, size=(2, H, W), dtype=np.uint8)).to(eng.device)
+
+    def images(sweep):
+        eng.set_tuning(pyr_sweep=sweep)
+        flow = eng.farneback(frames, pair_stride=2)
+        torch.cuda.synchronize()
+        eng._keep_alive = (frames, flow)
+        return [eng.tap('img', lvl, j).cpu().numpy() for lvl in range(1, len(eng.levels)) for j in (0, 1)], \
+            flow.cpu().numpy()
+
+    ref, flow_ref = images(0)
+    assert len(ref) >= 4
+    for sweep in (1, 2, 5, 64):
+        got, flow = images(sweep)
+        for k, (a, b) in enumerate(zip(ref, got)):
+            assert np.array_equal(a, b), (sweep, 1 + k // 2, k % 2, float(np.abs(a - b).max()))
+        assert np.array_equal(flow, flow_ref), sweep
+    eng.close()
