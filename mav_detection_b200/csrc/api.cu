@@ -349,15 +349,16 @@ int mavd_create(const mavd_config* cfg, mavd_handle* out) {
                 }
                 {
                     // pyr_scale 0.5 with src = dst * 2^li: the level is an exact decimation (farneback.cu: HalfPyr)
-                    static const int kT[5] = {0, 4, 10, 20, 40}, kNB[5] = {0, 1, 3, 6, 12};
-                    bool half = li <= 4 && L.ksz + 1 == kT[std::min(li, 4)] && dst >= 1 && src == dst << li;
+                    static const int kT[7] = {0, 4, 10, 20, 40, 80, 160}, kNB[7] = {0, 1, 3, 6, 12, 24, 48};
+                    const int lc = std::min(li, 6);
+                    bool half = li <= 6 && L.ksz + 1 == kT[lc] && dst >= 1 && src == dst << lc;
                     for (int d = 0; half && d < dst; ++d) {
-                        half = base[d] == (d << li) - kNB[li];
+                        half = base[d] == (d << lc) - kNB[lc];
                         for (int j = 0; half && j < taps; ++j) half = tab[(size_t)d * taps + j] == tab[j];
                     }
-                    for (int j = kT[std::min(li, 4)]; half && j < taps; ++j) half = tab[j] == 0.f;
+                    for (int j = kT[lc]; half && j < taps; ++j) half = tab[j] == 0.f;
                     (axis == 0 ? L.x_half : L.y_half) = half;
-                    if (half) std::copy(tab.begin(), tab.begin() + kT[li], axis == 0 ? L.xwt : L.ywt);
+                    if (half) std::copy(tab.begin(), tab.begin() + kT[lc], axis == 0 ? L.xwt : L.ywt);
                 }
                 if (axis == 0) {
                     C_TRY(A.upload(&L.xbase, base)); C_TRY(A.upload(&L.xtab, tab));

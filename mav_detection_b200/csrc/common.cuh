@@ -135,7 +135,7 @@ struct Level {
     // exact power-of-two level (farneback.cu: HalfPyr): every output sample has the same ksz + 1 weights and its window
     // starts 2^k samples after its neighbour's; host copies of those weights for the kernels that exploit it
     bool x_half = false, y_half = false;
-    float xwt[40] = {}, ywt[40] = {};
+    float xwt[160] = {}, ywt[160] = {};
     // flow upsample tables (next-coarser level -> this level)
     int* fxi0 = nullptr; float* fxa = nullptr;  // [w]
     int* fyi0 = nullptr; float* fya = nullptr;  // [h]

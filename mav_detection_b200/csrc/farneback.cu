@@ -216,16 +216,20 @@ __global__ void __launch_bounds__(256) pyr_hsecond_staged_kernel(int W, int Wp, 
 //                constant, the weight a constant-bank operand of the FFMA); a finished output row is stored and its
 //                accumulator starts the next one.  11 instead of ~50 instructions per source sample.
 //   pyr_hpass    horizontal pass of level 1 or 2: thread = 4 adjacent outputs of one row, source span read as float4
+//   pyr_hpass1   horizontal pass of levels 3..6 (windows of 20..160 samples, 8..64 apart): thread = one output, its
+//                window streamed as float4 groups (the staged generic kernel spends 600 instructions per output on
+//                copying spans into shared memory)
 // Per output sample the products are accumulated in the same tap order with the same FMAs as in the generic kernels:
 // the images are bit-identical (test_pyramid_sweep_is_bit_identical).
 // ------------------------------------------------------------------------------------------------
-struct HalfPyr {    // level l = 1..4: stride, taps, -(window start of output 0), live outputs per source row
+struct HalfPyr {    // level l = 1..6: stride, taps, -(window start of output 0), live outputs per source row
     __host__ __device__ static constexpr int S(int l) { return 1 << l; }
-    __host__ __device__ static constexpr int T(int l) { return l == 1 ? 4 : l == 2 ? 10 : l == 3 ? 20 : 40; }
-    __host__ __device__ static constexpr int NB(int l) { return l == 1 ? 1 : l == 2 ? 3 : l == 3 ? 6 : 12; }
+    __host__ __device__ static constexpr int T(int l) { return l == 1 ? 4 : 10 << (l - 2); }        // 4 10 20 40 80 160
+    __host__ __device__ static constexpr int NB(int l) { return l == 1 ? 1 : 3 << (l - 2); }        // 1 3 6 12 24 48
     __host__ __device__ static constexpr int K(int l) { return (T(l) + S(l) - 1) / S(l); }
 };
-constexpr int VS_MAXLV = 4, VS_MAXT = 40;
+constexpr int VS_MAXLV = 4, VS_MAXT = 40;      // levels one sweep takes; their taps
+constexpr int HP_MAXLV = 6, HP_MAXT = 160;     // levels with a uniform horizontal pass; their taps
 struct VSweepDesc {
     float* tmp[VS_MAXLV];
     size_t tmp_stride[VS_MAXLV];   // floats per frame
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(192) pyr_vsweep_kernel(const uint8_t* __restri
     }
 }
 
-struct HPassW { float w[VS_MAXT]; };
+struct HPassW { float w[HP_MAXT]; };
 
 template <int LV>
 __global__ void __launch_bounds__(128) pyr_hpass_kernel(const float* __restrict__ tmp, size_t tmp_stride, int W, int Wp,
@@ -343,6 +347,36 @@ __global__ void __launch_bounds__(128) pyr_hpass_kernel(const float* __restrict_
         for (int k = 0; k < 4; ++k)
             if (x + k < wl) dst[k] = o[k];
     }
+}
+
+template <int LV>
+__global__ void __launch_bounds__(128) pyr_hpass1_kernel(const float* __restrict__ tmp, size_t tmp_stride, int W, int Wp,
+                                                        int wl, float* __restrict__ img, size_t img_stride, int pitch,
+                                                        const __grid_constant__ HPassW wts) {
+    pdl_entry();
+    constexpr int S = HalfPyr::S(LV), T = HalfPyr::T(LV), NB = HalfPyr::NB(LV);
+    constexpr int OFF = (4 - NB % 4) % 4;               // the window starts OFF floats into a 16-byte group
+    constexpr int NV = (OFF + T + 3) / 4;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= wl) return;
+    const float* row = tmp + (size_t)blockIdx.z * tmp_stride + (size_t)y * Wp;
+    const int a0 = S * x - NB - OFF;                    // a multiple of 4 (S is a multiple of 8)
+    float acc = 0.f;
+    if (a0 >= 0 && a0 + 4 * NV <= W) {
+        const float4* q = reinterpret_cast<const float4*>(row + a0);
+#pragma unroll
+        for (int g = 0; g < NV; ++g) {
+            const float4 t = __ldg(q + g);
+            const float u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * g + e >= OFF && 4 * g + e - OFF < T) acc = fmaf(wts.w[4 * g + e - OFF], u[e], acc);
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < T; ++j) acc = fmaf(wts.w[j], row[reflect101(a0 + OFF + j, W)], acc);
+    }
+    img[(size_t)blockIdx.z * img_stride + (size_t)y * pitch + x] = acc;
 }
 
 // level-0 image on its own (tests / taps only): 3x3 [1/4 1/2 1/4] blur of the u8 frame, REFLECT_101
@@ -1692,7 +1726,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         int nv = 0, nh = 0;
         if (H->tune.pyr_sweep != 0 && lo == 1 && word_ok) {
             while (nv < VS_MAXLV && 1 + nv <= hi && H->lv[1 + nv].y_half) ++nv;
-            while (nh < 2 && 1 + nh <= hi && H->lv[1 + nh].x_half) ++nh;
+            while (nh < HP_MAXLV && 1 + nh <= hi && H->lv[1 + nh].x_half) ++nh;
         }
         MAVD_REQUIRE(n_frames <= 65535, MAVD_ERR_UNSUPPORTED, "pyramid: grid too large");
         if (nv > 0) {
@@ -1738,13 +1772,19 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             const Level& L = H->lv[l];
             HPassW hw;
             memcpy(hw.w, L.xwt, sizeof(hw.w));
-            const dim3 g(ceil_div(ceil_div(L.w, 4), 128), L.h, n_frames);
+            const dim3 g(ceil_div(l <= 2 ? ceil_div(L.w, 4) : L.w, 128), L.h, n_frames);
             MAVD_REQUIRE(L.h <= 65535, MAVD_ERR_UNSUPPORTED, "pyramid: grid too large");
             const bool pdl = pdl_next(H, lane(st));
-            if (l == 1) MAVD_CUDA(launch_chained(pdl, pyr_hpass_kernel<1>, g, 128, 0, st, (const float*)L.tmp, (size_t)L.h * Wp, W, Wp,
-                                                 L.w, L.img, L.plane, L.pitch, hw));
-            else MAVD_CUDA(launch_chained(pdl, pyr_hpass_kernel<2>, g, 128, 0, st, (const float*)L.tmp, (size_t)L.h * Wp, W, Wp, L.w,
-                                          L.img, L.plane, L.pitch, hw));
+#define HP_ARGS g, 128, 0, st, (const float*)L.tmp, (size_t)L.h * Wp, W, Wp, L.w, L.img, L.plane, L.pitch, hw
+            switch (l) {
+                case 1: MAVD_CUDA(launch_chained(pdl, pyr_hpass_kernel<1>, HP_ARGS)); break;
+                case 2: MAVD_CUDA(launch_chained(pdl, pyr_hpass_kernel<2>, HP_ARGS)); break;
+                case 3: MAVD_CUDA(launch_chained(pdl, pyr_hpass1_kernel<3>, HP_ARGS)); break;
+                case 4: MAVD_CUDA(launch_chained(pdl, pyr_hpass1_kernel<4>, HP_ARGS)); break;
+                case 5: MAVD_CUDA(launch_chained(pdl, pyr_hpass1_kernel<5>, HP_ARGS)); break;
+                default: MAVD_CUDA(launch_chained(pdl, pyr_hpass1_kernel<6>, HP_ARGS)); break;
+            }
+#undef HP_ARGS
             MAVD_LAUNCHED();
         }
         if (lo + nh <= hi) {
