@@ -116,7 +116,9 @@ typedef struct mavd_tuning {
                              the ramp of the first wave leave the critical path (default 1) */
     int32_t pyr_sweep;    /* pyramid: exact power-of-two levels (pyr_scale 0.5) through the sweep / vectorised kernels;
                              0 = off, 1 = on with an automatic band count (default), n >= 2 = on with n bands */
-    int32_t reserved[2];
+    int32_t pyr_fuse_h1;  /* pyramid sweep: level 1's horizontal pass inside the sweep, its vertical sums never go
+                             through HBM (default 1) */
+    int32_t reserved[1];
 } mavd_tuning;
 
 /* Optional per-frame inputs of the detection stages.  All pointers are DEVICE pointers for the d_ entry points and

@@ -57,7 +57,7 @@ class Tuning(C.Structure):
                 ('last_fused', C.c_int32), ('mat_coord', C.c_int32), ('mat_r0_first', C.c_int32),
                 ('mat_txlog', C.c_int32), ('pyr_staged', C.c_int32), ('use_graph', C.c_int32),
                 ('polyexp_tma', C.c_int32), ('iter_small_tiles', C.c_int32), ('use_pdl', C.c_int32),
-                ('pyr_sweep', C.c_int32), ('reserved', C.c_int32 * 2)]
+                ('pyr_sweep', C.c_int32), ('pyr_fuse_h1', C.c_int32), ('reserved', C.c_int32 * 1)]
 
 
 class AuxInputs(C.Structure):

@@ -514,6 +514,7 @@ void mavd_default_tuning(mavd_tuning* t) {
     t->iter_small_tiles = 1;
     t->use_pdl = 1;
     t->pyr_sweep = 1;
+    t->pyr_fuse_h1 = 1;
 }
 
 int mavd_set_tuning(mavd_handle h, const mavd_tuning* t) {

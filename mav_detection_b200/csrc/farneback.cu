@@ -236,9 +236,16 @@ struct VSweepDesc {
     int h[VS_MAXLV];
     float w[VS_MAXLV][VS_MAXT];
     int band_rows;                 // output rows of level NLV per band (grid.y)
+    // H1: level 1's horizontal pass inside the sweep (its image instead of its tmp rows)
+    float* img1; size_t img1_stride; int pitch1;
+    float xw1[4];
 };
 
-template <int NLV>
+// H1: the thread also filters the column left and the column right of its four (REFLECT_101 at the frame edge) for
+// level 1, so that a finished level-1 row gets its horizontal pass (two outputs per thread, four taps) on the spot and
+// goes to the level image: the 4 bytes per full-resolution column of tmp never make their round trip through HBM
+// (270 MB written + 270 MB read per 65 frames of 1080p, what the sweep and pyr_hpass<1> were bound by).
+template <int NLV, bool H1>
 __global__ void __launch_bounds__(192) pyr_vsweep_kernel(const uint8_t* __restrict__ frames, size_t frame_stride, int W,
                                                         int H, int Wp, const __grid_constant__ VSweepDesc d) {
     pdl_entry();
@@ -254,20 +261,37 @@ __global__ void __launch_bounds__(192) pyr_vsweep_kernel(const uint8_t* __restri
         for (int k = 0; k < 3; ++k)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[l][k][c] = 0.f;
+    float e1[2][2] = {{0.f, 0.f}, {0.f, 0.f}};       // H1: level 1, [k][left / right neighbour column]
+    // neighbour columns: byte 3 of the word on the left, byte 0 of the word on the right; at the frame edge the
+    // reflected column is byte 1 / byte 2 of the thread's own word
+    const int offl = x >= 4 ? -4 : 0, offr = x + 4 < W ? 4 : 0;
+    const uint32_t sell = x >= 4 ? 0x7543u : 0x7541u, selr = x + 4 < W ? 0x7540u : 0x7542u;
     // the window of output D0 of level l starts at U * D0 - NB(l) >= U * (D0 - 1); that of output D1 - 1 ends before
     // U * (D1 + 2): steps q = D0 - 1 .. D1 + 1.  Outputs outside the band (their sums are incomplete) are not stored.
 #pragma unroll 1
     for (int q = D0 - 1; q <= D1 + 1; ++q) {
         const int r0 = q * U;
-        uint32_t wv[U];
+        uint32_t wv[U], wl[H1 ? U : 1], wr[H1 ? U : 1];
         if (r0 >= 0 && r0 + U <= H) {
             const uint8_t* p = src + (size_t)r0 * W;
 #pragma unroll
-            for (int i = 0; i < U; ++i) wv[i] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)i * W));
+            for (int i = 0; i < U; ++i) {
+                wv[i] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)i * W));
+                if (H1) {
+                    wl[i] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)i * W + offl));
+                    wr[i] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)i * W + offr));
+                }
+            }
         } else {
 #pragma unroll
-            for (int i = 0; i < U; ++i)
-                wv[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)reflect101(r0 + i, H) * W));
+            for (int i = 0; i < U; ++i) {
+                const uint8_t* p = src + (size_t)reflect101(r0 + i, H) * W;
+                wv[i] = __ldg(reinterpret_cast<const uint32_t*>(p));
+                if (H1) {
+                    wl[i] = __ldg(reinterpret_cast<const uint32_t*>(p + offl));
+                    wr[i] = __ldg(reinterpret_cast<const uint32_t*>(p + offr));
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < U; ++i) {
@@ -283,14 +307,36 @@ __global__ void __launch_bounds__(192) pyr_vsweep_kernel(const uint8_t* __restri
                         const float wt = d.w[l - 1][ph + k * S];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) acc[l - 1][k][c] = fmaf(wt, v[c], acc[l - 1][k][c]);
+                        if (H1 && l == 1) {
+                            e1[k][0] = fmaf(wt, byte_to_float(wl[i], sell), e1[k][0]);
+                            e1[k][1] = fmaf(wt, byte_to_float(wr[i], selr), e1[k][1]);
+                        }
                     }
                 if (ph == S - 1) {
                     // the oldest live output is complete: index = newest - (K - 1)
                     const int dn = (U / S) * q + (i + NB) / S - (K - 1);
                     if (dn >= D0 * (U / S) && dn < min(D1 * (U / S), d.h[l - 1])) {
-                        float* out = d.tmp[l - 1] + (size_t)blockIdx.z * d.tmp_stride[l - 1] + (size_t)dn * Wp + x;
-                        *reinterpret_cast<float4*>(out) = make_float4(acc[l - 1][K - 1][0], acc[l - 1][K - 1][1],
-                                                                     acc[l - 1][K - 1][2], acc[l - 1][K - 1][3]);
+                        if (H1 && l == 1) {
+                            // outputs x / 2 and x / 2 + 1 of the level-1 row: columns x - 1 .. x + 2 and x + 1 .. x + 4
+                            const float c6[6] = {e1[K - 1][0], acc[0][K - 1][0], acc[0][K - 1][1], acc[0][K - 1][2],
+                                                 acc[0][K - 1][3], e1[K - 1][1]};
+                            float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                o0 = fmaf(d.xw1[j], c6[j], o0);
+                                o1 = fmaf(d.xw1[j], c6[2 + j], o1);
+                            }
+                            float* out = d.img1 + (size_t)blockIdx.z * d.img1_stride + (size_t)dn * d.pitch1 + (x >> 1);
+                            *reinterpret_cast<float2*>(out) = make_float2(o0, o1);
+                        } else {
+                            float* out = d.tmp[l - 1] + (size_t)blockIdx.z * d.tmp_stride[l - 1] + (size_t)dn * Wp + x;
+                            *reinterpret_cast<float4*>(out) = make_float4(acc[l - 1][K - 1][0], acc[l - 1][K - 1][1],
+                                                                         acc[l - 1][K - 1][2], acc[l - 1][K - 1][3]);
+                        }
+                    }
+                    if (H1 && l == 1) {
+                        e1[1][0] = e1[0][0]; e1[1][1] = e1[0][1];
+                        e1[0][0] = e1[0][1] = 0.f;
                     }
 #pragma unroll
                     for (int k = 2; k >= 1; --k)
@@ -1724,6 +1770,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
         // exact power-of-two levels (leading levels of a pyr_scale 0.5 pyramid): one sweep down the frame does their
         // vertical passes, level 1 and 2 get the vectorised horizontal pass (tuning.pyr_sweep; HalfPyr above)
         int nv = 0, nh = 0;
+        bool h1_fused = false;
         if (H->tune.pyr_sweep != 0 && lo == 1 && word_ok) {
             while (nv < VS_MAXLV && 1 + nv <= hi && H->lv[1 + nv].y_half) ++nv;
             while (nh < HP_MAXLV && 1 + nh <= hi && H->lv[1 + nh].x_half) ++nh;
@@ -1751,12 +1798,25 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
             }
             const dim3 g(ceil_div(words, tb), nb, n_frames);
             const bool pdl = pdl_next(H, lane(st));
-            switch (nv) {
-                case 1: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<1>, g, tb, 0, st, d_frames, frame_bytes, W, Hh, Wp, vd)); break;
-                case 2: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<2>, g, tb, 0, st, d_frames, frame_bytes, W, Hh, Wp, vd)); break;
-                case 3: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<3>, g, tb, 0, st, d_frames, frame_bytes, W, Hh, Wp, vd)); break;
-                default: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<4>, g, tb, 0, st, d_frames, frame_bytes, W, Hh, Wp, vd)); break;
+            // level 1's horizontal pass inside the sweep (tuning.pyr_fuse_h1)
+            h1_fused = nh >= 1 && H->tune.pyr_fuse_h1 != 0;
+            if (h1_fused) {
+                const Level& L1 = H->lv[1];
+                vd.img1 = L1.img; vd.img1_stride = L1.plane; vd.pitch1 = L1.pitch;
+                memcpy(vd.xw1, L1.xwt, sizeof(vd.xw1));
             }
+#define VS_ARGS g, tb, 0, st, d_frames, frame_bytes, W, Hh, Wp, vd
+            switch (nv * 2 + (h1_fused ? 1 : 0)) {
+                case 2: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<1, false>, VS_ARGS)); break;
+                case 3: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<1, true>, VS_ARGS)); break;
+                case 4: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<2, false>, VS_ARGS)); break;
+                case 5: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<2, true>, VS_ARGS)); break;
+                case 6: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<3, false>, VS_ARGS)); break;
+                case 7: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<3, true>, VS_ARGS)); break;
+                case 8: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<4, false>, VS_ARGS)); break;
+                default: MAVD_CUDA(launch_chained(pdl, pyr_vsweep_kernel<4, true>, VS_ARGS)); break;
+            }
+#undef VS_ARGS
             MAVD_LAUNCHED();
         }
         if (lo + nv <= hi) {
@@ -1768,7 +1828,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
                                      d_frames, frame_bytes, W, Hh, Wp, word_ok, d));
             MAVD_LAUNCHED();
         }
-        for (int l = 1; l <= nh; ++l) {
+        for (int l = h1_fused ? 2 : 1; l <= nh; ++l) {
             const Level& L = H->lv[l];
             HPassW hw;
             memcpy(hw.w, L.xwt, sizeof(hw.w));

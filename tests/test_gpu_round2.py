@@ -549,8 +549,8 @@ def test_pyramid_sweep_is_bit_identical(size):
     rng = np.random.default_rng(W + H)
     frames = torch.from_numpy(rng.integers(0, 256, size=(2, H, W), dtype=np.uint8)).to(eng.device)
 
-    def images(sweep):
-        eng.set_tuning(pyr_sweep=sweep)
+    def images(sweep, fuse_h1=1):
+        eng.set_tuning(pyr_sweep=sweep, pyr_fuse_h1=fuse_h1)
         flow = eng.farneback(frames, pair_stride=2)
         torch.cuda.synchronize()
         eng._keep_alive = (frames, flow)
@@ -559,8 +559,8 @@ def test_pyramid_sweep_is_bit_identical(size):
 
     ref, flow_ref = images(0)
     assert len(ref) >= 4
-    for sweep in (1, 2, 5, 64):
-        got, flow = images(sweep)
+    for sweep, fuse_h1 in ((1, 1), (1, 0), (2, 1), (5, 0), (64, 1)):
+        got, flow = images(sweep, fuse_h1)
         for k, (a, b) in enumerate(zip(ref, got)):
             assert np.array_equal(a, b), (sweep, 1 + k // 2, k % 2, float(np.abs(a - b).max()))
         assert np.array_equal(flow, flow_ref), sweep
