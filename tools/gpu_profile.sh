@@ -32,7 +32,7 @@ ncu -i $OUT/prof_all_$TAG.ncu-rep --page raw --csv > $OUT/prof_all_$TAG.csv 2>/d
 python tools/ncu_summary.py raw $OUT/prof_all_$TAG.csv > $OUT/prof_all_$TAG.md 2>/dev/null
 rm -f $OUT/prof_all_$TAG.ncu-rep
 # source-level capture of the heaviest kernels: the LAST launch of each (finest level of the last step)
-for K in ${PROFILE_KERNELS:-iter_box_tma_kernel matrices_init polyexp_tma residual_kernel ccl_merge}; do
+for K in ${PROFILE_KERNELS:-iter_box_tma_kernel matrices_init polyexp_tma residual_kernel pyr_vsweep}; do
   CNT=$(python - <<PY
 import csv
 rows=[r for r in csv.reader(open('$OUT/launches_$TAG.csv', errors='replace')) if len(r)>5 and r[0].isdigit() and '$K' in r[4]]
