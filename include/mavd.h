@@ -96,7 +96,8 @@ typedef struct mavd_detect_params {
  * mavd_create with mavd_set_tuning while the handle is idle; tools/gpu_ab.sh A/Bs them through bench.py --tune. */
 typedef struct mavd_tuning {
     int32_t overlap;      /* 0 = every launch on the caller's stream, 1 = coarse levels on a side stream,
-                             2 = pyramid + coarse levels on the side stream (default) */
+                             2 = pyramid + coarse levels on the side stream, 3 = that and the residual stage's
+                             preparation (statistics reset, segmentation maxima, unit list) during FoE (default) */
     int32_t pair_group;   /* pairs interleaved per tile in the fused iteration's CTA order (default 4) */
     int32_t r1_staged;    /* fused iteration: second frame's expansion staged in shared memory by TMA (default 1) */
     int32_t iter_fuse;    /* not-last iterations: horizontal sums + solve in registers (default 1) */

@@ -500,7 +500,7 @@ int mavd_destroy(mavd_handle h) {
 void mavd_default_tuning(mavd_tuning* t) {
     if (!t) return;
     memset(t, 0, sizeof(*t));
-    t->overlap = 2;
+    t->overlap = 3;
     t->pair_group = 4;
     t->r1_staged = 1;
     t->iter_fuse = 1;
@@ -519,7 +519,7 @@ void mavd_default_tuning(mavd_tuning* t) {
 
 int mavd_set_tuning(mavd_handle h, const mavd_tuning* t) {
     MAVD_REQUIRE(h && t, MAVD_ERR_INVALID, "set_tuning: NULL argument");
-    MAVD_REQUIRE(t->overlap >= 0 && t->overlap <= 2 && t->pair_group >= 1 && t->mat_coord >= 0 && t->mat_coord <= 2 &&
+    MAVD_REQUIRE(t->overlap >= 0 && t->overlap <= 3 && t->pair_group >= 1 && t->mat_coord >= 0 && t->mat_coord <= 2 &&
                      t->mat_txlog >= 4 && t->mat_txlog <= 8 && t->iter_fuse >= 0 && t->iter_fuse <= 1,
                  MAVD_ERR_INVALID, "set_tuning: value out of range");
     DeviceGuard dg(h->cfg.device);
@@ -822,14 +822,31 @@ static const mavd_aux_inputs kNoAux = {nullptr, 0, nullptr, 0, nullptr};
 static int detect_run(mavd_handle h, const float* flow, int n, const mavd_detect_params& p, int n64, int n32,
                       const int32_t* d_samples, const mavd_aux_inputs& aux, uint8_t* d_total_out, uint8_t* fixed,
                       mavd_frame_record* d_records, cudaStream_t s) {
-    TRY(foe_run(h, flow, 0, n, h->d_imu, p, d_samples, h->d_foe, h->d_ninter, s));
     char* stats0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, stats);
-    // the residual kernel lists the 128-pixel units of the fixed mask that hold foreground; the labelling passes then
-    // visit only those (detection masks are almost empty)
-    TRY(ccl_list_reset(h, n, s));
+    // FoE estimation is one CTA per frame; what the residual kernel needs besides the FoE (zeroed statistics, the
+    // segmentation maxima, an empty unit list) does not depend on it and runs on the side stream meanwhile
+    const bool fork = h->s_aux != nullptr && h->tune.overlap >= 3 && !h->prof.on;
+    if (fork) {
+        MAVD_CUDA(cudaEventRecord(h->ev_fork, s));
+        MAVD_CUDA(cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
+        pdl_break(h, 1);
+        // the residual kernel lists the 128-pixel units of the fixed mask that hold foreground; the labelling passes
+        // then visit only those (detection masks are almost empty)
+        TRY(ccl_list_reset(h, n, h->s_aux, 1));
+        TRY(residual_prepare(h, n, aux.seg, aux.seg_stride, reinterpret_cast<mavd_frame_stats*>(stats0),
+                             sizeof(mavd_frame_record), h->s_aux, 1));
+        MAVD_CUDA(cudaEventRecord(h->ev_join, h->s_aux));
+    }
+    TRY(foe_run(h, flow, 0, n, h->d_imu, p, d_samples, h->d_foe, h->d_ninter, s));
+    if (fork) {
+        MAVD_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+        pdl_break(h, 0);
+    } else {
+        TRY(ccl_list_reset(h, n, s));
+    }
     TRY(residual_run(h, flow, 0, n, h->d_imu, p, h->d_foe, aux.sky, aux.sky_stride, aux.seg, aux.seg_stride, nullptr,
                      d_total_out, fixed, reinterpret_cast<mavd_frame_stats*>(stats0), sizeof(mavd_frame_record), n64 > 0,
-                     n32 > 0, s, true, aux.gt_flow));
+                     n32 > 0, s, true, aux.gt_flow, fork));
     int32_t* boxes0 = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, boxes));
     char* nl0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, n_labels);
     TRY(ccl_run(h, fixed, n, nullptr, boxes0, sizeof(mavd_frame_record) / sizeof(int32_t), MAVD_MAX_BOXES,

@@ -298,7 +298,11 @@ int residual_run(mavd_handle h, const void* d_flow, int flow_kind, int n, const 
                  const double* d_foe, const uint8_t* d_sky, int64_t sky_stride, const uint8_t* d_seg,
                  int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed, mavd_frame_stats* d_stats,
                  size_t stats_stride_bytes, int run_f64, int run_f32, cudaStream_t s, bool list_fixed_units = false,
-                 const float* d_gt_flow = nullptr);
+                 const float* d_gt_flow = nullptr, bool prepared = false);
+// the part of residual_run that does not depend on the flow or the FoE (lane: common.cuh pdl_next); a caller that ran
+// it passes prepared = true
+int residual_prepare(mavd_handle h, int n, const uint8_t* d_seg, int64_t seg_stride, mavd_frame_stats* d_stats,
+                     size_t stats_stride_bytes, cudaStream_t s, int lane);
 int phi_colormap_run(const void* d_phi, int is_f64, int64_t n, double max_value, uint8_t* d_gray_rgb, uint8_t* d_bgr,
                      cudaStream_t s);
 int mask_overlay_run(const uint8_t* d_frame, int channels, const uint8_t* d_mask, int64_t n, uint8_t* d_out,
@@ -308,7 +312,7 @@ int unpack_mask_run(const uint8_t* d_bits, int n, int64_t npx, uint8_t value, ui
 static inline int64_t packed_mask_bytes(int64_t npx) { return ((npx + 7) / 8 + 3) / 4 * 4; }
 // The labelling passes walk a list of occupied 128-pixel units of the mask.  residual_run(list_fixed_units) appends the
 // units of the fixed mask while it writes it (after ccl_list_reset), so that ccl_run(list_ready) never streams the mask.
-int ccl_list_reset(mavd_handle h, int n, cudaStream_t s);
+int ccl_list_reset(mavd_handle h, int n, cudaStream_t s, int lane = 0);
 int ccl_n_units(mavd_handle h);
 int* ccl_unit_marks(mavd_handle h);
 int* ccl_unit_list(mavd_handle h);

@@ -811,11 +811,32 @@ static int launch_residual(const ResidualArgs& A, const FastPrm& fp, int n, bool
 
 // flow_kind: 0 = float32 flow with the per-frame imu deciding between MODE 0 and MODE 1,
 //            1 = float32 flow, no derotation for any frame (MODE 1), 2 = float64 flow, no derotation (MODE 2)
+// What the residual kernel needs besides the flow and the FoE: zeroed statistics and the per-frame maximum of the
+// segmentation (get_simple_bounding_box's threshold).  Independent of both, so the batch call (api.cu: detect_run) runs
+// it on the side stream (lane 1) while the FoE estimation, 64 CTAs, has the GPU almost to itself.
+int residual_prepare(mavd_handle H, int n, const uint8_t* d_seg, int64_t seg_stride, mavd_frame_stats* d_stats,
+                     size_t stats_stride, cudaStream_t s, int lane) {
+    if (!d_stats) return MAVD_OK;
+    ProfScope ps(&H->prof, MAVD_PROF_RESIDUAL, s);
+    int* seg_max = reinterpret_cast<int*>(H->d_scan);  // scratch: n ints
+    MAVD_CUDA(launch_chained(pdl_next(H, lane), stats_init_kernel, ceil_div(n, 128), 128, 0, s, (char*)d_stats, stats_stride, n,
+                             d_seg ? seg_max : nullptr));
+    MAVD_LAUNCHED();
+    if (d_seg) {
+        dim3 g(32, n);
+        MAVD_CUDA(launch_chained(pdl_next(H, lane), seg_max_kernel, g, 256, 0, s, d_seg, seg_stride,
+                                 (int64_t)H->cfg.width * H->cfg.height, seg_max));
+        MAVD_LAUNCHED();
+    }
+    return MAVD_OK;
+}
+
 int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const mavd_imu* d_imu,
                  const mavd_detect_params& p, const double* d_foe, const uint8_t* d_sky, int64_t sky_stride,
                  const uint8_t* d_seg, int64_t seg_stride, void* d_phi, uint8_t* d_total, uint8_t* d_fixed,
                  mavd_frame_stats* d_stats, size_t stats_stride, int run_f64, int run_f32, cudaStream_t s,
-                 bool list_fixed_units, const float* d_gt_flow) {
+                 bool list_fixed_units, const float* d_gt_flow, bool prepared) {
+    if (!prepared) TRY_RC(residual_prepare(H, n, d_seg, seg_stride, d_stats, stats_stride, s, 0));
     ProfScope ps(&H->prof, MAVD_PROF_RESIDUAL, s);
     const int w = H->cfg.width, h = H->cfg.height;
     const int64_t npx = (int64_t)w * h;
@@ -825,16 +846,6 @@ int residual_run(mavd_handle H, const void* d_flow, int flow_kind, int n, const 
                       p.dyn_offset - p.dyn_base < -1e-2 && p.dyn_min_mag >= 0.0 && p.fixed_min_mag >= 0.0 &&
                       p.fixed_angle <= 170.0 && p.dyn_offset + p.dyn_base < 160.0 && p.dyn_gain < 1e6 &&
                       p.dyn_min_mag < 1e3 && p.fixed_min_mag < 1e3;
-    if (d_stats) {
-        MAVD_CUDA(launch_chained(pdl_next(H), stats_init_kernel, ceil_div(n, 128), 128, 0, s, (char*)d_stats, stats_stride, n,
-                                 d_seg ? seg_max : nullptr));
-        MAVD_LAUNCHED();
-        if (d_seg) {
-            dim3 g(32, n);
-            MAVD_CUDA(launch_chained(pdl_next(H), seg_max_kernel, g, 256, 0, s, d_seg, seg_stride, npx, seg_max));
-            MAVD_LAUNCHED();
-        }
-    }
     ResidualArgs A;
     A.flow = d_flow; A.imu = flow_kind == 0 ? d_imu : nullptr; A.foe = d_foe; A.xn = H->d_xn; A.yn = H->d_yn; A.w = w; A.h = h;
     A.prm = ResidualPrm{p.dyn_offset, p.dyn_base, p.dyn_gain, p.dyn_min_mag, p.fixed_min_mag, p.fixed_angle};
@@ -1789,10 +1800,10 @@ __global__ void __launch_bounds__(256) ccl_list_reset_kernel(int* __restrict__ p
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ints; i += stride) p[i] = 0;
 }
 
-int ccl_list_reset(mavd_handle H, int n, cudaStream_t s) {
+int ccl_list_reset(mavd_handle H, int n, cudaStream_t s, int lane) {
     const size_t n_ints = 4 + (size_t)n * ccl_n_units(H);
     const int blocks = (int)min((size_t)148 * 8, (n_ints + 255) / 256);
-    MAVD_CUDA(launch_chained(pdl_next(H), ccl_list_reset_kernel, blocks, 256, 0, s, ccl_count_ptr(H), n_ints));
+    MAVD_CUDA(launch_chained(pdl_next(H, lane), ccl_list_reset_kernel, blocks, 256, 0, s, ccl_count_ptr(H), n_ints));
     MAVD_LAUNCHED();
     return MAVD_OK;
 }

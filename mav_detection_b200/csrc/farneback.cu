@@ -9,7 +9,11 @@
 //
 // Kernels (algorithmic bytes per level pixel P):
 //   pyr_vfirst / pyr_hsecond / pyr_hsecond_staged
-//                             blur+resize from full-res u8 for all coarse levels, three launches
+//                             blur+resize from full-res u8 for all coarse levels, any pyr_scale (generic)
+//   pyr_vsweep / pyr_hpass / pyr_hpass1
+//                             the same for the exact power-of-two levels of a pyr_scale 0.5 pyramid: one sweep down the
+//                             frame does the vertical passes of levels 1..4 (each u8 row converted once) and level
+//                             1's horizontal pass; vectorised / streamed horizontal passes for the other levels
 //   polyexp_tma_kernel        separable polynomial expansion, tile staged by one TMA box  4P -> 20P (level 0: 1P -> 20P)
 //   polyexp_kernel            the same with per-thread loads (rows that are not 16-byte aligned)
 //   matrices_init_kernel      flow upsample (x 1/pyr_scale) fused with UpdateMatrices   (8P' +) 40P -> 20P
@@ -1997,7 +2001,7 @@ int farneback_run(mavd_handle H, const uint8_t* d_frames, int n_pairs, int pair_
     // matrices need the level-2 flow.  Stream order as seen by the caller is unchanged.
     const bool fork = H->n_levels >= 3 && H->s_aux != nullptr && H->tune.overlap != 0;
     const int top_level = H->n_levels - 1;
-    if (fork && H->tune.overlap == 2) {
+    if (fork && H->tune.overlap >= 2) {
         // the pyramid too goes to the side stream: level 0's expansion reads only the u8 frames
         MAVD_CUDA(cudaEventRecord(H->ev_fork, s));
         MAVD_CUDA(cudaStreamWaitEvent(H->s_aux, H->ev_fork, 0));
