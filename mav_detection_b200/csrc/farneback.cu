@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(256) pyr_hsecond_staged_kernel(int W, int Wp, 
 //   pyr_vsweep   vertical pass of levels 1..NLV in ONE sweep down the frame: thread = 4 adjacent columns (one 32-bit
 //                word per row, coalesced), each row is loaded and converted once and added to the <= 3 live output
 //                rows of every level (polyphase decimation: the tap index of (row, live output) is a compile-time
-//                constant, the weight a constant-bank operand of the FFMA); a finished output row is stored and its
-//                accumulator starts the next one.  11 instead of ~50 instructions per source sample.
+//                constant, the weight a uniform-register operand of the FFMA); a finished output row is stored and its
+//                accumulator starts the next one.  ~20 instead of ~50 instructions per source sample for three levels.
 //   pyr_hpass    horizontal pass of level 1 or 2: thread = 4 adjacent outputs of one row, source span read as float4
 //   pyr_hpass1   horizontal pass of levels 3..6 (windows of 20..160 samples, 8..64 apart): thread = one output, its
 //                window streamed as float4 groups (the staged generic kernel spends 600 instructions per output on
