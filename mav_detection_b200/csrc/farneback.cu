@@ -1463,6 +1463,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) iter_box_tma_kernel(con
                     u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w;
                 }
                 hsum(u, o[c]);
+                // the weighted filter keeps its half kernel and 20 inputs live: without this fence the compiler hoists
+                // the loads of all five planes above the first filter and spills 152 bytes per thread
+                if (GAUSS) asm volatile("" ::: "memory");
             }
             const int x = x0 + 4 * q4, y = y0 + r;
             if (y >= h || x >= w) continue;
