@@ -645,17 +645,20 @@ int mavd_farneback_tap(mavd_handle h, int32_t kind, int32_t level, int32_t index
 
 static int upload_imu(mavd_handle h, const mavd_imu* h_imu, int n, cudaStream_t s, int* n64, int* n32) {
     MAVD_REQUIRE(h_imu != nullptr, MAVD_ERR_INVALID, "imu array is NULL");
-    int a = 0, b = 0;
+    int a = 0, b = 0, rot = 0;
     for (int i = 0; i < n; ++i) {
         if (h_imu[i].derotate) {
             MAVD_REQUIRE(h_imu[i].dt != 0.0, MAVD_ERR_INVALID, "imu[%d].dt is zero", i);
             ++a;
+            // anything but an exact zero rotation (NaN included) takes the float64 derotation on the device
+            if (!(h_imu[i].ang[0] == 0.0 && h_imu[i].ang[1] == 0.0 && h_imu[i].ang[2] == 0.0)) ++rot;
         } else {
             ++b;
         }
     }
     if (n64) *n64 = a;
     if (n32) *n32 = b;
+    h->batch_rot = rot;
     // the caller's array is not retained: it is copied into the next pinned ring slot, and the asynchronous upload
     // reads that slot (a slot is rewritten only after the upload that used it has completed)
     const int k = h->imu_next;
@@ -755,7 +758,7 @@ int mavd_residual_masks(mavd_handle h, const float* d_flow, int32_t n, const mav
     int n64 = 0, n32 = 0;
     TRY(upload_imu(h, h_imu, n, (cudaStream_t)stream, &n64, &n32));
     return residual_run(h, d_flow, 0, n, h->d_imu, p, d_foe, d_sky, sky_stride, d_seg, seg_stride, d_phi, d_total, d_fixed,
-                        d_stats, sizeof(mavd_frame_stats), n64 > 0, n32 > 0, (cudaStream_t)stream);
+                        d_stats, sizeof(mavd_frame_stats), n64 > 0 ? (h->batch_rot > 0 ? 1 : 2) : 0, n32 > 0, (cudaStream_t)stream);
 }
 
 int mavd_ccl(mavd_handle h, const uint8_t* d_mask, int32_t n, int32_t* d_labels, int32_t* d_boxes, int32_t max_boxes,
@@ -845,8 +848,8 @@ static int detect_run(mavd_handle h, const float* flow, int n, const mavd_detect
         TRY(ccl_list_reset(h, n, s));
     }
     TRY(residual_run(h, flow, 0, n, h->d_imu, p, h->d_foe, aux.sky, aux.sky_stride, aux.seg, aux.seg_stride, nullptr,
-                     d_total_out, fixed, reinterpret_cast<mavd_frame_stats*>(stats0), sizeof(mavd_frame_record), n64 > 0,
-                     n32 > 0, s, true, aux.gt_flow, fork));
+                     d_total_out, fixed, reinterpret_cast<mavd_frame_stats*>(stats0), sizeof(mavd_frame_record),
+                     n64 > 0 ? (h->batch_rot > 0 ? 1 : 2) : 0, n32 > 0, s, true, aux.gt_flow, fork));
     int32_t* boxes0 = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, boxes));
     char* nl0 = reinterpret_cast<char*>(d_records) + offsetof(mavd_frame_record, n_labels);
     TRY(ccl_run(h, fixed, n, nullptr, boxes0, sizeof(mavd_frame_record) / sizeof(int32_t), MAVD_MAX_BOXES,
@@ -996,7 +999,7 @@ int mavd_detect_ex(mavd_handle h, const float* d_flow, int32_t n, const mavd_imu
     int n64 = 0, n32 = 0;
     TRY(upload_imu(h, h_imu, n, ss.s, &n64, &n32));
     uint8_t* fixed = d_fixed_out ? d_fixed_out : h->d_fixed;
-    return run_graphed(h, std::move(KeyBuilder()(int64_t(2))(d_flow)(int64_t(n))(p)(int64_t(n64))(int64_t(n32))(d_samples)(aux)
+    return run_graphed(h, std::move(KeyBuilder()(int64_t(2))(d_flow)(int64_t(n))(p)(int64_t(n64))(int64_t(h->batch_rot > 0))(int64_t(n32))(d_samples)(aux)
                                         (d_total_out)(fixed)(d_records).k),
                        ss.s, [&](cudaStream_t s) {
                            return detect_run(h, d_flow, n, p, n64, n32, d_samples, aux, d_total_out, fixed, d_records, s);
@@ -1029,7 +1032,7 @@ int mavd_process_ex(mavd_handle h, const uint8_t* d_frames, int32_t n_pairs, int
     int n64 = 0, n32 = 0;
     TRY(upload_imu(h, h_imu, n_pairs, ss.s, &n64, &n32));
     note_farneback_call(h, d_frames, n_pairs, pair_stride, flow);
-    return run_graphed(h, std::move(KeyBuilder()(int64_t(3))(d_frames)(int64_t(n_pairs))(int64_t(pair_stride))(p)(int64_t(n64))
+    return run_graphed(h, std::move(KeyBuilder()(int64_t(3))(d_frames)(int64_t(n_pairs))(int64_t(pair_stride))(p)(int64_t(n64))(int64_t(h->batch_rot > 0))
                                         (int64_t(n32))(d_samples)(aux)(flow)(d_total_out)(fixed)(d_records).k),
                        ss.s, [&](cudaStream_t s) {
                            TRY(farneback_run(h, d_frames, n_pairs, pair_stride, flow, s));

@@ -258,6 +258,7 @@ struct mavd_handle_s {
     cudaStream_t s_main = nullptr;    // work submitted on the legacy default stream runs here between two events
     cudaEvent_t ev_main_in = nullptr, ev_main_out = nullptr;
     bool force_generic_iter = false;  // tests: run the non-TMA iteration kernel
+    int batch_rot = 0;                // frames of the last uploaded imu array that derotate by a non-zero rotation
     // programmatic dependent launch (pdl_next / pdl_break below): may the next kernel on the caller's stream [0] /
     // the side stream [1] be chained to the kernel launched before it on that stream?
     bool pdl_ok[2] = {false, false};
