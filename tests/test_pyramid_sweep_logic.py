@@ -118,7 +118,8 @@ def test_sweep_gives_every_output_its_taps_once_in_order(H, nlv, band_rows):
 
 
 def _fma(a, b, c):
-    return F32(np.float64(a) * np.float64(b) + np.float64(c))      # one rounding: exact product of two float32 fits
+    # one rounding: the exact product of two float32 fits in a float64
+    return (np.asarray(a, dtype=np.float64) * np.asarray(b, dtype=np.float64) + np.asarray(c, dtype=np.float64)).astype(F32)
 
 
 def pyramid_by_kernels(img, nlv_v, levels):
@@ -162,12 +163,11 @@ def pyramid_by_kernels(img, nlv_v, levels):
     return out
 
 
-@pytest.mark.parametrize('size', [(64, 48), (96, 64)])
-def test_restated_kernels_match_the_oracle_pyramid(size):
+@pytest.mark.parametrize('size,levels', [((64, 48), 3), ((96, 64), 3), ((256, 128), 5), ((128, 64), 6)])
+def test_restated_kernels_match_the_oracle_pyramid(size, levels):
     W, H = size
     rng = np.random.default_rng(W * H)
     img = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
-    levels = 3
     got = pyramid_by_kernels(img, levels, levels)
     for l in range(1, levels + 1):
         ref = fb.pyramid_image(img, 0.5 ** l, W >> l, H >> l)
