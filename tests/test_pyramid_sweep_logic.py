@@ -118,7 +118,8 @@ def test_sweep_gives_every_output_its_taps_once_in_order(H, nlv, band_rows):
 
 
 def _fma(a, b, c):
-    # one rounding: the exact product of two float32 fits in a float64
+    # the exact product of two float32 fits in a float64; the float64 sum rounded to float32 differs from a true fma
+    # only in rare double-rounding ties (the comparison below is tolerance-based)
     return (np.asarray(a, dtype=np.float64) * np.asarray(b, dtype=np.float64) + np.asarray(c, dtype=np.float64)).astype(F32)
 
 
